@@ -1,0 +1,456 @@
+// Sliced bf16 GEMM for sm_100a: TMA -> shared memory (128B swizzle) -> tcgen05.mma
+// (accumulators in TMEM, double buffered) -> epilogue warps (tcgen05.ld) -> global.
+//
+// Replaces the cuBLAS calls behind F.linear on the sampled-subnet path
+// (AutoFormer/model/module/Linear_super.py:52-54, qkv_super.py:53-55) and their
+// autograd backward (dgrad / wgrad).  The sampled slice is carried by the TMA
+// descriptor extents over the FULL supernet tensors, so no sliced weight copy exists
+// and ragged K / N tails are zero-filled by the TMA unit.
+//
+// Persistent kernel: one CTA per SM, static round-robin tile schedule.
+//   warp 0      : TMA producer (one lane)
+//   warp 1      : tcgen05.mma issuer (one lane)
+//   warp 2      : TMEM allocator
+//   warps 4..11 : epilogue (two warps per TMEM lane quarter, alternating column chunks)
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace cb {
+
+namespace {
+
+constexpr int kBM = 128;          // UMMA M
+constexpr int kBK = 64;           // K block = one 128-byte swizzle row of bf16
+constexpr int kMaxStages = 8;
+constexpr int kNumThreads = 384;  // 12 warps
+constexpr int kEpiWarp0 = 4;
+constexpr int kNumEpiWarps = 8;
+constexpr uint32_t kTmemCols = 512;  // 2 accumulator stages x 256 columns
+
+struct GemmKernelParams {
+  int M, N, K, groups, BN;
+  int num_mt, num_nt, split_k, kb_total, kb_per_split, total_work;
+  int a_mn, b_mn, a_group_off, kpg;
+  int b_group_rows;
+  int num_stages;
+  uint32_t stage_bytes, a_bytes, tx_bytes;
+  int nb64;
+  int epi;
+  void* out;
+  int64_t ldo;
+  int out_row_mul, out_g_row, out_g_col;
+  void* aux;
+  int64_t ldaux;
+  const float* bias;
+  const float* resid;
+  int64_t ldr;
+  const float* row_scale;
+  int rows_per_scale;
+  float alpha;
+};
+
+struct WorkItem {
+  int mt, nt, g, kb0, kb1;
+};
+
+__device__ __forceinline__ WorkItem decode_work(const GemmKernelParams& p, int w) {
+  WorkItem it;
+  it.mt = w % p.num_mt;
+  int rest = w / p.num_mt;
+  it.nt = rest % p.num_nt;
+  rest /= p.num_nt;
+  it.g = rest % p.groups;
+  const int ks = rest / p.groups;
+  it.kb0 = ks * p.kb_per_split;
+  it.kb1 = min(p.kb_total, it.kb0 + p.kb_per_split);
+  return it;
+}
+
+template <int EPI>
+__device__ __forceinline__ void epilogue_chunk(const GemmKernelParams& p, const uint32_t (&raw)[32],
+                                               int row, int g, int col0, int ncols) {
+  // row: global output row (already < M); col0: first column of this chunk within the
+  // group; ncols: number of valid columns (1..32).
+  const int64_t orow = static_cast<int64_t>(row) * p.out_row_mul + static_cast<int64_t>(g) * p.out_g_row;
+  const int ocol = col0 + g * p.out_g_col;
+  float v[32];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(raw[i]);
+
+  if constexpr (EPI != CREAM_EPI_F32_ATOMIC && EPI != CREAM_EPI_BF16_DGELU) {
+    if (p.bias != nullptr) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i)
+        if (i < ncols) v[i] += __ldg(p.bias + ocol + i);
+    }
+  }
+
+  if constexpr (EPI == CREAM_EPI_BF16 || EPI == CREAM_EPI_BF16_GELU || EPI == CREAM_EPI_BF16_DGELU) {
+    __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(p.out) + orow * p.ldo + ocol;
+    if constexpr (EPI == CREAM_EPI_BF16_GELU) {
+      __nv_bfloat16* aux = reinterpret_cast<__nv_bfloat16*>(p.aux) + orow * p.ldaux + ocol;
+      if (ncols == 32) {
+        uint4* a4 = reinterpret_cast<uint4*>(aux);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          uint4 u;
+          u.x = pack_bf16x2(v[8 * q + 0], v[8 * q + 1]);
+          u.y = pack_bf16x2(v[8 * q + 2], v[8 * q + 3]);
+          u.z = pack_bf16x2(v[8 * q + 4], v[8 * q + 5]);
+          u.w = pack_bf16x2(v[8 * q + 6], v[8 * q + 7]);
+          a4[q] = u;
+        }
+      } else {
+        for (int i = 0; i < ncols; ++i) aux[i] = __float2bfloat16_rn(v[i]);
+      }
+      // GELU acts on the bf16-rounded pre-activation (what backward will see).
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] = gelu_f(__bfloat162float(__float2bfloat16_rn(v[i])));
+    }
+    if constexpr (EPI == CREAM_EPI_BF16_DGELU) {
+      const __nv_bfloat16* aux =
+          reinterpret_cast<const __nv_bfloat16*>(p.aux) + orow * p.ldaux + ocol;
+      if (ncols == 32) {
+        const uint4* a4 = reinterpret_cast<const uint4*>(aux);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const uint4 u = __ldg(a4 + q);
+          const float2 f0 = unpack_bf16x2(u.x), f1 = unpack_bf16x2(u.y);
+          const float2 f2 = unpack_bf16x2(u.z), f3 = unpack_bf16x2(u.w);
+          v[8 * q + 0] *= dgelu_f(f0.x);
+          v[8 * q + 1] *= dgelu_f(f0.y);
+          v[8 * q + 2] *= dgelu_f(f1.x);
+          v[8 * q + 3] *= dgelu_f(f1.y);
+          v[8 * q + 4] *= dgelu_f(f2.x);
+          v[8 * q + 5] *= dgelu_f(f2.y);
+          v[8 * q + 6] *= dgelu_f(f3.x);
+          v[8 * q + 7] *= dgelu_f(f3.y);
+        }
+      } else {
+        for (int i = 0; i < ncols; ++i) v[i] *= dgelu_f(__bfloat162float(aux[i]));
+      }
+    }
+    if (ncols == 32) {
+      uint4* o4 = reinterpret_cast<uint4*>(out);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        uint4 u;
+        u.x = pack_bf16x2(v[8 * q + 0], v[8 * q + 1]);
+        u.y = pack_bf16x2(v[8 * q + 2], v[8 * q + 3]);
+        u.z = pack_bf16x2(v[8 * q + 4], v[8 * q + 5]);
+        u.w = pack_bf16x2(v[8 * q + 6], v[8 * q + 7]);
+        o4[q] = u;
+      }
+    } else {
+      for (int i = 0; i < ncols; ++i) out[i] = __float2bfloat16_rn(v[i]);
+    }
+  } else if constexpr (EPI == CREAM_EPI_F32_RESID) {
+    float* out = reinterpret_cast<float*>(p.out) + orow * p.ldo + ocol;
+    const float* res = p.resid + orow * p.ldr + ocol;
+    const float s = (p.row_scale != nullptr) ? __ldg(p.row_scale + row / p.rows_per_scale) : 1.0f;
+    if (ncols == 32) {
+      const float4* r4 = reinterpret_cast<const float4*>(res);
+      float4* o4 = reinterpret_cast<float4*>(out);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const float4 r = __ldg(r4 + q);
+        float4 o;
+        o.x = fmaf(s, v[4 * q + 0], r.x);
+        o.y = fmaf(s, v[4 * q + 1], r.y);
+        o.z = fmaf(s, v[4 * q + 2], r.z);
+        o.w = fmaf(s, v[4 * q + 3], r.w);
+        o4[q] = o;
+      }
+    } else {
+      for (int i = 0; i < ncols; ++i) out[i] = fmaf(s, v[i], res[i]);
+    }
+  } else if constexpr (EPI == CREAM_EPI_F32) {
+    float* out = reinterpret_cast<float*>(p.out) + orow * p.ldo + ocol;
+    if (ncols == 32) {
+      float4* o4 = reinterpret_cast<float4*>(out);
+#pragma unroll
+      for (int q = 0; q < 8; ++q)
+        o4[q] = make_float4(v[4 * q + 0], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+    } else {
+      for (int i = 0; i < ncols; ++i) out[i] = v[i];
+    }
+  } else {  // CREAM_EPI_F32_ATOMIC
+    float* out = reinterpret_cast<float*>(p.out) + orow * p.ldo + ocol;
+#pragma unroll
+    for (int i = 0; i < 32; ++i)
+      if (i < ncols) atomicAdd(out + i, p.alpha * v[i]);
+  }
+}
+
+template <int EPI>
+__global__ void __launch_bounds__(kNumThreads, 1)
+gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a,
+                 const __grid_constant__ CUtensorMap tmap_b, const GemmKernelParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>(
+      (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + p.num_stages * p.stage_bytes);
+  uint64_t* empty_bar = full_bar + kMaxStages;
+  uint64_t* tmem_full = empty_bar + kMaxStages;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmap_a);
+    prefetch_tmap(&tmap_b);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < p.num_stages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tmem_full[a], 1);
+      mbar_init(&tmem_empty[a], kNumEpiWarps);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) tmem_alloc<kTmemCols>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0 && lane == 0) {
+    // ===================== TMA producer =====================
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int w = blockIdx.x; w < p.total_work; w += gridDim.x) {
+      const WorkItem it = decode_work(p, w);
+      const int m0 = it.mt * kBM, n0 = it.nt * p.BN;
+      for (int kb = it.kb0; kb < it.kb1; ++kb) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        uint8_t* sa = smem + stage * p.stage_bytes;
+        uint8_t* sb = sa + p.a_bytes;
+        mbar_arrive_expect_tx(&full_bar[stage], p.tx_bytes);
+        if (!p.a_mn) {
+          tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * kBK, m0);
+        } else {
+          const int c = it.g * p.a_group_off + m0;
+          tma_load_2d(sa, &tmap_a, &full_bar[stage], c, kb * kBK);
+          tma_load_2d(sa + 8192, &tmap_a, &full_bar[stage], c + 64, kb * kBK);
+        }
+        if (!p.b_mn) {
+          tma_load_3d(sb, &tmap_b, &full_bar[stage], kb * kBK, n0, it.g);
+        } else {
+          const int krow = (kb / p.kpg) * p.b_group_rows + (kb % p.kpg) * kBK;
+          for (int c = 0; c < p.nb64; ++c)
+            tma_load_2d(sb + c * 8192, &tmap_b, &full_bar[stage], n0 + c * 64, krow);
+        }
+        if (++stage == p.num_stages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ===================== MMA issuer =====================
+    const uint32_t idesc = umma_idesc_bf16(kBM, p.BN, p.a_mn, p.b_mn);
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int w = blockIdx.x; w < p.total_work; w += gridDim.x) {
+      const WorkItem it = decode_work(p, w);
+      mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * 256;
+      for (int kb = it.kb0; kb < it.kb1; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(smem + stage * p.stage_bytes);
+        const uint32_t sb = sa + p.a_bytes;
+#pragma unroll
+        for (int k = 0; k < kBK / 16; ++k) {
+          // K-major: advance 32 bytes inside the 128B swizzle row; SBO = 8 rows * 128B.
+          // MN-major: advance 16 K-rows (2048B); LBO = next 64-wide MN chunk (8192B).
+          const uint64_t adesc = p.a_mn ? umma_smem_desc_sw128(sa + k * 2048, 8192, 1024)
+                                        : umma_smem_desc_sw128(sa + k * 32, 16, 1024);
+          const uint64_t bdesc = p.b_mn ? umma_smem_desc_sw128(sb + k * 2048, 8192, 1024)
+                                        : umma_smem_desc_sw128(sb + k * 32, 16, 1024);
+          umma_ss(d_tmem, adesc, bdesc, idesc, (kb > it.kb0 || k > 0) ? 1u : 0u);
+        }
+        umma_commit(&empty_bar[stage]);
+        if (++stage == p.num_stages) { stage = 0; phase ^= 1; }
+      }
+      umma_commit(&tmem_full[acc]);
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  } else if (warp >= kEpiWarp0) {
+    // ===================== epilogue =====================
+    const int ew = warp - kEpiWarp0;       // 0..7
+    const int quarter = warp & 3;          // TMEM lane quarter this warp may access
+    const int half = ew >> 2;              // which alternating column chunks
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int w = blockIdx.x; w < p.total_work; w += gridDim.x) {
+      const WorkItem it = decode_work(p, w);
+      const int m0 = it.mt * kBM, n0 = it.nt * p.BN;
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+      const int row = m0 + quarter * 32 + lane;
+      const int tile_cols = min(p.BN, p.N - n0);
+      const int nchunks = (tile_cols + 31) >> 5;
+      for (int c = half; c < nchunks; c += 2) {
+        uint32_t raw[32];
+        const uint32_t taddr = tmem_base + acc * 256 + c * 32 + (static_cast<uint32_t>(quarter * 32) << 16);
+        tmem_ld32(taddr, raw);
+        tmem_ld_wait();
+        if (row < p.M) {
+          const int ncols = min(32, tile_cols - c * 32);
+          epilogue_chunk<EPI>(p, raw, row, it.g, n0 + c * 32, ncols);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc<kTmemCols>(tmem_base);
+  }
+}
+
+template <int EPI>
+int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmKernelParams& p,
+                size_t smem_bytes, int grid, cudaStream_t stream) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    CB_CUDA_OK(cudaFuncSetAttribute(gemm_bf16_kernel<EPI>,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set = true;
+  }
+  gemm_bf16_kernel<EPI><<<grid, kNumThreads, smem_bytes, stream>>>(ta, tb, p);
+  return check_last("gemm_bf16_kernel launch");
+}
+
+}  // namespace
+
+}  // namespace cb
+
+extern "C" int cream_gemm_bf16(const cream_gemm_desc* d, void* stream_) {
+  using namespace cb;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  CB_REQUIRE(d != nullptr, "desc is null");
+  CB_REQUIRE(d->M > 0 && d->N > 0 && d->K > 0 && d->groups >= 1, "empty GEMM");
+  CB_REQUIRE(d->a != nullptr && d->b != nullptr && d->out != nullptr, "null operand");
+  CB_REQUIRE(d->lda % 8 == 0 && d->ldb % 8 == 0, "bf16 leading dims must be multiples of 8");
+  CB_REQUIRE((reinterpret_cast<uintptr_t>(d->a) & 15) == 0 &&
+                 (reinterpret_cast<uintptr_t>(d->b) & 15) == 0,
+             "operands must be 16-byte aligned");
+  CB_REQUIRE(d->epi >= 0 && d->epi <= CREAM_EPI_F32, "bad epilogue");
+  const bool out_bf16 = d->epi == CREAM_EPI_BF16 || d->epi == CREAM_EPI_BF16_GELU ||
+                        d->epi == CREAM_EPI_BF16_DGELU;
+  if (out_bf16) {
+    CB_REQUIRE(d->ldo % 8 == 0 && (d->out_g_col % 8) == 0, "bf16 out pitch/offset % 8");
+  } else {
+    CB_REQUIRE(d->ldo % 4 == 0 && (d->out_g_col % 4) == 0, "fp32 out pitch/offset % 4");
+  }
+  if (d->epi == CREAM_EPI_BF16_GELU || d->epi == CREAM_EPI_BF16_DGELU)
+    CB_REQUIRE(d->aux != nullptr && d->ldaux % 8 == 0, "aux required");
+  if (d->epi == CREAM_EPI_F32_RESID) CB_REQUIRE(d->resid != nullptr && d->ldr % 4 == 0, "resid");
+
+  GemmKernelParams p{};
+  p.M = d->M; p.N = d->N; p.K = d->K; p.groups = d->groups;
+  const int nt = ceil_div(d->N, 256);
+  p.BN = std::min(256, round_up(ceil_div(d->N, nt), 16));
+  p.num_nt = ceil_div(d->N, p.BN);
+  p.num_mt = ceil_div(d->M, kBM);
+  p.a_mn = d->a_mn ? 1 : 0;
+  p.b_mn = d->b_mn ? 1 : 0;
+  p.a_group_off = d->a_group_off;
+  const int k_groups = std::max(1, d->k_groups);
+  if (k_groups > 1) {
+    CB_REQUIRE(p.b_mn == 1 && d->k_group_len % kBK == 0 && d->k_group_len * k_groups == d->K,
+               "k-groups need MN-major B and 64-multiple group length");
+    p.kpg = d->k_group_len / kBK;
+  } else {
+    p.kpg = 1 << 30;
+  }
+  p.b_group_rows = static_cast<int>(d->b_group_rows);
+  p.kb_total = ceil_div(d->K, kBK);
+  const int tiles = p.num_mt * p.num_nt * p.groups;
+  int split = 1;
+  if (d->epi == CREAM_EPI_F32_ATOMIC) {
+    split = d->split_k > 0 ? d->split_k : std::max(1, kNumSMs / tiles);
+    split = std::min(split, p.kb_total);
+  }
+  p.kb_per_split = ceil_div(p.kb_total, split);
+  p.split_k = ceil_div(p.kb_total, p.kb_per_split);
+  p.total_work = tiles * p.split_k;
+  p.nb64 = ceil_div(p.BN, 64);
+  p.a_bytes = kBM * kBK * 2;
+  p.stage_bytes = p.a_bytes + p.nb64 * 8192;
+  p.tx_bytes = p.a_bytes + (p.b_mn ? p.nb64 * 8192 : p.BN * kBK * 2);
+  const size_t tail_bytes = 1024;  // barriers + tmem slot
+  p.num_stages = std::min<int>(kMaxStages, (227 * 1024 - 1024 - tail_bytes) / p.stage_bytes);
+  CB_REQUIRE(p.num_stages >= 2, "not enough shared memory for 2 stages");
+  const size_t smem_bytes = 1024 + static_cast<size_t>(p.num_stages) * p.stage_bytes + tail_bytes;
+  p.epi = d->epi;
+  p.out = d->out; p.ldo = d->ldo;
+  p.out_row_mul = d->out_row_mul > 0 ? d->out_row_mul : 1;
+  p.out_g_row = d->out_g_row; p.out_g_col = d->out_g_col;
+  p.aux = d->aux; p.ldaux = d->ldaux;
+  p.bias = d->bias; p.resid = d->resid; p.ldr = d->ldr;
+  p.row_scale = d->row_scale; p.rows_per_scale = d->rows_per_scale > 0 ? d->rows_per_scale : 1;
+  p.alpha = d->alpha == 0.0f ? 1.0f : d->alpha;
+
+  // ---- tensor maps -----------------------------------------------------------
+  const CUtensorMap *ta, *tb;
+  if (!p.a_mn) {
+    const uint64_t dims[2] = {static_cast<uint64_t>(d->K), static_cast<uint64_t>(d->M)};
+    const uint64_t strides[2] = {1, static_cast<uint64_t>(d->lda)};
+    const uint32_t box[2] = {kBK, kBM};
+    ta = get_tensor_map(d->a, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, dims, strides, box,
+                        CU_TENSOR_MAP_SWIZZLE_128B);
+  } else {
+    const uint64_t cols = static_cast<uint64_t>(p.groups - 1) * d->a_group_off + d->M;
+    const uint64_t dims[2] = {cols, static_cast<uint64_t>(d->K)};
+    const uint64_t strides[2] = {1, static_cast<uint64_t>(d->lda)};
+    const uint32_t box[2] = {64, kBK};
+    ta = get_tensor_map(d->a, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, dims, strides, box,
+                        CU_TENSOR_MAP_SWIZZLE_128B);
+  }
+  if (!p.b_mn) {
+    const uint64_t dims[3] = {static_cast<uint64_t>(d->K), static_cast<uint64_t>(d->N),
+                              static_cast<uint64_t>(p.groups)};
+    const uint64_t gstride = p.groups > 1 ? static_cast<uint64_t>(d->b_group_rows) * d->ldb
+                                          : static_cast<uint64_t>(d->N) * d->ldb;
+    const uint64_t strides[3] = {1, static_cast<uint64_t>(d->ldb), gstride};
+    const uint32_t box[3] = {kBK, static_cast<uint32_t>(p.BN), 1};
+    tb = get_tensor_map(d->b, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, dims, strides, box,
+                        CU_TENSOR_MAP_SWIZZLE_128B);
+  } else {
+    const uint64_t krows = k_groups > 1
+                               ? static_cast<uint64_t>(k_groups - 1) * d->b_group_rows + d->k_group_len
+                               : static_cast<uint64_t>(d->K);
+    const uint64_t dims[2] = {static_cast<uint64_t>(d->N), krows};
+    const uint64_t strides[2] = {1, static_cast<uint64_t>(d->ldb)};
+    const uint32_t box[2] = {64, kBK};
+    tb = get_tensor_map(d->b, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, dims, strides, box,
+                        CU_TENSOR_MAP_SWIZZLE_128B);
+  }
+  if (ta == nullptr || tb == nullptr) return CREAM_ERR_CUDA;
+
+  const int grid = std::min(p.total_work, kNumSMs);
+  switch (d->epi) {
+    case CREAM_EPI_BF16: return launch_gemm<CREAM_EPI_BF16>(*ta, *tb, p, smem_bytes, grid, stream);
+    case CREAM_EPI_BF16_GELU: return launch_gemm<CREAM_EPI_BF16_GELU>(*ta, *tb, p, smem_bytes, grid, stream);
+    case CREAM_EPI_F32_RESID: return launch_gemm<CREAM_EPI_F32_RESID>(*ta, *tb, p, smem_bytes, grid, stream);
+    case CREAM_EPI_BF16_DGELU: return launch_gemm<CREAM_EPI_BF16_DGELU>(*ta, *tb, p, smem_bytes, grid, stream);
+    case CREAM_EPI_F32_ATOMIC: return launch_gemm<CREAM_EPI_F32_ATOMIC>(*ta, *tb, p, smem_bytes, grid, stream);
+    default: return launch_gemm<CREAM_EPI_F32>(*ta, *tb, p, smem_bytes, grid, stream);
+  }
+}
