@@ -1,0 +1,151 @@
+"""The oracle (oracle/) against fixtures produced by the UNMODIFIED reference
+(tests/golden/make_golden.py).  CPU only; this is what pins the oracle."""
+import ctypes
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import rel_index, vit_oracle as vo
+from tests.helpers import check_summary, rand
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+@pytest.fixture(scope="module")
+def tables(golden_dir):
+    return np.load(golden_dir / "index_tables.npz")
+
+
+@pytest.mark.parametrize("ratio", [1.9, 1.0, 2.5, 3.3])
+def test_piecewise_index_bit_exact(tables, ratio):
+    xs = tables["pw_x"]
+    got = rel_index.piecewise_index(xs, 1 * ratio, 2 * ratio, 8 * ratio)
+    np.testing.assert_array_equal(got, tables[f"pw_int_{ratio}"])
+    xf = np.arange(0, 60, dtype=np.float32)
+    np.testing.assert_array_equal(rel_index.piecewise_index(xf, 1 * ratio, 2 * ratio, 8 * ratio),
+                                  tables[f"pw_float_{ratio}"])
+
+
+def test_piecewise_survey_known_answers():
+    # ratio 1.9 on [-13, 13]
+    got = rel_index.piecewise_index(np.arange(-13, 14), 1.9, 3.8, 15.2)
+    want = [-3] * 10 + [-2, -2, -1, 0, 1, 2, 2] + [3] * 10
+    assert got.tolist() == want
+
+
+METHODS = {"euc": rel_index.EUCLIDEAN, "quant": rel_index.QUANT, "product": rel_index.PRODUCT,
+           "rows": rel_index.CROSS_ROWS, "cols": rel_index.CROSS_COLS}
+GRIDS = [(14, 14, 1, 1.9), (7, 7, 0, 1.9), (5, 9, 2, 1.9), (14, 14, 1, 3.3), (24, 24, 1, 1.9)]
+
+
+@pytest.mark.parametrize("mname", list(METHODS))
+@pytest.mark.parametrize("h,w,skip,ratio", GRIDS)
+def test_irpe_bucket_ids_bit_exact(tables, mname, h, w, skip, ratio):
+    ids, nb = rel_index.irpe_bucket_ids(METHODS[mname], h, w, skip, 1 * ratio, 2 * ratio, 8 * ratio)
+    key = f"{mname}_{h}_{w}_{skip}_{ratio}"
+    assert nb == int(tables["nb_" + key])
+    np.testing.assert_array_equal(ids, tables["ids_" + key])
+
+
+def test_irpe_product_survey_known_answers():
+    ids, nb = rel_index.irpe_bucket_ids(rel_index.PRODUCT, 14, 14, 1, 1.9, 3.8, 15.2)
+    assert nb == 50 and ids.min() == 0 and ids.max() == 49 and len(np.unique(ids)) == 50
+    assert ids[1, 1:16].tolist() == [24, 23, 22, 22, 21, 21, 21, 21, 21, 21, 21, 21, 21, 21, 17]
+    assert (ids[0] == 49).all() and (ids[:, 0] == 49).all()
+
+
+@pytest.mark.parametrize("grid", [14, 4, 7])
+def test_autoformer_rel_index_bit_exact(tables, grid):
+    iv, ih = rel_index.autoformer_rel_index(grid, 14)
+    np.testing.assert_array_equal(iv, tables[f"af_idx_v_{grid}"])
+    np.testing.assert_array_equal(ih, tables[f"af_idx_h_{grid}"])
+    vals = set(np.unique(iv)) | set(np.unique(ih))
+    assert 1 not in vals and 29 not in vals
+
+
+def test_rpe_index_matches_reference_op(golden_dir):
+    g = np.load(golden_dir / "rpe_index.npz")
+    B, H, L, nb = 4, 3, 50, 50
+    x = rand((B, H, L, nb), 5).numpy()
+    idx = np.random.default_rng(6).integers(0, nb, (L, L)).astype(np.int32)
+    gy = rand((B, H, L, L), 8).numpy()
+    np.testing.assert_array_equal(rel_index.rpe_index_fwd(x, idx), g["y"])
+    np.testing.assert_allclose(rel_index.rpe_index_bwd(gy, idx, nb), g["gx"], rtol=0, atol=1e-5)
+    # plain-C restatement
+    from oracle.build_ref import build_c_oracle
+    lib = ctypes.CDLL(str(build_c_oracle()))
+    y = np.empty((B, H, L, L), np.float32)
+    P = ctypes.c_void_p
+    lib.oracle_rpe_index_fwd_f32(P(x.ctypes.data), P(idx.ctypes.data), P(y.ctypes.data), B, H, L, L, nb)
+    np.testing.assert_array_equal(y, g["y"])
+    gx = np.zeros((B, H, L, nb), np.float32)
+    lib.oracle_rpe_index_bwd_f32(P(gx.ctypes.data), P(gy.ctypes.data), P(idx.ctypes.data), B, H, L, L, nb)
+    np.testing.assert_allclose(gx, g["gx"], rtol=0, atol=1e-5)
+
+
+# ------------------------------------------------------------------------------------------
+sys.path.insert(0, str(ROOT / "tests" / "golden"))
+from make_golden import IRPE_CASES, MICRO_SPECS  # noqa: E402  (specs only; no reference import)
+
+
+@pytest.mark.parametrize("name", list(MICRO_SPECS))
+def test_supernet_oracle_matches_reference(golden_dir, name):
+    g = np.load(golden_dir / "supernet_micro.npz")
+    spec, batch, configs = MICRO_SPECS[name]
+    images = rand((batch, 3, spec.img_size, spec.img_size), seed=11)
+    targets = torch.from_numpy(np.random.default_rng(13).integers(0, spec.num_classes, batch))
+    for ci, cfg in enumerate(configs):
+        sd = {k: v.clone().requires_grad_(True) for k, v in vo.init_params(spec, seed=7).items()}
+        logits = vo.supernet_forward(sd, cfg, images, spec)
+        loss = torch.nn.functional.cross_entropy(logits, targets)
+        loss.backward()
+        key = f"{name}_c{ci}"
+        np.testing.assert_allclose(logits.detach().numpy(), g[key + "_logits"], rtol=2e-4, atol=2e-5)
+        assert abs(loss.item() - float(g[key + "_loss"])) < 1e-5
+        assert vo.sampled_param_count(cfg, spec) == int(g[key + "_numel"])
+        none = set(g[key + "_none"].tolist())
+        for pn, p in sd.items():
+            if pn in none:
+                # reference: parameters of identity layers get no grad at all
+                assert p.grad is None or float(p.grad.abs().sum()) == 0.0, pn
+                assert int(pn.split(".")[1]) >= cfg["layer_num"]
+            else:
+                check_summary(g, f"{key}_grad_{pn}", p.grad, 2e-4, what=f"{key} grad {pn}")
+
+
+def _irpe_params(name):
+    """Recreate the seeded parameters make_golden gave the reference RPEAttention."""
+    rpe_on, mode, shared, method, C, heads, grid = IRPE_CASES[name]
+    g = np.load(ROOT / "tests" / "golden" / "irpe_attention.npz")
+    shapes = {k[len(name) + 7:]: tuple(int(v) for v in g[k]) for k in g.files if k.startswith(name + "_shape_")}
+    return shapes
+
+
+@pytest.mark.parametrize("name", list(IRPE_CASES))
+def test_irpe_attention_oracle_matches_reference(golden_dir, name):
+    g = np.load(golden_dir / "irpe_attention.npz")
+    rpe_on, mode, shared, method, C, heads, grid = IRPE_CASES[name]
+    mid = {"product": rel_index.PRODUCT, "euc": rel_index.EUCLIDEAN, "quant": rel_index.QUANT}[method]
+    ids, nb = rel_index.irpe_bucket_ids(mid, grid, grid, 1, 1.9, 3.8, 15.2)
+    N, B = grid * grid + 1, 2
+    # parameter order of RPEAttention.named_parameters(): qkv.weight, qkv.bias, proj.weight,
+    # proj.bias, then rpe_q / rpe_k / rpe_v lookup tables in attribute order
+    shapes = _irpe_params(name)
+    params, seed = {}, 100
+    for pn, shape in shapes.items():
+        seed += 1
+        params[pn] = rand(shape, seed, 0.3 if "lookup" in pn else 0.08).requires_grad_(True)
+    tab = lambda w: next((v for k, v in params.items() if k.startswith(f"rpe_{w}.")), None)
+    x = rand((B, N, C), 99).requires_grad_(True)
+    gy = rand((B, N, C), 98)
+    y = vo.rpe_attention(x, params["qkv.weight"], params["qkv.bias"], params["proj.weight"], params["proj.bias"],
+                         heads, ids, rpe_q=tab("q"), rpe_k=tab("k"), rpe_v=tab("v"),
+                         mode="bias" if mode == "bias" else "contextual")
+    y.backward(gy)
+    check_summary(g, f"{name}_y", y, 1e-5)
+    check_summary(g, f"{name}_gx", x.grad, 1e-4)
+    for pn, p in params.items():
+        check_summary(g, f"{name}_grad_{pn}", p.grad, 1e-4, what=f"{name} grad {pn}")
