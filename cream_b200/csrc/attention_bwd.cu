@@ -1,0 +1,567 @@
+// Fused attention backward with relative-position terms, sm_100a (tcgen05 + TMEM + TMA).
+//
+// Adjoint of attention_fwd.cu (autograd of AutoFormer/model/module/multihead_super.py:135-154
+// and iRPE/DeiT-with-iRPE/rpe_vision_transformer.py:73-92).  Two kernels:
+//
+//  bwd_rows (CTA = query tile x head x batch, one thread per query row i):
+//      recompute T = scale*(Q K^T + R-gather) and P = exp(T - lse);
+//      dP = dO V^T + gather(dO TV^T);  dT = P o (dP - delta_i),  delta_i = dO_i . O_i;
+//      thread-local bucket sums  PB[i,b] = sum_j P[i,j][idx_v=b],  dR[i,b] = sum_j dT[i,j][idx_k=b];
+//      dQ = scale * [dT | dR] . [K ; TK]   (tcgen05, A operand from TMEM);
+//      [P | PB] and [dT | dR] (bf16) go to a workspace for the column-form products.
+//  bwd_cols (CTA = head x batch):
+//      [dV ; dTV] = [P | PB]^T dO        [dK ; dTK] = scale * [dT | dR]^T Q
+//      (MN-major A operands streamed from the workspace by TMA; table gradients are
+//      accumulated across (batch, head) with fp32 atomics on 64x64 tiles).
+//
+// Round-1 note: the workspace round trip (2 x B*H*N*(Npad+64) bf16) costs about 3x the
+// algorithmic bytes of the fused ideal; fusing bwd_cols into bwd_rows is the next step.
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace cb {
+namespace {
+
+constexpr int kD = 64;
+constexpr int kNB = 64;
+constexpr int kRowsThreads = 160;
+constexpr int kStride = 65;  // floats per row of the staged R / dPB / dR tiles
+constexpr float kLog2e = 1.4426950408889634f;
+
+struct BwdRowsParams {
+  int B, H, N, Npad, ldw;
+  float scale;
+  int ctx_k, ctx_v, shared_tables;
+  const uint8_t* idx_a; const uint8_t* idx_b; const uint8_t* idx_va; const uint8_t* idx_vb;
+  int ldi;
+  const float* bias;
+  const __nv_bfloat16* out; int64_t ldo;     // forward output (for delta)
+  const __nv_bfloat16* dout; int64_t lddo;
+  const float* lse;
+  __nv_bfloat16* dqkv; int64_t lddqkv;
+  __nv_bfloat16* ws_p; __nv_bfloat16* ws_dt;  // (B*H*N, ldw)
+  float* dbias;
+};
+
+__device__ __forceinline__ float fast_exp2(float x) {
+  float y;
+  asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+      : "memory");
+}
+
+__device__ __forceinline__ uint32_t byte_of(const uint32_t (&w)[4], int k) {
+  return (w[k >> 2] >> (8 * (k & 3))) & 0xFF;
+}
+
+__global__ void __launch_bounds__(kRowsThreads, 1)
+attn_bwd_rows_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_kv,
+                     const __grid_constant__ CUtensorMap map_do, const __grid_constant__ CUtensorMap map_tk,
+                     const __grid_constant__ CUtensorMap map_tv, const BwdRowsParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>(
+      (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  const int kv_bytes = p.Npad * 128;
+  const int v_slot = max(kv_bytes, 26 * 1024);
+  uint8_t* sQ = smem;                       // 16 KB
+  uint8_t* sdO = sQ + 16384;                // 16 KB
+  uint8_t* sK = sdO + 16384;                // [K ; TK] contiguous rows
+  uint8_t* sTK = sK + kv_bytes;
+  uint8_t* sV = sTK + 8192;                 // [V ; TV]
+  uint8_t* sTV = sV + v_slot;
+  float* sR = reinterpret_cast<float*>(sTV + 8192);
+  float* sdPB = sR + 128 * kStride;
+  float* sBias = sdPB + 128 * kStride;
+  float* sDbias = sBias + 64;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sDbias + 64);
+  uint64_t* bar_ld = bars + 0;
+  uint64_t* bar_r = bars + 1;
+  uint64_t* bar_rfree = bars + 2;
+  uint64_t* bar_s = bars + 3;
+  uint64_t* bar_p = bars + 4;
+  uint64_t* bar_o = bars + 5;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+  float* sPB = reinterpret_cast<float*>(sQ);   // 128 x 64 fp32, xor-swizzled, over sQ|sdO
+  float* sdR = reinterpret_cast<float*>(sV);   // 128 x 65 fp32 over sV|sTV
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.x * 128, head = blockIdx.y, b = blockIdx.z;
+  const int Npad = p.Npad;
+  const int tab = p.shared_tables ? 0 : head;
+  const bool any_r = p.ctx_k || p.ctx_v;
+
+  if (threadIdx.x == 0) {
+    prefetch_tmap(&map_q);
+    prefetch_tmap(&map_kv);
+    prefetch_tmap(&map_do);
+    mbar_init(bar_ld, 1);
+    mbar_init(bar_r, 1);
+    mbar_init(bar_rfree, 128);
+    mbar_init(bar_s, 1);
+    mbar_init(bar_p, 128);
+    mbar_init(bar_o, 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) tmem_alloc<512>(tmem_slot);
+  if (threadIdx.x >= 32 && threadIdx.x < 96) {
+    sBias[threadIdx.x - 32] = p.bias ? p.bias[tab * 64 + threadIdx.x - 32] : 0.f;
+    sDbias[threadIdx.x - 32] = 0.f;
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      const int qcol = head * kD, kcol = (p.H + head) * kD, vcol = (2 * p.H + head) * kD;
+      mbar_arrive_expect_tx(bar_ld, 2 * 16384 + 2 * kv_bytes + (p.ctx_k ? 8192 : 0) + (p.ctx_v ? 8192 : 0));
+      tma_load_3d(sQ, &map_q, bar_ld, qcol, m0, b);
+      tma_load_3d(sdO, &map_do, bar_ld, qcol, m0, b);
+      tma_load_3d(sK, &map_kv, bar_ld, kcol, 0, b);
+      tma_load_3d(sV, &map_kv, bar_ld, vcol, 0, b);
+      if (p.ctx_k) tma_load_3d(sTK, &map_tk, bar_ld, 0, 0, tab);
+      if (p.ctx_v) tma_load_3d(sTV, &map_tv, bar_ld, 0, 0, tab);
+      mbar_wait(bar_ld, 0);
+      tc_fence_after();
+      const uint32_t aQ = smem_u32(sQ), adO = smem_u32(sdO), aK = smem_u32(sK), aV = smem_u32(sV);
+      const uint32_t aTK = smem_u32(sTK), aTV = smem_u32(sTV);
+      const uint32_t id64 = umma_idesc_bf16(128, kNB, 0, 0);
+      const uint32_t idN = umma_idesc_bf16(128, Npad, 0, 0);
+      if (p.ctx_k)
+        for (int k = 0; k < 4; ++k)
+          umma_ss(tmem + 0, umma_smem_desc_sw128(aQ + k * 32, 16, 1024),
+                  umma_smem_desc_sw128(aTK + k * 32, 16, 1024), id64, k > 0);
+      if (p.ctx_v)
+        for (int k = 0; k < 4; ++k)
+          umma_ss(tmem + 64, umma_smem_desc_sw128(adO + k * 32, 16, 1024),
+                  umma_smem_desc_sw128(aTV + k * 32, 16, 1024), id64, k > 0);
+      if (any_r) umma_commit(bar_r);
+      for (int k = 0; k < 4; ++k)   // dP = dO V^T
+        umma_ss(tmem + 256, umma_smem_desc_sw128(adO + k * 32, 16, 1024),
+                umma_smem_desc_sw128(aV + k * 32, 16, 1024), idN, k > 0);
+      if (any_r) {
+        mbar_wait(bar_rfree, 0);
+        tc_fence_after();
+      }
+      for (int k = 0; k < 4; ++k)   // T = Q K^T
+        umma_ss(tmem + 0, umma_smem_desc_sw128(aQ + k * 32, 16, 1024),
+                umma_smem_desc_sw128(aK + k * 32, 16, 1024), idN, k > 0);
+      umma_commit(bar_s);
+
+      mbar_wait(bar_p, 0);
+      tc_fence_after();
+      const uint32_t id_o = umma_idesc_bf16(128, kD, 0, 1);
+      const int ksteps = (Npad + (p.ctx_k ? kNB : 0)) / 16;
+      for (int k = 0; k < ksteps; ++k)   // dQ = [dT | dR] [K ; TK]
+        umma_ts(tmem + 192, tmem + 8 * k, umma_smem_desc_sw128(aK + k * 2048, 8192, 1024), id_o, k > 0);
+      umma_commit(bar_o);
+    }
+  } else {
+    const int quarter = warp & 3;
+    const int r_local = quarter * 32 + lane;
+    const int row = m0 + r_local;
+    const int row_c = min(row, p.N - 1);
+    const uint32_t trow = tmem + (static_cast<uint32_t>(quarter * 32) << 16);
+    float* myR = sR + r_local * kStride;
+    float* mydPB = sdPB + r_local * kStride;
+
+    if (any_r) {
+      mbar_wait(bar_r, 0);
+      tc_fence_after();
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        uint32_t raw[32];
+        if (p.ctx_k) {
+          tmem_ld32(trow + c * 32, raw);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) myR[c * 32 + i] = p.scale * __uint_as_float(raw[i]);
+        }
+        if (p.ctx_v) {
+          tmem_ld32(trow + 64 + c * 32, raw);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) mydPB[c * 32 + i] = __uint_as_float(raw[i]);
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(bar_rfree);
+    }
+
+    // delta_i = dO_i . O_i and lse_i straight from global (256 B per row)
+    float delta = 0.f, lse = 0.f;
+    if (row < p.N) {
+      const uint4* o4 = reinterpret_cast<const uint4*>(p.out + (static_cast<int64_t>(b) * p.N + row) * p.ldo + head * kD);
+      const uint4* g4 = reinterpret_cast<const uint4*>(p.dout + (static_cast<int64_t>(b) * p.N + row) * p.lddo + head * kD);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const uint4 a = __ldg(o4 + q), g = __ldg(g4 + q);
+        const float2 a0 = unpack_bf16x2(a.x), a1 = unpack_bf16x2(a.y), a2 = unpack_bf16x2(a.z), a3 = unpack_bf16x2(a.w);
+        const float2 g0 = unpack_bf16x2(g.x), g1 = unpack_bf16x2(g.y), g2 = unpack_bf16x2(g.z), g3 = unpack_bf16x2(g.w);
+        delta += a0.x * g0.x + a0.y * g0.y + a1.x * g1.x + a1.y * g1.y + a2.x * g2.x + a2.y * g2.y +
+                 a3.x * g3.x + a3.y * g3.y;
+      }
+      lse = p.lse[(static_cast<int64_t>(b) * p.H + head) * p.N + row];
+    }
+    mbar_wait(bar_s, 0);
+    tc_fence_after();
+
+    // bucket-sum accumulators (thread-private rows; sPB xor-swizzled to fit 32 KB)
+    float* myPB = sPB + r_local * 64;
+    float* mydR = sdR + r_local * kStride;
+    const int sw = r_local & 31;
+    for (int k = 0; k < kNB; ++k) { myPB[k] = 0.f; mydR[k] = 0.f; }
+
+    const uint8_t* ia = p.idx_a ? p.idx_a + static_cast<int64_t>(row_c) * p.ldi : nullptr;
+    const uint8_t* ib = p.idx_b ? p.idx_b + static_cast<int64_t>(row_c) * p.ldi : nullptr;
+    const uint8_t* iva = p.idx_va ? p.idx_va + static_cast<int64_t>(row_c) * p.ldi : nullptr;
+    const uint8_t* ivb = p.idx_vb ? p.idx_vb + static_cast<int64_t>(row_c) * p.ldi : nullptr;
+    const bool use_bias = p.bias != nullptr;
+    const bool want_dr = p.ctx_k || use_bias;
+    const float lsel = lse * kLog2e;
+    const int64_t wrow = ((static_cast<int64_t>(b) * p.H + head) * p.N + row) * p.ldw;
+    const int nchunks = Npad / 16;
+    for (int c = 0; c < nchunks; ++c) {
+      uint32_t rt[16], rp[16];
+      tmem_ld16(trow + c * 16, rt);
+      tmem_ld16(trow + 256 + c * 16, rp);
+      uint4 va = make_uint4(0, 0, 0, 0), vb = va, vva = va, vvb = va;
+      if (ia) va = __ldg(reinterpret_cast<const uint4*>(ia + c * 16));
+      if (ib) vb = __ldg(reinterpret_cast<const uint4*>(ib + c * 16));
+      if (iva) vva = __ldg(reinterpret_cast<const uint4*>(iva + c * 16));
+      if (ivb) vvb = __ldg(reinterpret_cast<const uint4*>(ivb + c * 16));
+      tmem_ld_wait();
+      const uint32_t wa[4] = {va.x, va.y, va.z, va.w}, wb[4] = {vb.x, vb.y, vb.z, vb.w};
+      const uint32_t wva[4] = {vva.x, vva.y, vva.z, vva.w}, wvb[4] = {vvb.x, vvb.y, vvb.z, vvb.w};
+      float pv[16], dt[16];
+#pragma unroll
+      for (int k = 0; k < 16; ++k) {
+        const uint32_t a_id = byte_of(wa, k), b_id = byte_of(wb, k);
+        const uint32_t va_id = byte_of(wva, k), vb_id = byte_of(wvb, k);
+        float t = p.scale * __uint_as_float(rt[k]);
+        if (p.ctx_k) {
+          if (ia) t += myR[a_id];
+          if (ib) t += myR[b_id];
+        }
+        if (use_bias) t += sBias[a_id];
+        float pr = fast_exp2(fmaf(t, kLog2e, -lsel));
+        if (c * 16 + k >= p.N || row >= p.N) pr = 0.f;
+        float dp = __uint_as_float(rp[k]);
+        if (p.ctx_v) {
+          if (iva) dp += mydPB[va_id];
+          if (ivb) dp += mydPB[vb_id];
+        }
+        const float d = pr * (dp - delta);
+        pv[k] = pr;
+        dt[k] = d;
+        if (p.ctx_v) {
+          if (iva) myPB[va_id ^ sw] += pr;
+          if (ivb) myPB[vb_id ^ sw] += pr;
+        }
+        if (want_dr) {
+          if (ia) mydR[a_id] += d;
+          if (ib) mydR[b_id] += d;
+        }
+      }
+      uint32_t pk[8], dk[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        pk[k] = pack_bf16x2(pv[2 * k], pv[2 * k + 1]);
+        dk[k] = pack_bf16x2(dt[2 * k], dt[2 * k + 1]);
+      }
+      tmem_st8(trow + c * 8, dk);   // dT (bf16x2) in place over T, A operand of the dQ MMA
+      if (row < p.N) {
+        uint4* wp = reinterpret_cast<uint4*>(p.ws_p + wrow + c * 16);
+        uint4* wd = reinterpret_cast<uint4*>(p.ws_dt + wrow + c * 16);
+        wp[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        wp[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+        wd[0] = make_uint4(dk[0], dk[1], dk[2], dk[3]);
+        wd[1] = make_uint4(dk[4], dk[5], dk[6], dk[7]);
+      }
+    }
+    // bucket sums: PB -> workspace ; dR -> workspace + TMEM (A operand of the dQ MMA)
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      uint32_t pk[16], dk[16];
+#pragma unroll
+      for (int k = 0; k < 16; ++k) {
+        const int b0 = c * 32 + 2 * k;
+        pk[k] = pack_bf16x2(myPB[b0 ^ sw], myPB[(b0 + 1) ^ sw]);
+        dk[k] = pack_bf16x2(mydR[b0], mydR[b0 + 1]);
+      }
+      if (p.ctx_k) tmem_st16(trow + Npad / 2 + c * 16, dk);
+      if (row < p.N) {
+        uint4* wp = reinterpret_cast<uint4*>(p.ws_p + wrow + Npad + c * 32);
+        uint4* wd = reinterpret_cast<uint4*>(p.ws_dt + wrow + Npad + c * 32);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          wp[q] = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+          wd[q] = make_uint4(dk[4 * q], dk[4 * q + 1], dk[4 * q + 2], dk[4 * q + 3]);
+        }
+      }
+    }
+    if (p.dbias != nullptr && row < p.N) {
+      for (int k = 0; k < kNB; ++k) atomicAdd(&sDbias[k], mydR[k]);
+    }
+    tmem_st_wait();
+    tc_fence_before();
+    mbar_arrive(bar_p);
+
+    mbar_wait(bar_o, 0);
+    tc_fence_after();
+    __nv_bfloat16* qrow = p.dqkv + (static_cast<int64_t>(b) * p.N + row) * p.lddqkv + head * kD;
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      uint32_t raw[32];
+      tmem_ld32(trow + 192 + c * 32, raw);
+      tmem_ld_wait();
+      if (row < p.N) {
+        uint4* o4 = reinterpret_cast<uint4*>(qrow + c * 32);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          uint4 u;
+          u.x = pack_bf16x2(p.scale * __uint_as_float(raw[8 * q + 0]), p.scale * __uint_as_float(raw[8 * q + 1]));
+          u.y = pack_bf16x2(p.scale * __uint_as_float(raw[8 * q + 2]), p.scale * __uint_as_float(raw[8 * q + 3]));
+          u.z = pack_bf16x2(p.scale * __uint_as_float(raw[8 * q + 4]), p.scale * __uint_as_float(raw[8 * q + 5]));
+          u.w = pack_bf16x2(p.scale * __uint_as_float(raw[8 * q + 6]), p.scale * __uint_as_float(raw[8 * q + 7]));
+          o4[q] = u;
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (p.dbias != nullptr && threadIdx.x < 64) atomicAdd(p.dbias + tab * 64 + threadIdx.x, sDbias[threadIdx.x]);
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc<512>(tmem);
+  }
+}
+
+// -------------------------------------------------------------------------------------------
+// Column-form products.  One CTA per (head, batch):
+//   acc_v[m, d] = sum_i Wp[i, m] dO[i, d]        m in [0, Npad+64)   ([P | PB]^T dO)
+//   acc_k[m, d] = sum_i Wd[i, m] Q[i, d]                             ([dT | dR]^T Q)
+// M is covered by 3 tiles of 128 (cols beyond Npad+64 are zero-filled by TMA).
+// warp 0: TMA, warp 1: MMA, warps 2..5: epilogue.
+// -------------------------------------------------------------------------------------------
+constexpr int kColsThreads = 192;
+constexpr int kColStages = 2;
+constexpr int kColStageBytes = 2 * 6 * 8192 + 2 * 8192;  // 6 A boxes per workspace + dO + Q = 112 KB
+
+struct BwdColsParams {
+  int B, H, N, Npad, ldw;
+  float scale;
+  int shared_tables;
+  __nv_bfloat16* dqkv; int64_t lddqkv;
+  float* dtk; float* dtv;
+};
+
+__global__ void __launch_bounds__(kColsThreads, 1)
+attn_bwd_cols_kernel(const __grid_constant__ CUtensorMap map_wp, const __grid_constant__ CUtensorMap map_wd,
+                     const __grid_constant__ CUtensorMap map_do, const __grid_constant__ CUtensorMap map_q,
+                     const BwdColsParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>(
+      (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kColStages * kColStageBytes);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + kColStages;
+  uint64_t* done = bars + 2 * kColStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int head = blockIdx.x, b = blockIdx.y;
+  const int bh = b * p.H + head;
+  const int nkb = ceil_div(p.N, 64);
+  const int mtiles = ceil_div(p.Npad + kNB, 128);  // <= 3
+
+  if (threadIdx.x == 0) {
+    prefetch_tmap(&map_wp);
+    prefetch_tmap(&map_wd);
+    for (int s = 0; s < kColStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    mbar_init(done, 1);
+    fence_mbar_init();
+  }
+  if (warp == 2) tmem_alloc<512>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 0 && lane == 0) {
+    for (int kb = 0; kb < nkb; ++kb) {
+      const int s = kb % kColStages;
+      mbar_wait(&empty[s], ((kb / kColStages) & 1) ^ 1);
+      uint8_t* st = smem + s * kColStageBytes;
+      mbar_arrive_expect_tx(&full[s], kColStageBytes);
+      for (int c = 0; c < 6; ++c) {
+        tma_load_3d(st + c * 8192, &map_wp, &full[s], c * 64, kb * 64, bh);
+        tma_load_3d(st + (6 + c) * 8192, &map_wd, &full[s], c * 64, kb * 64, bh);
+      }
+      tma_load_3d(st + 12 * 8192, &map_do, &full[s], head * kD, kb * 64, b);
+      tma_load_3d(st + 13 * 8192, &map_q, &full[s], head * kD, kb * 64, b);
+    }
+  } else if (warp == 1 && lane == 0) {
+    const uint32_t idesc = umma_idesc_bf16(128, kD, 1, 1);
+    for (int kb = 0; kb < nkb; ++kb) {
+      const int s = kb % kColStages;
+      mbar_wait(&full[s], (kb / kColStages) & 1);
+      tc_fence_after();
+      const uint32_t st = smem_u32(smem + s * kColStageBytes);
+      for (int mt = 0; mt < mtiles; ++mt) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const uint32_t acc = (kb > 0 || k > 0) ? 1u : 0u;
+          // A: two 64-wide MN chunks (LBO = 8192) of 64 K-rows; B: one chunk.
+          umma_ss(tmem + mt * 64, umma_smem_desc_sw128(st + (2 * mt) * 8192 + k * 2048, 8192, 1024),
+                  umma_smem_desc_sw128(st + 12 * 8192 + k * 2048, 8192, 1024), idesc, acc);
+          umma_ss(tmem + 192 + mt * 64, umma_smem_desc_sw128(st + (6 + 2 * mt) * 8192 + k * 2048, 8192, 1024),
+                  umma_smem_desc_sw128(st + 13 * 8192 + k * 2048, 8192, 1024), idesc, acc);
+        }
+      }
+      umma_commit(&empty[s]);
+    }
+    umma_commit(done);
+  } else if (warp >= 2) {
+    const int quarter = warp & 3;
+    mbar_wait(done, 0);
+    tc_fence_after();
+    const uint32_t trow = tmem + (static_cast<uint32_t>(quarter * 32) << 16);
+    const int tab = p.shared_tables ? 0 : head;
+    for (int which = 0; which < 2; ++which) {          // 0: dV / dTV   1: dK / dTK
+      const float mul = which ? p.scale : 1.0f;
+      float* dtab = which ? p.dtk : p.dtv;
+      const int col0 = ((which ? 1 : 2) * p.H + head) * kD;
+      for (int mt = 0; mt < mtiles; ++mt) {
+        const int m = mt * 128 + quarter * 32 + lane;
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          uint32_t raw[32];
+          tmem_ld32(trow + which * 192 + mt * 64 + c * 32, raw);
+          tmem_ld_wait();
+          if (m < p.N) {
+            uint4* o4 = reinterpret_cast<uint4*>(p.dqkv + (static_cast<int64_t>(b) * p.N + m) * p.lddqkv + col0 + c * 32);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              uint4 u;
+              u.x = pack_bf16x2(mul * __uint_as_float(raw[8 * q + 0]), mul * __uint_as_float(raw[8 * q + 1]));
+              u.y = pack_bf16x2(mul * __uint_as_float(raw[8 * q + 2]), mul * __uint_as_float(raw[8 * q + 3]));
+              u.z = pack_bf16x2(mul * __uint_as_float(raw[8 * q + 4]), mul * __uint_as_float(raw[8 * q + 5]));
+              u.w = pack_bf16x2(mul * __uint_as_float(raw[8 * q + 6]), mul * __uint_as_float(raw[8 * q + 7]));
+              o4[q] = u;
+            }
+          } else if (m >= p.Npad && m < p.Npad + kNB && dtab != nullptr) {
+            float* dst = dtab + (static_cast<int64_t>(tab) * kNB + (m - p.Npad)) * kD + c * 32;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) atomicAdd(dst + i, mul * __uint_as_float(raw[i]));
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc<512>(tmem);
+  }
+}
+
+}  // namespace
+}  // namespace cb
+
+extern "C" int64_t cream_attn_bwd_workspace_bytes(int B, int H, int N) {
+  const int64_t ldw = cb::round_up(N, 16) + 64;
+  return 2 * static_cast<int64_t>(B) * H * N * ldw * 2 + 256;
+}
+
+extern "C" int cream_attn_bwd(const cream_attn_desc* d, void* stream_) {
+  using namespace cb;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  CB_REQUIRE(d != nullptr && d->qkv && d->out && d->dout && d->dqkv && d->lse && d->workspace, "null pointer");
+  CB_REQUIRE(d->head_dim == kD, "head_dim must be 64");
+  CB_REQUIRE(d->N >= 1 && d->N <= 208, "1 <= tokens <= 208");
+  CB_REQUIRE(d->ld_qkv % 8 == 0 && d->ld_out % 8 == 0 && d->ld_dout % 8 == 0 && d->ld_dqkv % 8 == 0, "leading dims % 8");
+  const int Npad = round_up(d->N, 16);
+  const int ldw = Npad + kNB;
+  CB_REQUIRE(d->workspace_bytes >= cream_attn_bwd_workspace_bytes(d->B, d->H, d->N), "workspace too small");
+  CB_REQUIRE((reinterpret_cast<uintptr_t>(d->workspace) & 255) == 0, "workspace alignment");
+  const bool ctx_k = d->tk_pack != nullptr, ctx_v = d->tv_pack != nullptr;
+  if (ctx_k) CB_REQUIRE(d->idx_a != nullptr && d->dtk_pack != nullptr, "K tables need idx_a and dtk_pack");
+  if (ctx_v) CB_REQUIRE(d->idx_va != nullptr && d->dtv_pack != nullptr, "V tables need idx_va and dtv_pack");
+  if (d->idx_a || d->idx_va) CB_REQUIRE(d->ld_idx >= Npad && d->ld_idx % 16 == 0, "index pitch");
+
+  __nv_bfloat16* ws_p = static_cast<__nv_bfloat16*>(d->workspace);
+  const int64_t ws_elems = static_cast<int64_t>(d->B) * d->H * d->N * ldw;
+  __nv_bfloat16* ws_dt = ws_p + ((ws_elems + 127) / 128) * 128;
+
+  BwdRowsParams p{};
+  p.B = d->B; p.H = d->H; p.N = d->N; p.Npad = Npad; p.ldw = ldw;
+  p.scale = d->scale;
+  p.ctx_k = ctx_k; p.ctx_v = ctx_v; p.shared_tables = d->tables_per_head ? 0 : 1;
+  p.idx_a = d->idx_a; p.idx_b = d->idx_b; p.idx_va = d->idx_va; p.idx_vb = d->idx_vb; p.ldi = d->ld_idx;
+  p.bias = d->bias_pack;
+  p.out = static_cast<const __nv_bfloat16*>(d->out); p.ldo = d->ld_out;
+  p.dout = static_cast<const __nv_bfloat16*>(d->dout); p.lddo = d->ld_dout;
+  p.lse = d->lse;
+  p.dqkv = static_cast<__nv_bfloat16*>(d->dqkv); p.lddqkv = d->ld_dqkv;
+  p.ws_p = ws_p; p.ws_dt = ws_dt;
+  p.dbias = d->dbias_pack;
+
+  const uint64_t dims[3] = {static_cast<uint64_t>(3 * d->H * kD), static_cast<uint64_t>(d->N), static_cast<uint64_t>(d->B)};
+  const uint64_t strides[3] = {1, static_cast<uint64_t>(d->ld_qkv), static_cast<uint64_t>(d->N) * d->ld_qkv};
+  const uint32_t box_q[3] = {64, 128, 1};
+  const uint32_t box_kv[3] = {64, static_cast<uint32_t>(Npad), 1};
+  const uint32_t box_64[3] = {64, 64, 1};
+  const CUtensorMap* mq = get_tensor_map(d->qkv, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, dims, strides, box_q, CU_TENSOR_MAP_SWIZZLE_128B);
+  const CUtensorMap* mkv = get_tensor_map(d->qkv, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, dims, strides, box_kv, CU_TENSOR_MAP_SWIZZLE_128B);
+  const CUtensorMap* mq64 = get_tensor_map(d->qkv, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, dims, strides, box_64, CU_TENSOR_MAP_SWIZZLE_128B);
+  const uint64_t ddims[3] = {static_cast<uint64_t>(d->H * kD), static_cast<uint64_t>(d->N), static_cast<uint64_t>(d->B)};
+  const uint64_t dstrides[3] = {1, static_cast<uint64_t>(d->ld_dout), static_cast<uint64_t>(d->N) * d->ld_dout};
+  const CUtensorMap* mdo = get_tensor_map(d->dout, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, ddims, dstrides, box_q, CU_TENSOR_MAP_SWIZZLE_128B);
+  const CUtensorMap* mdo64 = get_tensor_map(d->dout, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, ddims, dstrides, box_64, CU_TENSOR_MAP_SWIZZLE_128B);
+  const int ntab = d->tables_per_head ? d->H : 1;
+  const uint64_t tdims[3] = {64, 64, static_cast<uint64_t>(ntab)};
+  const uint64_t tstrides[3] = {1, 64, 64 * 64};
+  const CUtensorMap* mtk = ctx_k ? get_tensor_map(d->tk_pack, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, tdims, tstrides, box_64, CU_TENSOR_MAP_SWIZZLE_128B) : mq;
+  const CUtensorMap* mtv = ctx_v ? get_tensor_map(d->tv_pack, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, tdims, tstrides, box_64, CU_TENSOR_MAP_SWIZZLE_128B) : mq;
+  const uint64_t wdims[3] = {static_cast<uint64_t>(ldw), static_cast<uint64_t>(d->N), static_cast<uint64_t>(d->B) * d->H};
+  const uint64_t wstrides[3] = {1, static_cast<uint64_t>(ldw), static_cast<uint64_t>(d->N) * ldw};
+  const CUtensorMap* mwp = get_tensor_map(ws_p, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, wdims, wstrides, box_64, CU_TENSOR_MAP_SWIZZLE_128B);
+  const CUtensorMap* mwd = get_tensor_map(ws_dt, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, wdims, wstrides, box_64, CU_TENSOR_MAP_SWIZZLE_128B);
+  if (!mq || !mkv || !mq64 || !mdo || !mdo64 || !mtk || !mtv || !mwp || !mwd) return CREAM_ERR_CUDA;
+
+  static bool attr_set = false;
+  if (!attr_set) {
+    CB_CUDA_OK(cudaFuncSetAttribute(attn_bwd_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CB_CUDA_OK(cudaFuncSetAttribute(attn_bwd_cols_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set = true;
+  }
+  const size_t smem_rows = 1024 + 2 * 16384 + static_cast<size_t>(Npad) * 128 + 8192 +
+                           std::max<size_t>(Npad * 128, 26 * 1024) + 8192 + 2 * 128 * kStride * 4 + 2 * 64 * 4 + 128;
+  CB_REQUIRE(smem_rows <= 227 * 1024, "shared memory budget");
+  dim3 grid(ceil_div(d->N, 128), d->H, d->B);
+  attn_bwd_rows_kernel<<<grid, kRowsThreads, smem_rows, stream>>>(*mq, *mkv, *mdo, *mtk, *mtv, p);
+  int rc = check_last("attn_bwd_rows_kernel");
+  if (rc) return rc;
+
+  BwdColsParams c{};
+  c.B = d->B; c.H = d->H; c.N = d->N; c.Npad = Npad; c.ldw = ldw;
+  c.scale = d->scale;
+  c.shared_tables = d->tables_per_head ? 0 : 1;
+  c.dqkv = static_cast<__nv_bfloat16*>(d->dqkv); c.lddqkv = d->ld_dqkv;
+  c.dtk = ctx_k ? d->dtk_pack : nullptr;
+  c.dtv = ctx_v ? d->dtv_pack : nullptr;
+  const size_t smem_cols = 1024 + kColStages * kColStageBytes + 256;
+  dim3 grid2(d->H, d->B);
+  attn_bwd_cols_kernel<<<grid2, kColsThreads, smem_cols, stream>>>(*mwp, *mwd, *mdo64, *mq64, c);
+  return check_last("attn_bwd_cols_kernel");
+}

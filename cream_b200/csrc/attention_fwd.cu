@@ -1,0 +1,386 @@
+// Fused attention forward with relative-position terms, sm_100a (tcgen05 + TMEM + TMA).
+//
+// Replaces, per layer, the five batched GEMMs + two index gathers + softmax of
+//   AutoFormer/model/module/multihead_super.py:133-154  (AttentionSuper.forward)
+//   iRPE/DeiT-with-iRPE/rpe_vision_transformer.py:73-92 (RPEAttention.forward, rpe on k / v,
+//   contextual or bias mode) + irpe.py:585-687 + rpe_ops/rpe_index_cuda.cu
+// by ONE kernel that reads q,k,v once and writes o once.
+//
+// "Bucket formulation": a contextual RPE term  q_i . T[idx[i,j]]  is computed as
+//   R = Q . Tpack^T  (one extra 128x64x64 MMA, Tpack = up to two tables packed in 64 rows)
+// followed by a per-row gather  S[i,j] += R[i, idx[i,j]]  staged through shared memory and
+// fused into the softmax pass; the value-side term  sum_j P[i,j] T'[idx[i,j]]  becomes
+//   PB[i,b] = sum_{j: idx[i,j]=b} P[i,j]   (bucket sums, thread-local)   and
+//   O = [P | PB] . [V ; T'pack]           (a single chain of tcgen05.mma, A from TMEM).
+//
+// CTA = (query tile of 128 rows, head, batch); 5 warps; 256 TMEM columns and ~101 KB of
+// shared memory so that two CTAs are resident per SM and overlap each other's phases.
+//   warp 0 (one lane): TMA loads, tcgen05.mma issue
+//   warps 1..4       : one thread per query row: R copy-out, softmax, epilogue
+// TMEM columns: S fp32 [0,Npad) -> P bf16x2 in place [0,Npad/2) | PB [Npad/2,Npad/2+32);
+//               R fp32 [192,256) (dead before S cols >= 192 are produced); O fp32 [192,256).
+#include <cuda_fp16.h>
+
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace cb {
+namespace {
+
+constexpr int kD = 64;              // head dim
+constexpr int kNB = 64;             // packed bucket rows (two tables of <= 32, or one of <= 64)
+constexpr int kThreads = 160;
+constexpr int kRStride = 66;        // halfs per row of the staged R tile (bank spread)
+constexpr int kPBStride = 65;       // floats per row of the bucket-sum tile
+constexpr float kLog2e = 1.4426950408889634f;
+
+struct AttnFwdParams {
+  int B, H, N, Npad;
+  float scale;
+  int ctx_k, ctx_v;                    // contextual tables on K / V present
+  int shared_tables;                   // 1: one table pack for all heads
+  const uint8_t* idx_a; const uint8_t* idx_b;   // K-side gather indices (N, ldi), values < 64
+  const uint8_t* idx_va; const uint8_t* idx_vb; // V-side
+  int ldi;
+  const float* bias;                   // (H or 1, 64) pre-packed bias table, gathered by idx_a
+  __nv_bfloat16* out; int64_t ldo;     // (B*N, H*64)
+  float* lse;                          // (B, H, N)
+};
+
+__device__ __forceinline__ float fast_exp2(float x) {
+  float y;
+  asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+      : "memory");
+}
+
+__global__ void __launch_bounds__(kThreads, 2)
+attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_kv,
+                const __grid_constant__ CUtensorMap map_tk, const __grid_constant__ CUtensorMap map_tv,
+                const AttnFwdParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>(
+      (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  const int kv_bytes = p.Npad * 128;
+  const int k_slot = max(kv_bytes, 9216);  // sQ + sTK + sK must hold the 128 x 65 fp32 PB overlay
+  uint8_t* sQ = smem;
+  uint8_t* sTK = sQ + 16384;
+  uint8_t* sK = sTK + 8192;
+  uint8_t* sV = sK + k_slot;         // [V ; TV] contiguous rows
+  uint8_t* sTV = sV + kv_bytes;
+  __half* sR = reinterpret_cast<__half*>(sTV + 8192);
+  float* sBias = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(sR) + 128 * kRStride * 2);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sBias + 64);
+  uint64_t* bar_qk = bars + 0;
+  uint64_t* bar_v = bars + 1;
+  uint64_t* bar_r = bars + 2;
+  uint64_t* bar_rfree = bars + 3;
+  uint64_t* bar_s = bars + 4;
+  uint64_t* bar_p = bars + 5;
+  uint64_t* bar_o = bars + 6;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+  float* sPB = reinterpret_cast<float*>(smem);  // overlays sQ/sK/sTK once S is complete
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.x * 128, head = blockIdx.y, b = blockIdx.z;
+  const int Npad = p.Npad;
+  const int n_a = min(Npad, 192);     // S columns produced before R is released
+  const int n_b = Npad - n_a;         // remaining S columns (overlap the R region)
+
+  if (threadIdx.x == 0) {
+    prefetch_tmap(&map_q);
+    prefetch_tmap(&map_kv);
+    mbar_init(bar_qk, 1);
+    mbar_init(bar_v, 1);
+    mbar_init(bar_r, 1);
+    mbar_init(bar_rfree, 128);
+    mbar_init(bar_s, 1);
+    mbar_init(bar_p, 128);
+    mbar_init(bar_o, 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) tmem_alloc<256>(tmem_slot);
+  if (p.bias != nullptr && threadIdx.x >= 32 && threadIdx.x < 96)
+    sBias[threadIdx.x - 32] = p.bias[(p.shared_tables ? 0 : head) * 64 + threadIdx.x - 32];
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const int tab = p.shared_tables ? 0 : head;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ---------------- loads ----------------
+      const int qcol = head * kD, kcol = (p.H + head) * kD, vcol = (2 * p.H + head) * kD;
+      uint32_t qk_bytes = 16384 + kv_bytes + (p.ctx_k ? 8192 : 0);
+      mbar_arrive_expect_tx(bar_qk, qk_bytes);
+      tma_load_3d(sQ, &map_q, bar_qk, qcol, m0, b);
+      tma_load_3d(sK, &map_kv, bar_qk, kcol, 0, b);
+      if (p.ctx_k) tma_load_3d(sTK, &map_tk, bar_qk, 0, 0, tab);
+      mbar_arrive_expect_tx(bar_v, kv_bytes + (p.ctx_v ? 8192 : 0));
+      tma_load_3d(sV, &map_kv, bar_v, vcol, 0, b);
+      if (p.ctx_v) tma_load_3d(sTV, &map_tv, bar_v, 0, 0, tab);
+
+      // ---------------- S = Q K^T (+ R = Q TK^T) ----------------
+      mbar_wait(bar_qk, 0);
+      tc_fence_after();
+      const uint32_t aQ = smem_u32(sQ), aK = smem_u32(sK), aTK = smem_u32(sTK);
+      if (p.ctx_k) {
+        const uint32_t id_r = umma_idesc_bf16(128, kNB, 0, 0);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_ss(tmem + 192, umma_smem_desc_sw128(aQ + k * 32, 16, 1024),
+                  umma_smem_desc_sw128(aTK + k * 32, 16, 1024), id_r, k > 0);
+        umma_commit(bar_r);
+      }
+      {
+        const uint32_t id_s = umma_idesc_bf16(128, n_a, 0, 0);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_ss(tmem, umma_smem_desc_sw128(aQ + k * 32, 16, 1024),
+                  umma_smem_desc_sw128(aK + k * 32, 16, 1024), id_s, k > 0);
+      }
+      if (n_b > 0) {
+        if (p.ctx_k) {
+          mbar_wait(bar_rfree, 0);
+          tc_fence_after();
+        }
+        const uint32_t id_s = umma_idesc_bf16(128, n_b, 0, 0);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_ss(tmem + 192, umma_smem_desc_sw128(aQ + k * 32, 16, 1024),
+                  umma_smem_desc_sw128(aK + 192 * 128 + k * 32, 16, 1024), id_s, k > 0);
+      }
+      umma_commit(bar_s);
+
+      // ---------------- O = [P | PB] [V ; TV] ----------------
+      mbar_wait(bar_v, 0);
+      mbar_wait(bar_p, 0);
+      tc_fence_after();
+      const uint32_t aV = smem_u32(sV);
+      const uint32_t id_o = umma_idesc_bf16(128, kD, 0, 1);
+      const int ksteps = (Npad + (p.ctx_v ? kNB : 0)) / 16;
+      for (int k = 0; k < ksteps; ++k)
+        umma_ts(tmem + 192, tmem + 8 * k, umma_smem_desc_sw128(aV + k * 2048, 8192, 1024), id_o, k > 0);
+      umma_commit(bar_o);
+    }
+  } else {
+    // =================== softmax warps: one thread per query row ===================
+    const int quarter = warp & 3;
+    const int r_local = quarter * 32 + lane;
+    const int row = m0 + r_local;                 // query index within the image
+    const int row_c = min(row, p.N - 1);          // clamp for index-table reads of padding rows
+    const uint32_t lane_base = static_cast<uint32_t>(quarter * 32) << 16;
+    const uint32_t trow = tmem + lane_base;
+    const __half* myR = sR + r_local * kRStride;
+
+    if (p.ctx_k) {
+      mbar_wait(bar_r, 0);
+      tc_fence_after();
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        uint32_t raw[32];
+        tmem_ld32(trow + 192 + c * 32, raw);
+        tmem_ld_wait();
+        __half2* dst = reinterpret_cast<__half2*>(sR + r_local * kRStride + c * 32);
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+          dst[i] = __floats2half2_rn(p.scale * __uint_as_float(raw[2 * i]),
+                                     p.scale * __uint_as_float(raw[2 * i + 1]));
+      }
+      tc_fence_before();
+      mbar_arrive(bar_rfree);
+    }
+    mbar_wait(bar_s, 0);
+    tc_fence_after();
+
+    const int nchunks = Npad / 16;
+    const uint8_t* ia = p.idx_a ? p.idx_a + static_cast<int64_t>(row_c) * p.ldi : nullptr;
+    const uint8_t* ib = p.idx_b ? p.idx_b + static_cast<int64_t>(row_c) * p.ldi : nullptr;
+    const bool use_bias = p.bias != nullptr;
+
+    // ---- pass 1: t = scale*S + gathers ; running max ; write t back ----
+    float mx = -INFINITY;
+    for (int c = 0; c < nchunks; ++c) {
+      uint32_t raw[16];
+      tmem_ld16(trow + c * 16, raw);
+      uint4 va = make_uint4(0, 0, 0, 0), vb = make_uint4(0, 0, 0, 0);
+      if (ia) va = __ldg(reinterpret_cast<const uint4*>(ia + c * 16));
+      if (ib) vb = __ldg(reinterpret_cast<const uint4*>(ib + c * 16));
+      tmem_ld_wait();
+      const uint32_t wa[4] = {va.x, va.y, va.z, va.w};
+      const uint32_t wb[4] = {vb.x, vb.y, vb.z, vb.w};
+#pragma unroll
+      for (int k = 0; k < 16; ++k) {
+        float t = p.scale * __uint_as_float(raw[k]);
+        const uint32_t a_id = (wa[k >> 2] >> (8 * (k & 3))) & 0xFF;
+        if (p.ctx_k) {
+          if (ia) t += __half2float(myR[a_id]);
+          if (ib) t += __half2float(myR[(wb[k >> 2] >> (8 * (k & 3))) & 0xFF]);
+        }
+        if (use_bias) t += sBias[a_id];
+        if (c * 16 + k >= p.N) t = -INFINITY;
+        mx = fmaxf(mx, t);
+        raw[k] = __float_as_uint(t);
+      }
+      tmem_st16(trow + c * 16, raw);
+    }
+    tmem_st_wait();
+
+    // ---- pass 2: p = exp(t - max) ; row sum ; P (bf16) in place ; bucket sums ----
+    float* myPB = sPB + r_local * kPBStride;
+    if (p.ctx_v) {
+#pragma unroll 8
+      for (int k = 0; k < kNB; ++k) myPB[k] = 0.f;
+    }
+    const uint8_t* iva = p.idx_va ? p.idx_va + static_cast<int64_t>(row_c) * p.ldi : nullptr;
+    const uint8_t* ivb = p.idx_vb ? p.idx_vb + static_cast<int64_t>(row_c) * p.ldi : nullptr;
+    const float mxl = mx * kLog2e;
+    float sum = 0.f;
+    for (int c = 0; c < nchunks; ++c) {
+      uint32_t raw[16];
+      tmem_ld16(trow + c * 16, raw);
+      uint4 va = make_uint4(0, 0, 0, 0), vb = make_uint4(0, 0, 0, 0);
+      if (iva) va = __ldg(reinterpret_cast<const uint4*>(iva + c * 16));
+      if (ivb) vb = __ldg(reinterpret_cast<const uint4*>(ivb + c * 16));
+      tmem_ld_wait();
+      const uint32_t wa[4] = {va.x, va.y, va.z, va.w};
+      const uint32_t wb[4] = {vb.x, vb.y, vb.z, vb.w};
+      float pv[16];
+#pragma unroll
+      for (int k = 0; k < 16; ++k) {
+        pv[k] = fast_exp2(fmaf(__uint_as_float(raw[k]), kLog2e, -mxl));
+        sum += pv[k];
+      }
+      if (p.ctx_v) {
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+          // padded key columns have p == 0 exactly, so their (arbitrary) ids are harmless
+          if (iva) myPB[(wa[k >> 2] >> (8 * (k & 3))) & 0xFF] += pv[k];
+          if (ivb) myPB[(wb[k >> 2] >> (8 * (k & 3))) & 0xFF] += pv[k];
+        }
+      }
+      uint32_t pk[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) pk[k] = pack_bf16x2(pv[2 * k], pv[2 * k + 1]);
+      tmem_st8(trow + c * 8, pk);
+    }
+    if (p.ctx_v) {
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        uint32_t pk[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) pk[k] = pack_bf16x2(myPB[c * 32 + 2 * k], myPB[c * 32 + 2 * k + 1]);
+        tmem_st16(trow + Npad / 2 + c * 16, pk);
+      }
+    }
+    tmem_st_wait();
+    tc_fence_before();
+    mbar_arrive(bar_p);
+
+    // ---- epilogue: O / sum -> bf16 -> global ; log-sum-exp ----
+    mbar_wait(bar_o, 0);
+    tc_fence_after();
+    const float inv = 1.0f / sum;
+    __nv_bfloat16* orow = p.out + (static_cast<int64_t>(b) * p.N + row) * p.ldo + head * kD;
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      uint32_t raw[32];
+      tmem_ld32(trow + 192 + c * 32, raw);
+      tmem_ld_wait();
+      if (row < p.N) {
+        uint4* o4 = reinterpret_cast<uint4*>(orow + c * 32);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          uint4 u;
+          u.x = pack_bf16x2(inv * __uint_as_float(raw[8 * q + 0]), inv * __uint_as_float(raw[8 * q + 1]));
+          u.y = pack_bf16x2(inv * __uint_as_float(raw[8 * q + 2]), inv * __uint_as_float(raw[8 * q + 3]));
+          u.z = pack_bf16x2(inv * __uint_as_float(raw[8 * q + 4]), inv * __uint_as_float(raw[8 * q + 5]));
+          u.w = pack_bf16x2(inv * __uint_as_float(raw[8 * q + 6]), inv * __uint_as_float(raw[8 * q + 7]));
+          o4[q] = u;
+        }
+      }
+    }
+    if (row < p.N && p.lse != nullptr)
+      p.lse[(static_cast<int64_t>(b) * p.H + head) * p.N + row] = mx + __logf(sum);
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc<256>(tmem);
+  }
+}
+
+}  // namespace
+}  // namespace cb
+
+extern "C" int cream_attn_fwd(const cream_attn_desc* d, void* stream_) {
+  using namespace cb;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  CB_REQUIRE(d != nullptr && d->qkv != nullptr && d->out != nullptr, "null pointer");
+  CB_REQUIRE(d->head_dim == kD, "head_dim must be 64");
+  CB_REQUIRE(d->N >= 1 && d->N <= 208, "1 <= tokens <= 208");
+  CB_REQUIRE(d->B >= 1 && d->H >= 1, "empty batch");
+  CB_REQUIRE(d->ld_qkv % 8 == 0 && d->ld_out % 8 == 0, "leading dims % 8");
+  const int Npad = round_up(d->N, 16);
+  const int ldi = d->ld_idx;
+  if (d->idx_a || d->idx_va) CB_REQUIRE(ldi >= Npad && ldi % 16 == 0, "index pitch must be >= Npad and % 16");
+  const bool ctx_k = d->tk_pack != nullptr, ctx_v = d->tv_pack != nullptr;
+  if (ctx_k) CB_REQUIRE(d->idx_a != nullptr, "K tables need idx_a");
+  if (ctx_v) CB_REQUIRE(d->idx_va != nullptr, "V tables need idx_va");
+  if (d->bias_pack) CB_REQUIRE(d->idx_a != nullptr, "bias needs idx_a");
+
+  AttnFwdParams p{};
+  p.B = d->B; p.H = d->H; p.N = d->N; p.Npad = Npad;
+  p.scale = d->scale;
+  p.ctx_k = ctx_k; p.ctx_v = ctx_v;
+  p.shared_tables = d->tables_per_head ? 0 : 1;
+  p.idx_a = d->idx_a; p.idx_b = d->idx_b; p.idx_va = d->idx_va; p.idx_vb = d->idx_vb;
+  p.ldi = ldi;
+  p.bias = d->bias_pack;
+  p.out = static_cast<__nv_bfloat16*>(d->out); p.ldo = d->ld_out;
+  p.lse = d->lse;
+
+  const uint64_t dims[3] = {static_cast<uint64_t>(3 * d->H * kD), static_cast<uint64_t>(d->N),
+                            static_cast<uint64_t>(d->B)};
+  const uint64_t strides[3] = {1, static_cast<uint64_t>(d->ld_qkv),
+                               static_cast<uint64_t>(d->N) * d->ld_qkv};
+  const uint32_t box_q[3] = {64, 128, 1};
+  const uint32_t box_kv[3] = {64, static_cast<uint32_t>(Npad), 1};
+  const CUtensorMap* mq = get_tensor_map(d->qkv, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, dims, strides,
+                                         box_q, CU_TENSOR_MAP_SWIZZLE_128B);
+  const CUtensorMap* mkv = get_tensor_map(d->qkv, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, dims, strides,
+                                          box_kv, CU_TENSOR_MAP_SWIZZLE_128B);
+  const int ntab = d->tables_per_head ? d->H : 1;
+  const uint64_t tdims[3] = {64, 64, static_cast<uint64_t>(ntab)};
+  const uint64_t tstrides[3] = {1, 64, 64 * 64};
+  const uint32_t tbox[3] = {64, 64, 1};
+  const CUtensorMap* mtk = ctx_k ? get_tensor_map(d->tk_pack, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, tdims,
+                                                  tstrides, tbox, CU_TENSOR_MAP_SWIZZLE_128B)
+                                 : mq;
+  const CUtensorMap* mtv = ctx_v ? get_tensor_map(d->tv_pack, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, tdims,
+                                                  tstrides, tbox, CU_TENSOR_MAP_SWIZZLE_128B)
+                                 : mq;
+  if (!mq || !mkv || !mtk || !mtv) return CREAM_ERR_CUDA;
+
+  const size_t smem_bytes = 1024 + 16384 + std::max<size_t>(Npad * 128, 9216) +
+                            static_cast<size_t>(Npad) * 128 + 2 * 8192 + 128 * kRStride * 2 + 64 * 4 + 128;
+  static bool attr_set = false;
+  if (!attr_set) {
+    CB_CUDA_OK(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    113 * 1024));
+    attr_set = true;
+  }
+  CB_REQUIRE(smem_bytes <= 113 * 1024, "shared memory budget");
+  dim3 grid(ceil_div(d->N, 128), d->H, d->B);
+  attn_fwd_kernel<<<grid, kThreads, smem_bytes, stream>>>(*mq, *mkv, *mtk, *mtv, p);
+  return check_last("attn_fwd_kernel");
+}

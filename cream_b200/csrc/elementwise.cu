@@ -1,0 +1,300 @@
+// Memory-bound glue kernels of the sampled-subnet block engine (all HBM-bound; coalesced,
+// 16-byte vectorised where alignment allows, grids sized in multiples of the SM count).
+//
+//   patch im2col        AutoFormer/model/module/embedding_super.py:33-40 (conv16x16/16 == GEMM)
+//   token assembly      AutoFormer/model/supernet_transformer.py:150-155 (cls cat + pos add)
+//   mean pooling        supernet_transformer.py:164-165 (gp)
+//   grad cast/scale     DropPath backward + fp32->bf16 (model/utils.py:71-99)
+//   bias gradient       column sums of dY
+//   RPE table packing   multihead_super.py:32-35 / irpe.py:483-496 tables -> 64x64 bf16 packs
+#include "common.cuh"
+
+namespace cb {
+namespace {
+
+inline int grid_for(int64_t work, int threads, int waves = 8) {
+  return static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(ceil_div64(work, threads), kNumSMs * waves)));
+}
+
+// images (B, C, H, W) fp32 -> patches (B*gh*gw, C*P*P) bf16, col = c*P*P + ky*P + kx
+__global__ void __launch_bounds__(256)
+im2col_kernel(const float* __restrict__ img, __nv_bfloat16* __restrict__ out, int64_t ldo, int B, int C,
+              int H, int W, int P) {
+  const int gh = H / P, gw = W / P;
+  const int K = C * P * P;
+  const int K4 = K >> 2;
+  const int64_t total = static_cast<int64_t>(B) * gh * gw * K4;
+  for (int64_t t = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; t < total;
+       t += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int k4 = static_cast<int>(t % K4);
+    const int64_t row = t / K4;
+    const int k = k4 << 2;
+    const int c = k / (P * P), ky = (k / P) % P, kx = k % P;
+    const int pw = static_cast<int>(row % gw), ph = static_cast<int>((row / gw) % gh);
+    const int64_t b = row / (gw * gh);
+    const float4 v = __ldg(reinterpret_cast<const float4*>(
+        img + ((b * C + c) * H + (ph * P + ky)) * static_cast<int64_t>(W) + pw * P + kx));
+    uint2 o;
+    o.x = pack_bf16x2(v.x, v.y);
+    o.y = pack_bf16x2(v.z, v.w);
+    *reinterpret_cast<uint2*>(out + row * ldo + k) = o;
+  }
+}
+
+// x[b,0,:] = cls + pos[0] ; x[b,1+t,:] = patch[b*T+t,:] + pos[1+t]
+__global__ void __launch_bounds__(256)
+assemble_fwd_kernel(const __nv_bfloat16* __restrict__ patch, int64_t ldp, const float* __restrict__ cls,
+                    const float* __restrict__ pos, int64_t ldpos, float* __restrict__ x, int64_t ldx,
+                    int B, int N, int E) {
+  const int64_t total = static_cast<int64_t>(B) * N * E;
+  for (int64_t t = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; t < total;
+       t += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int e = static_cast<int>(t % E);
+    const int64_t r = t / E;
+    const int n = static_cast<int>(r % N);
+    const int64_t b = r / N;
+    float v = pos ? pos[static_cast<int64_t>(n) * ldpos + e] : 0.f;
+    v += (n == 0) ? cls[e] : __bfloat162float(patch[(b * (N - 1) + n - 1) * ldp + e]);
+    x[r * ldx + e] = v;
+  }
+}
+
+// dpatch (bf16) = g[b,1+t,:] ; dpos[n,:] += sum_b g[b,n,:] ; dcls += sum_b g[b,0,:]
+__global__ void __launch_bounds__(256)
+assemble_bwd_kernel(const float* __restrict__ g, int64_t ldg, __nv_bfloat16* __restrict__ dpatch,
+                    int64_t ldp, float* __restrict__ dpos, int64_t ldpos, float* __restrict__ dcls,
+                    int B, int N, int E) {
+  const int64_t total = static_cast<int64_t>(N) * E;
+  for (int64_t t = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; t < total;
+       t += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int e = static_cast<int>(t % E);
+    const int n = static_cast<int>(t / E);
+    float acc = 0.f;
+    for (int b = 0; b < B; ++b) {
+      const float v = g[(static_cast<int64_t>(b) * N + n) * ldg + e];
+      acc += v;
+      if (n > 0) dpatch[(static_cast<int64_t>(b) * (N - 1) + n - 1) * ldp + e] = __float2bfloat16_rn(v);
+    }
+    if (dpos) dpos[static_cast<int64_t>(n) * ldpos + e] += acc;
+    if (n == 0 && dcls) dcls[e] += acc;
+  }
+}
+
+// pooled[b,e] = mean_{n>=first} y[b,n,e]  (first = 1 for gp, pooling skips cls)
+__global__ void __launch_bounds__(256)
+pool_fwd_kernel(const float* __restrict__ y, int64_t ldy, __nv_bfloat16* __restrict__ out, int64_t ldo,
+                int B, int N, int E, int first, int count) {
+  const int64_t total = static_cast<int64_t>(B) * E;
+  for (int64_t t = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; t < total;
+       t += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int e = static_cast<int>(t % E);
+    const int64_t b = t / E;
+    float acc = 0.f;
+    for (int n = first; n < first + count; ++n) acc += y[(b * N + n) * ldy + e];
+    out[b * ldo + e] = __float2bfloat16_rn(acc / count);
+  }
+}
+
+// dy[b,n,e] = dpooled[b,e] / count for first <= n < first+count, else 0
+__global__ void __launch_bounds__(256)
+pool_bwd_kernel(const __nv_bfloat16* __restrict__ dp, int64_t lddp, float* __restrict__ dy, int64_t lddy,
+                int B, int N, int E, int first, int count) {
+  const int64_t total = static_cast<int64_t>(B) * N * E;
+  const float inv = 1.0f / count;
+  for (int64_t t = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; t < total;
+       t += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int e = static_cast<int>(t % E);
+    const int64_t r = t / E;
+    const int n = static_cast<int>(r % N);
+    const int64_t b = r / N;
+    dy[r * lddy + e] = (n >= first && n < first + count) ? inv * __bfloat162float(dp[b * lddp + e]) : 0.f;
+  }
+}
+
+// out_bf16[r,c] = bf16(scale[r / rows_per] * in[r,c]); optional fused bias gradient
+// dbias[c] += sum_r out[r,c] (per-thread partials over a column strip -> global atomics).
+__global__ void __launch_bounds__(256)
+cast_scale_kernel(const float* __restrict__ in, int64_t ldi, __nv_bfloat16* __restrict__ out, int64_t ldo,
+                  const float* __restrict__ scale, int rows_per, float* __restrict__ dbias, int64_t rows,
+                  int cols) {
+  // 2-D tiling: blockDim.x covers columns (x4), rows strided by gridDim.y
+  const int c = (blockIdx.x * blockDim.x + threadIdx.x) << 2;
+  if (c >= cols) return;
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  for (int64_t r = blockIdx.y; r < rows; r += gridDim.y) {
+    const float s = scale ? __ldg(scale + r / rows_per) : 1.0f;
+    const float4 v = __ldg(reinterpret_cast<const float4*>(in + r * ldi + c));
+    const __nv_bfloat162 lo = __floats2bfloat162_rn(s * v.x, s * v.y);
+    const __nv_bfloat162 hi = __floats2bfloat162_rn(s * v.z, s * v.w);
+    uint2 o;
+    o.x = *reinterpret_cast<const uint32_t*>(&lo);
+    o.y = *reinterpret_cast<const uint32_t*>(&hi);
+    *reinterpret_cast<uint2*>(out + r * ldo + c) = o;
+    a0 += __bfloat162float(lo.x); a1 += __bfloat162float(lo.y);
+    a2 += __bfloat162float(hi.x); a3 += __bfloat162float(hi.y);
+  }
+  if (dbias) {
+    atomicAdd(dbias + c, a0);
+    if (c + 1 < cols) atomicAdd(dbias + c + 1, a1);
+    if (c + 2 < cols) atomicAdd(dbias + c + 2, a2);
+    if (c + 3 < cols) atomicAdd(dbias + c + 3, a3);
+  }
+}
+
+// dbias[c] += sum_r dy[r,c]  (bf16 input)
+__global__ void __launch_bounds__(256)
+colsum_kernel(const __nv_bfloat16* __restrict__ dy, int64_t ld, float* __restrict__ dbias, int64_t rows,
+              int cols) {
+  const int c = (blockIdx.x * blockDim.x + threadIdx.x) << 1;
+  if (c >= cols) return;
+  float a0 = 0.f, a1 = 0.f;
+  for (int64_t r = blockIdx.y; r < rows; r += gridDim.y) {
+    const float2 v = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(dy + r * ld + c));
+    a0 += v.x;
+    a1 += v.y;
+  }
+  atomicAdd(dbias + c, a0);
+  if (c + 1 < cols) atomicAdd(dbias + c + 1, a1);
+}
+
+struct PackSrc {
+  const float* src;
+  float* grad;
+  int nb, row_off;
+  int64_t stride_b, stride_d;
+};
+
+// dst[T][64][64] bf16: rows [row_off, row_off+nb) <- src[t][b][d] (any strides), zeros elsewhere
+__global__ void __launch_bounds__(256)
+pack_tables_kernel(__nv_bfloat16* __restrict__ dst, PackSrc s0, PackSrc s1, int64_t table_stride0,
+                   int64_t table_stride1, int D) {
+  const int t = blockIdx.x;
+  for (int i = threadIdx.x; i < 64 * 64; i += blockDim.x) {
+    const int r = i >> 6, d = i & 63;
+    float v = 0.f;
+    if (d < D) {
+      if (s0.src && r >= s0.row_off && r < s0.row_off + s0.nb)
+        v = s0.src[t * table_stride0 + (r - s0.row_off) * s0.stride_b + d * s0.stride_d];
+      else if (s1.src && r >= s1.row_off && r < s1.row_off + s1.nb)
+        v = s1.src[t * table_stride1 + (r - s1.row_off) * s1.stride_b + d * s1.stride_d];
+    }
+    dst[(static_cast<int64_t>(t) * 64 + r) * 64 + d] = __float2bfloat16_rn(v);
+  }
+}
+
+// grad[t][b][d] += dpack[t][row_off+b][d]
+__global__ void __launch_bounds__(256)
+unpack_grads_kernel(const float* __restrict__ dpack, PackSrc s0, PackSrc s1, int64_t table_stride0,
+                    int64_t table_stride1, int D) {
+  const int t = blockIdx.x;
+  for (int i = threadIdx.x; i < 64 * 64; i += blockDim.x) {
+    const int r = i >> 6, d = i & 63;
+    if (d >= D) continue;
+    const float v = dpack[(static_cast<int64_t>(t) * 64 + r) * 64 + d];
+    if (s0.grad && r >= s0.row_off && r < s0.row_off + s0.nb)
+      s0.grad[t * table_stride0 + (r - s0.row_off) * s0.stride_b + d * s0.stride_d] += v;
+    else if (s1.grad && r >= s1.row_off && r < s1.row_off + s1.nb)
+      s1.grad[t * table_stride1 + (r - s1.row_off) * s1.stride_b + d * s1.stride_d] += v;
+  }
+}
+
+}  // namespace
+}  // namespace cb
+
+using namespace cb;
+
+extern "C" int cream_patch_im2col(const float* images, void* out_bf16, int64_t ldo, int B, int C, int H,
+                                  int W, int P, void* stream) {
+  CB_REQUIRE(images && out_bf16 && B > 0, "null pointer");
+  CB_REQUIRE(H % P == 0 && W % P == 0 && P % 4 == 0 && W % 4 == 0 && ldo % 4 == 0, "patch geometry");
+  const int64_t work = static_cast<int64_t>(B) * (H / P) * (W / P) * (C * P * P / 4);
+  im2col_kernel<<<grid_for(work, 256, 16), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      images, static_cast<__nv_bfloat16*>(out_bf16), ldo, B, C, H, W, P);
+  return check_last("im2col_kernel");
+}
+
+extern "C" int cream_tokens_assemble_fwd(const void* patch_bf16, int64_t ldp, const float* cls,
+                                         const float* pos, int64_t ldpos, float* x, int64_t ldx, int B,
+                                         int N, int E, void* stream) {
+  CB_REQUIRE(patch_bf16 && cls && x && B > 0 && N > 1 && E > 0, "bad args");
+  assemble_fwd_kernel<<<grid_for(static_cast<int64_t>(B) * N * E, 256, 16), 256, 0,
+                        static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(patch_bf16), ldp, cls, pos, ldpos, x, ldx, B, N, E);
+  return check_last("assemble_fwd_kernel");
+}
+
+extern "C" int cream_tokens_assemble_bwd(const float* g, int64_t ldg, void* dpatch_bf16, int64_t ldp,
+                                         float* dpos, int64_t ldpos, float* dcls, int B, int N, int E,
+                                         void* stream) {
+  CB_REQUIRE(g && dpatch_bf16 && B > 0 && N > 1 && E > 0, "bad args");
+  assemble_bwd_kernel<<<grid_for(static_cast<int64_t>(N) * E, 256), 256, 0,
+                        static_cast<cudaStream_t>(stream)>>>(
+      g, ldg, static_cast<__nv_bfloat16*>(dpatch_bf16), ldp, dpos, ldpos, dcls, B, N, E);
+  return check_last("assemble_bwd_kernel");
+}
+
+extern "C" int cream_pool_fwd(const float* y, int64_t ldy, void* out_bf16, int64_t ldo, int B, int N,
+                              int E, int first, int count, void* stream) {
+  CB_REQUIRE(y && out_bf16 && count > 0 && first >= 0 && first + count <= N, "bad args");
+  pool_fwd_kernel<<<grid_for(static_cast<int64_t>(B) * E, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      y, ldy, static_cast<__nv_bfloat16*>(out_bf16), ldo, B, N, E, first, count);
+  return check_last("pool_fwd_kernel");
+}
+
+extern "C" int cream_pool_bwd(const void* dpooled_bf16, int64_t lddp, float* dy, int64_t lddy, int B,
+                              int N, int E, int first, int count, void* stream) {
+  CB_REQUIRE(dpooled_bf16 && dy && count > 0, "bad args");
+  pool_bwd_kernel<<<grid_for(static_cast<int64_t>(B) * N * E, 256, 16), 256, 0,
+                    static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(dpooled_bf16), lddp, dy, lddy, B, N, E, first, count);
+  return check_last("pool_bwd_kernel");
+}
+
+extern "C" int cream_cast_scale(const float* in, int64_t ldi, void* out_bf16, int64_t ldo,
+                                const float* row_scale, int rows_per_scale, float* dbias, int64_t rows,
+                                int cols, void* stream) {
+  if (rows == 0 || cols == 0) return CREAM_OK;
+  CB_REQUIRE(in && out_bf16, "null pointer");
+  CB_REQUIRE(ldi % 4 == 0 && ldo % 4 == 0 && cols % 4 == 0, "cols and pitches must be multiples of 4");
+  dim3 block(64), grid(ceil_div(cols / 4, 64), static_cast<unsigned>(std::min<int64_t>(rows, kNumSMs * 8)));
+  cast_scale_kernel<<<grid, block, 0, static_cast<cudaStream_t>(stream)>>>(
+      in, ldi, static_cast<__nv_bfloat16*>(out_bf16), ldo, row_scale, rows_per_scale > 0 ? rows_per_scale : 1,
+      dbias, rows, cols);
+  return check_last("cast_scale_kernel");
+}
+
+extern "C" int cream_bias_grad(const void* dy_bf16, int64_t ld, float* dbias, int64_t rows, int cols,
+                               void* stream) {
+  if (rows == 0 || cols == 0) return CREAM_OK;
+  CB_REQUIRE(dy_bf16 && dbias && ld % 2 == 0, "bad args");
+  dim3 block(64), grid(ceil_div(ceil_div(cols, 2), 64), static_cast<unsigned>(std::min<int64_t>(rows, kNumSMs * 8)));
+  colsum_kernel<<<grid, block, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(dy_bf16), ld, dbias, rows, cols);
+  return check_last("colsum_kernel");
+}
+
+extern "C" int cream_pack_tables(void* dst_bf16, int num_tables, int head_dim, const float* src0, int nb0,
+                                 int row_off0, int64_t stride_t0, int64_t stride_b0, int64_t stride_d0,
+                                 const float* src1, int nb1, int row_off1, int64_t stride_t1,
+                                 int64_t stride_b1, int64_t stride_d1, void* stream) {
+  CB_REQUIRE(dst_bf16 && num_tables > 0 && head_dim > 0 && head_dim <= 64, "bad args");
+  CB_REQUIRE(row_off0 + nb0 <= 64 && row_off1 + nb1 <= 64, "packed rows exceed 64");
+  PackSrc a{src0, nullptr, nb0, row_off0, stride_b0, stride_d0};
+  PackSrc b{src1, nullptr, nb1, row_off1, stride_b1, stride_d1};
+  pack_tables_kernel<<<num_tables, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<__nv_bfloat16*>(dst_bf16), a, b, stride_t0, stride_t1, head_dim);
+  return check_last("pack_tables_kernel");
+}
+
+extern "C" int cream_unpack_table_grads(const float* dpack, int num_tables, int head_dim, float* grad0,
+                                        int nb0, int row_off0, int64_t stride_t0, int64_t stride_b0,
+                                        int64_t stride_d0, float* grad1, int nb1, int row_off1,
+                                        int64_t stride_t1, int64_t stride_b1, int64_t stride_d1,
+                                        void* stream) {
+  CB_REQUIRE(dpack && num_tables > 0 && head_dim > 0 && head_dim <= 64, "bad args");
+  PackSrc a{nullptr, grad0, nb0, row_off0, stride_b0, stride_d0};
+  PackSrc b{nullptr, grad1, nb1, row_off1, stride_b1, stride_d1};
+  unpack_grads_kernel<<<num_tables, 256, 0, static_cast<cudaStream_t>(stream)>>>(dpack, a, b, stride_t0,
+                                                                              stride_t1, head_dim);
+  return check_last("unpack_grads_kernel");
+}

@@ -49,8 +49,9 @@ const char* cream_rpe_index_version(void);
  *   fwd: Y[b,h,i,j] = input[b,h,i,index[i,j]]       input strides s0..s3 (elements),
  *        index (Lq,Lk) int32 contiguous, Y (B,H,Lq,Lk) contiguous.
  *   bwd: grad_input[b,h,i,index[i,j]] += grad_output[b,h,i,j]; grad_input is
- *        (B,H,Lq,nb) contiguous and caller-zeroed (rpe_index.py:51).  Deterministic
- *        (segmented per-row reduction, no global atomics).
+ *        (B,H,Lq,nb) contiguous and caller-zeroed (rpe_index.py:51).  Per-row
+ *        shared-memory histogram, one coalesced read-modify-write per row (the
+ *        reference issues one global atomic per element).
  * ------------------------------------------------------------------------- */
 int cream_rpe_index_fwd(const void* input, const int32_t* index, void* out, int B, int H, int Lq,
                         int Lk, int num_buckets, int64_t s0, int64_t s1, int64_t s2, int64_t s3,
@@ -126,6 +127,102 @@ typedef struct cream_gemm_desc {
 } cream_gemm_desc;
 
 int cream_gemm_bf16(const cream_gemm_desc* desc, void* stream);
+
+/* ------------------------------------------------------------------------- *
+ * Fused attention with relative-position terms (tcgen05 QK^T / PV, RPE bucket gather
+ * fused into the softmax).  Replaces AttentionSuper.forward's attention core
+ * (AutoFormer/model/module/multihead_super.py:135-154) and RPEAttention.forward's
+ * (iRPE/DeiT-with-iRPE/rpe_vision_transformer.py:73-92, irpe.py:585-687).
+ *
+ *   S[i,j] = scale * (q_i . k_j + sum_t q_i . TK_t[idx_t[i,j]]) + bias[idx_a[i,j]]
+ *   P = softmax_j(S);  O[i] = sum_j P[i,j] * (v_j + sum_t TV_t[idx_vt[i,j]])
+ *
+ * qkv : bf16 (B*N, ld_qkv), columns [q: H*64 | k: H*64 | v: H*64] — the layout
+ *       qkv(x).reshape(B, N, 3, H, 64) of the reference.
+ * tk_pack / tv_pack : bf16 (T, 64, 64) "packed tables": row = bucket id (two tables of
+ *       <= 32 buckets at rows [0,32) and [32,64), or one table of <= 64), col = head-dim
+ *       channel; T = H if tables_per_head else 1.  NULL = no contextual term.
+ * idx_* : uint8 (N, ld_idx) bucket ids ALREADY offset into the packed rows (< 64);
+ *       ld_idx % 16 == 0, ld_idx >= roundup(N,16), padding entries 0.  idx_b / idx_vb
+ *       are the second table's ids (AutoFormer horizontal table) or NULL.
+ * bias_pack : fp32 (T, 64) bias-mode table gathered with idx_a, or NULL.
+ * out : bf16 (B*N, ld_out) columns H*64;  lse: fp32 (B, H, N) log-sum-exp, or NULL.
+ * ------------------------------------------------------------------------- */
+typedef struct cream_attn_desc {
+  int B, H, N, head_dim;
+  float scale;
+  const void* qkv; int64_t ld_qkv;
+  void* out; int64_t ld_out;
+  float* lse;
+  const void* tk_pack; const void* tv_pack; int tables_per_head;
+  const uint8_t* idx_a; const uint8_t* idx_b; const uint8_t* idx_va; const uint8_t* idx_vb;
+  int ld_idx;
+  const float* bias_pack;
+  /* ---- backward only (cream_attn_bwd) ---- */
+  const void* dout; int64_t ld_dout;   /* bf16 (B*N, ld_dout)                              */
+  void* dqkv; int64_t ld_dqkv;         /* bf16 (B*N, ld_dqkv), same column layout as qkv    */
+  float* dtk_pack; float* dtv_pack;    /* fp32 (T, 64, 64) accumulated (+=), caller-zeroed  */
+  float* dbias_pack;                   /* fp32 (T, 64) accumulated, or NULL                 */
+  void* workspace; int64_t workspace_bytes; /* see cream_attn_bwd_workspace_bytes          */
+} cream_attn_desc;
+
+int cream_attn_fwd(const cream_attn_desc* desc, void* stream);
+int cream_attn_bwd(const cream_attn_desc* desc, void* stream);
+int64_t cream_attn_bwd_workspace_bytes(int B, int H, int N);
+
+/* ------------------------------------------------------------------------- *
+ * Sliced LayerNorm (AutoFormer/model/module/layernorm_super.py:26-37; fp32 statistics).
+ *   fwd: out = LN(x[:, :E]) * gamma[:E] + beta[:E]; out bf16 (A operand of the next GEMM)
+ *        or fp32 (out_f32 != 0); mean / rstd (rows) saved for backward (may be NULL).
+ *   bwd: dx = resid_grad + dLN/dx (resid_grad may be NULL); dgamma/dbeta accumulated (+=).
+ * ------------------------------------------------------------------------- */
+int cream_layernorm_fwd(const float* x, int64_t ldx, const float* gamma, const float* beta, float eps,
+                        void* out, int64_t ldo, int out_f32, float* mean, float* rstd, int64_t rows,
+                        int E, void* stream);
+int cream_layernorm_bwd(const void* dy, int64_t lddy, int dy_f32, const float* x, int64_t ldx,
+                        const float* gamma, const float* mean, const float* rstd,
+                        const float* resid_grad, int64_t ldrg, float* dx, int64_t lddx, float* dgamma,
+                        float* dbeta, int64_t rows, int E, void* stream);
+
+/* ------------------------------------------------------------------------- *
+ * Patch embedding / token assembly / pooling glue.
+ * ------------------------------------------------------------------------- */
+/* images (B,C,H,W) fp32 -> (B*(H/P)*(W/P), C*P*P) bf16 patches; the 16x16/16 conv of
+ * PatchembedSuper.forward (embedding_super.py:33-40) is then one sliced GEMM against
+ * proj.weight.view(E*, C*P*P)[:E]. */
+int cream_patch_im2col(const float* images, void* out_bf16, int64_t ldo, int B, int C, int H, int W,
+                       int P, void* stream);
+/* x[b,0] = cls[:E] + pos[0,:E]; x[b,1+t] = patch[b*T+t] + pos[1+t,:E]
+ * (supernet_transformer.py:150-155); pos may be NULL (abs_pos = False). */
+int cream_tokens_assemble_fwd(const void* patch_bf16, int64_t ldp, const float* cls, const float* pos,
+                              int64_t ldpos, float* x, int64_t ldx, int B, int N, int E, void* stream);
+int cream_tokens_assemble_bwd(const float* g, int64_t ldg, void* dpatch_bf16, int64_t ldp, float* dpos,
+                              int64_t ldpos, float* dcls, int B, int N, int E, void* stream);
+/* mean over tokens [first, first+count) (gp pooling, supernet_transformer.py:164-165). */
+int cream_pool_fwd(const float* y, int64_t ldy, void* out_bf16, int64_t ldo, int B, int N, int E,
+                   int first, int count, void* stream);
+int cream_pool_bwd(const void* dpooled_bf16, int64_t lddp, float* dy, int64_t lddy, int B, int N, int E,
+                   int first, int count, void* stream);
+/* out_bf16 = bf16(row_scale[r / rows_per_scale] * in); dbias (+=) column sums of out, or NULL. */
+int cream_cast_scale(const float* in, int64_t ldi, void* out_bf16, int64_t ldo, const float* row_scale,
+                     int rows_per_scale, float* dbias, int64_t rows, int cols, void* stream);
+/* dbias[c] += sum_r dy[r, c]. */
+int cream_bias_grad(const void* dy_bf16, int64_t ld, float* dbias, int64_t rows, int cols, void* stream);
+
+/* ------------------------------------------------------------------------- *
+ * Relative-position table packs: (T, 64, 64) bf16, row = packed bucket id.
+ * Up to two source tables src[t][b][d] with arbitrary element strides
+ * (AutoFormer embeddings_table_v/h (30, 64); iRPE lookup_table_weight (H|1, 64, nb)
+ * transposed or (H|1, nb, 64)).  unpack adds the packed gradient back (+=).
+ * ------------------------------------------------------------------------- */
+int cream_pack_tables(void* dst_bf16, int num_tables, int head_dim, const float* src0, int nb0,
+                      int row_off0, int64_t stride_t0, int64_t stride_b0, int64_t stride_d0,
+                      const float* src1, int nb1, int row_off1, int64_t stride_t1, int64_t stride_b1,
+                      int64_t stride_d1, void* stream);
+int cream_unpack_table_grads(const float* dpack, int num_tables, int head_dim, float* grad0, int nb0,
+                             int row_off0, int64_t stride_t0, int64_t stride_b0, int64_t stride_d0,
+                             float* grad1, int nb1, int row_off1, int64_t stride_t1, int64_t stride_b1,
+                             int64_t stride_d1, void* stream);
 
 #ifdef __cplusplus
 }
