@@ -1,0 +1,238 @@
+"""torch.autograd.Functions behind the drop-in modules (AutoFormer model.module.* and the
+iRPE attention).  Each forward/backward is a handful of cream_b200 C-ABI launches; torch
+only carries tensors and the autograd graph.  Gradients of sliced parameters are returned
+as full-size tensors that are zero outside the sampled slice, exactly like autograd through
+the reference's slicing views."""
+from __future__ import annotations
+
+import torch
+
+from .. import _lib, ops
+from .._lib import check
+
+_p, _stream = ops._p, ops._stream
+
+
+def _f32_2d(x: torch.Tensor) -> torch.Tensor:
+    x2 = x.reshape(-1, x.shape[-1])
+    if x2.dtype != torch.float32 or x2.stride(1) != 1:
+        x2 = x2.float().contiguous()
+    return x2
+
+
+class SlicedLinearFn(torch.autograd.Function):
+    """y = x @ W[:out, :in]^T + b[:out]  (Linear_super.py:52-54) or, with is_qkv, the
+    interleaved-row QKV slice of qkv_super.py:45-55,72-83."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, in_dim, out_dim, is_qkv):
+        if not x.is_cuda:
+            raise RuntimeError("cream_b200 modules run on CUDA (sm_100a) tensors only")
+        assert x.shape[-1] == in_dim, f"input feature dim {x.shape[-1]} != sampled in_dim {in_dim}"
+        x2 = ops.as_bf16_2d(x)
+        if is_qkv:
+            assert out_dim % (3 * ops.HEAD_DIM) == 0, "sampled qkv width must be 3*64*heads"
+            heads = out_dim // (3 * ops.HEAD_DIM)
+            y = ops.qkv_fwd(x2, ops.SHADOWS.get(weight, qkv=True), heads, in_dim, weight.shape[0] // 3, bias)
+        else:
+            y = ops.linear_fwd(x2, ops.SHADOWS.get(weight), out_dim, in_dim, bias)
+        ctx.save_for_backward(x2, weight)
+        ctx.meta = (in_dim, out_dim, is_qkv, bias is not None, x.dtype, tuple(x.shape))
+        return y.reshape(*x.shape[:-1], out_dim)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, weight = ctx.saved_tensors
+        in_dim, out_dim, is_qkv, has_bias, x_dtype, x_shape = ctx.meta
+        dy2 = ops.as_bf16_2d(dy)
+        dx = dw = db = None
+        if is_qkv:
+            heads = out_dim // (3 * ops.HEAD_DIM)
+            if ctx.needs_input_grad[0]:
+                dx = ops.qkv_dgrad(dy2, ops.SHADOWS.get(weight, qkv=True), heads, in_dim, weight.shape[0] // 3)
+            if ctx.needs_input_grad[1]:
+                dw = torch.zeros_like(weight)
+                ops.qkv_wgrad(dy2, x2, heads, in_dim, dw)
+        else:
+            if ctx.needs_input_grad[0]:
+                dx = ops.linear_dgrad(dy2, ops.SHADOWS.get(weight), out_dim, in_dim)
+            if ctx.needs_input_grad[1]:
+                dw = torch.zeros_like(weight)
+                ops.linear_wgrad(dy2, x2, out_dim, in_dim, dw)
+        if has_bias and ctx.needs_input_grad[2]:
+            db = torch.zeros(weight.shape[0], dtype=torch.float32, device=weight.device)
+            ops.bias_grad(dy2, db)
+        if dx is not None:
+            dx = dx.reshape(x_shape).to(x_dtype)
+        return dx, dw, db, None, None, None
+
+
+class SlicedLayerNormFn(torch.autograd.Function):
+    """F.layer_norm over the first E features with weight[:E], bias[:E]
+    (layernorm_super.py:35-37); fp32 in, fp32 out (as under the reference's autocast)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, E, eps):
+        if not x.is_cuda:
+            raise RuntimeError("cream_b200 modules run on CUDA (sm_100a) tensors only")
+        assert x.shape[-1] == E
+        x2 = _f32_2d(x)
+        y, mean, rstd = ops.layernorm_fwd(x2, weight, bias, eps, E, out_f32=True)
+        ctx.save_for_backward(x2, weight, mean, rstd)
+        ctx.meta = (E, x.dtype, tuple(x.shape))
+        return y.reshape(x.shape)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, weight, mean, rstd = ctx.saved_tensors
+        E, x_dtype, x_shape = ctx.meta
+        dy2 = _f32_2d(dy)
+        dg = torch.zeros_like(weight)
+        db = torch.zeros_like(weight)
+        dx = ops.layernorm_bwd(dy2, x2, weight, mean, rstd, E, dg, db)
+        return dx.reshape(x_shape).to(x_dtype), dg, db, None, None
+
+
+class PatchEmbedFn(torch.autograd.Function):
+    """conv2d(x, W[:E], b[:E], stride=P).flatten(2).transpose(1, 2) (embedding_super.py:33-40)
+    as im2col + sliced GEMM; returns (B, T, E) bf16."""
+
+    @staticmethod
+    def forward(ctx, images, weight, bias, E, P):
+        if not images.is_cuda:
+            raise RuntimeError("cream_b200 modules run on CUDA (sm_100a) tensors only")
+        B, Cin, H, W = images.shape
+        img = images.float().contiguous()
+        T = (H // P) * (W // P)
+        kdim = Cin * P * P
+        cols = ops.empty_bf16(B * T, kdim, images.device)
+        check(_lib.load().cream_patch_im2col(_p(img), _p(cols), cols.stride(0), B, Cin, H, W, P, _stream()),
+              "cream_patch_im2col")
+        y = ops.linear_fwd(cols, ops.SHADOWS.get(weight), E, kdim, bias)
+        ctx.save_for_backward(cols, weight)
+        ctx.meta = (E, kdim, bias is not None)
+        return y.reshape(B, T, E)
+
+    @staticmethod
+    def backward(ctx, dy):
+        cols, weight = ctx.saved_tensors
+        E, kdim, has_bias = ctx.meta
+        if ctx.needs_input_grad[0]:
+            raise NotImplementedError("gradient w.r.t. the input image is not part of the supernet path")
+        dy2 = ops.as_bf16_2d(dy)
+        dw = db = None
+        if ctx.needs_input_grad[1]:
+            dw = torch.zeros_like(weight)
+            ops.linear_wgrad(dy2, cols, E, kdim, dw)
+        if has_bias and ctx.needs_input_grad[2]:
+            db = torch.zeros(weight.shape[0], dtype=torch.float32, device=weight.device)
+            ops.bias_grad(dy2, db)
+        return None, dw, db, None, None
+
+
+def _pack_pair(tv, th):
+    pack = ops.new_pack(1, tv.device)
+    nb = tv.shape[0]
+    ops.pack_tables(pack, 1, tv, nb, 0, (0, tv.stride(0), tv.stride(1)), th, nb, 32, (0, th.stride(0), th.stride(1)))
+    return pack
+
+
+class AutoformerAttentionFn(torch.autograd.Function):
+    """Attention core of AttentionSuper.forward (multihead_super.py:135-154) on a
+    (B, N, 3*64h) qkv tensor; optional tables = (k_v, k_h, v_v, v_h) each (2*max_rel+2, 64)."""
+
+    @staticmethod
+    def forward(ctx, qkv, heads, scale, max_rel, *tables):
+        B, N, W3 = qkv.shape
+        assert W3 == 3 * ops.HEAD_DIM * heads
+        qkv2 = ops.as_bf16_2d(qkv)
+        tk = tv = None
+        idx = (None, None, None, None)
+        if tables:
+            assert tables[0].shape[1] == ops.HEAD_DIM and tables[0].dtype == torch.float32
+            iv, ih, _, _ = ops.autoformer_index_tables(N, max_rel, qkv.device)
+            idx = (iv, ih, iv, ih)
+            tk = _pack_pair(tables[0].detach(), tables[1].detach())
+            tv = _pack_pair(tables[2].detach(), tables[3].detach())
+        out, lse = ops.attention_fwd(qkv2, B, heads, N, scale, tk=tk, tv=tv, idx=idx)
+        ctx.save_for_backward(qkv2, out, lse, tk, tv, *tables)
+        ctx.meta = (B, heads, N, scale, idx, qkv.dtype)
+        return out.reshape(B, N, ops.HEAD_DIM * heads)
+
+    @staticmethod
+    def backward(ctx, dout):
+        qkv2, out, lse, tk, tv, *tables = ctx.saved_tensors
+        B, heads, N, scale, idx, dtype = ctx.meta
+        d2 = ops.as_bf16_2d(dout)
+        dqkv, dtk, dtv, _ = ops.attention_bwd(qkv2, out, lse, d2, B, heads, N, scale, tk=tk, tv=tv, idx=idx)
+        grads = []
+        if tables:
+            for pair, dpack in ((tables[0:2], dtk), (tables[2:4], dtv)):
+                gv, gh = torch.zeros_like(pair[0]), torch.zeros_like(pair[1])
+                ops.unpack_table_grads(dpack, 1, gv, gv.shape[0], 0, (0, gv.stride(0), gv.stride(1)),
+                                       gh, gh.shape[0], 32, (0, gh.stride(0), gh.stride(1)))
+                grads += [gv, gh]
+        return (dqkv.reshape(B, N, -1).to(dtype), None, None, None, *grads)
+
+
+class IrpeAttentionFn(torch.autograd.Function):
+    """Attention core of RPEAttention.forward (rpe_vision_transformer.py:73-92) with iRPE on
+    keys and/or values.  qkv (B, N, 3*64h); rpe_k: contextual lookup_table_weight
+    (H|1, 64, nb) or bias lookup_table_bias (H|1, nb); rpe_v: (H|1, nb, 64); ids: int (N, N)
+    bucket ids (numpy, from ops.irpe_bucket_ids)."""
+
+    @staticmethod
+    def forward(ctx, qkv, heads, scale, ids, mode, rpe_k, rpe_v):
+        B, N, W3 = qkv.shape
+        assert W3 == 3 * ops.HEAD_DIM * heads
+        dev = qkv.device
+        qkv2 = ops.as_bf16_2d(qkv)
+        idx_t = ops.irpe_index_table_u8(ids, dev)
+        tk = tv = bias = None
+        per_head = False
+        nb = int(ids.max()) + 1
+        if rpe_k is not None:
+            per_head = rpe_k.shape[0] > 1
+            T = rpe_k.shape[0]
+            if mode == "bias":
+                bias = torch.zeros((T, ops.NB_PACK), dtype=torch.float32, device=dev)
+                bias[:, :rpe_k.shape[1]] = rpe_k.detach()
+            else:
+                assert rpe_k.shape[1] == ops.HEAD_DIM and rpe_k.shape[2] >= nb
+                tk = ops.new_pack(T, dev)
+                w = rpe_k.detach()   # (T, D, nb): bucket stride = stride(2), channel stride = stride(1)
+                ops.pack_tables(tk, T, w, w.shape[2], 0, (w.stride(0), w.stride(2), w.stride(1)))
+        if rpe_v is not None:
+            assert mode != "bias", "bias mode has no value-side table (irpe.py:489-491)"
+            per_head = per_head or rpe_v.shape[0] > 1
+            T = rpe_v.shape[0]
+            assert rpe_k is None or rpe_k.shape[0] == T, "k and v tables must agree on head sharing"
+            tv = ops.new_pack(T, dev)
+            w = rpe_v.detach()       # (T, nb, D)
+            ops.pack_tables(tv, T, w, w.shape[1], 0, (w.stride(0), w.stride(1), w.stride(2)))
+        idx = (idx_t if (tk is not None or bias is not None) else None, None, idx_t if tv is not None else None, None)
+        out, lse = ops.attention_fwd(qkv2, B, heads, N, scale, tk=tk, tv=tv, per_head=per_head, idx=idx, bias=bias)
+        ctx.save_for_backward(qkv2, out, lse, tk, tv, bias, rpe_k, rpe_v)
+        ctx.meta = (B, heads, N, scale, idx, per_head, mode, qkv.dtype)
+        return out.reshape(B, N, ops.HEAD_DIM * heads)
+
+    @staticmethod
+    def backward(ctx, dout):
+        qkv2, out, lse, tk, tv, bias, rpe_k, rpe_v = ctx.saved_tensors
+        B, heads, N, scale, idx, per_head, mode, dtype = ctx.meta
+        d2 = ops.as_bf16_2d(dout)
+        dqkv, dtk, dtv, dbias = ops.attention_bwd(qkv2, out, lse, d2, B, heads, N, scale, tk=tk, tv=tv,
+                                                  per_head=per_head, idx=idx, bias=bias)
+        gk = gv = None
+        if rpe_k is not None:
+            gk = torch.zeros_like(rpe_k)
+            if mode == "bias":
+                gk += dbias[:, :rpe_k.shape[1]]
+            else:
+                T = rpe_k.shape[0]
+                ops.unpack_table_grads(dtk, T, gk, gk.shape[2], 0, (gk.stride(0), gk.stride(2), gk.stride(1)))
+        if rpe_v is not None:
+            gv = torch.zeros_like(rpe_v)
+            T = rpe_v.shape[0]
+            ops.unpack_table_grads(dtv, T, gv, gv.shape[1], 0, (gv.stride(0), gv.stride(1), gv.stride(2)))
+        return dqkv.reshape(B, N, -1).to(dtype), None, None, None, None, gk, gv

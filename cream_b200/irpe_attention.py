@@ -1,0 +1,85 @@
+"""DeiT attention with image relative position encoding on the fused B200 kernel.
+
+`RPEAttention` mirrors iRPE/DeiT-with-iRPE/rpe_vision_transformer.py:45-97 (constructor,
+parameter names `qkv`, `proj`, `rpe_q/rpe_k/rpe_v.lookup_table_{weight,bias}`), with the
+reference's q@k^T + rpe_k(q) gather, softmax, attn@v + rpe_v(attn) executed by ONE kernel.
+Supported in this round: rpe on k and/or v (contextual), bias mode on k, shared or per-head
+tables, methods euclidean / quant / product (<= 64 buckets); rpe on q and the cross method
+are the next rows of SURVEY.md §8f.
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+import torch.nn as nn
+
+from . import ops
+from .autoformer.functional import IrpeAttentionFn, SlicedLinearFn
+
+METHODS = {"euc": 0, "quant": 1, "product": 3}
+
+
+class IrpeTable(nn.Module):
+    """Parameter holder with the reference's iRPE attribute names (irpe.py:449-496)."""
+
+    def __init__(self, head_dim, num_heads, mode, transposed, num_buckets):
+        super().__init__()
+        self.head_dim, self.num_heads, self.mode = head_dim, num_heads, mode
+        self.transposed, self.num_buckets = transposed, num_buckets
+        if transposed:
+            if mode == 'bias':
+                self.lookup_table_bias = nn.Parameter(torch.zeros(num_heads, num_buckets))
+            else:
+                self.lookup_table_weight = nn.Parameter(torch.zeros(num_heads, head_dim, num_buckets))
+        else:
+            if mode == 'bias':
+                raise NotImplementedError("[Error] Bias non-transposed RPE does not exist.")
+            self.lookup_table_weight = nn.Parameter(torch.zeros(num_heads, num_buckets, head_dim))
+
+    @property
+    def table(self):
+        return self.lookup_table_bias if self.mode == 'bias' else self.lookup_table_weight
+
+
+class RPEAttention(nn.Module):
+    def __init__(self, dim, num_heads=8, qkv_bias=False, qk_scale=None, attn_drop=0., proj_drop=0.,
+                 rpe_on='k', method='product', mode='contextual', shared_head=True, ratio=1.9, skip=1):
+        super().__init__()
+        assert attn_drop == 0.0, "attention dropout is not supported by the fused kernel"
+        if 'q' in rpe_on:
+            raise NotImplementedError("iRPE on queries is not implemented yet (SURVEY.md §8f row 1)")
+        self.num_heads = num_heads
+        head_dim = dim // num_heads
+        assert head_dim == ops.HEAD_DIM, "fused attention kernel is built for head_dim 64"
+        self.scale = qk_scale or head_dim ** -0.5
+        self.qkv = nn.Linear(dim, dim * 3, bias=qkv_bias)
+        self.proj = nn.Linear(dim, dim)
+        self.proj_drop = nn.Dropout(proj_drop)
+        self.method, self.mode, self.skip, self.ratio = METHODS[method], mode, skip, ratio
+        if mode == 'ctx':
+            self.mode = 'contextual'
+        beta_int = int(2 * ratio)
+        nb = ((2 * beta_int + 1) ** 2 if method == 'product' else 2 * beta_int + 1) + (1 if skip > 0 else 0)
+        assert nb <= ops.NB_PACK, "more than 64 buckets is not supported by the fused kernel"
+        self.num_buckets = nb
+        t_heads = 1 if shared_head else num_heads
+        self.rpe_q = None
+        self.rpe_k = IrpeTable(head_dim, t_heads, self.mode, True, nb) if 'k' in rpe_on else None
+        self.rpe_v = IrpeTable(head_dim, t_heads, self.mode, False, nb) if 'v' in rpe_on else None
+
+    def bucket_ids(self, L):
+        side = int(math.sqrt(L))
+        skip = L - side * side
+        ids, nb = ops.irpe_bucket_ids(self.method, side, side, skip, 1 * self.ratio, 2 * self.ratio, 8 * self.ratio)
+        assert nb == self.num_buckets
+        return ids
+
+    def forward(self, x):
+        B, N, C = x.shape
+        qkv = SlicedLinearFn.apply(x, self.qkv.weight, self.qkv.bias, C, 3 * C, False)   # (B, N, 3C) bf16
+        out = IrpeAttentionFn.apply(qkv, self.num_heads, float(self.scale), self.bucket_ids(N), self.mode,
+                                    self.rpe_k.table if self.rpe_k is not None else None,
+                                    self.rpe_v.table if self.rpe_v is not None else None)
+        out = SlicedLinearFn.apply(out, self.proj.weight, self.proj.bias, C, C, False)
+        return self.proj_drop(out)

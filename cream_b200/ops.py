@@ -1,0 +1,402 @@
+"""Tensor-level wrappers over the C ABI (torch is used for device memory and streams only).
+
+All functions launch on the current CUDA stream and never synchronise.  Activations are
+2-D bf16 tensors `(rows, cols)` with `stride(1) == 1` and a row pitch that is a multiple
+of 8 elements (see `empty_bf16`).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import (EPI_BF16, EPI_BF16_DGELU, EPI_BF16_GELU, EPI_F32, EPI_F32_ATOMIC, EPI_F32_RESID,
+                   AttnDesc, GemmDesc, check)
+
+HEAD_DIM = 64
+NB_PACK = 64
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _p(t) -> Optional[int]:
+    if t is None:
+        return None
+    if isinstance(t, int):
+        return t
+    return t.data_ptr()
+
+
+def round_up(a: int, b: int) -> int:
+    return (a + b - 1) // b * b
+
+
+def empty_bf16(rows: int, cols: int, device=None, zero: bool = False) -> torch.Tensor:
+    """(rows, cols) bf16 view over a buffer whose row pitch is a multiple of 8 elements."""
+    ld = round_up(max(cols, 1), 8)
+    buf = (torch.zeros if zero else torch.empty)((rows, ld), dtype=torch.bfloat16, device=device or "cuda")
+    return buf[:, :cols]
+
+
+def empty_f32(rows: int, cols: int, device=None, zero: bool = False) -> torch.Tensor:
+    ld = round_up(max(cols, 1), 4)
+    buf = (torch.zeros if zero else torch.empty)((rows, ld), dtype=torch.float32, device=device or "cuda")
+    return buf[:, :cols]
+
+
+def as_bf16_2d(x: torch.Tensor) -> torch.Tensor:
+    """Any (..., C) float tensor -> (rows, C) bf16 with an 8-aligned pitch (copy only if needed)."""
+    x2 = x.reshape(-1, x.shape[-1])
+    if x2.dtype == torch.bfloat16 and x2.stride(1) == 1 and x2.stride(0) % 8 == 0 and x2.data_ptr() % 16 == 0:
+        return x2
+    out = empty_bf16(x2.shape[0], x2.shape[1], x2.device)
+    out.copy_(x2)
+    return out
+
+
+def _check_2d(t: torch.Tensor, dtype, name: str, mult: int):
+    assert t.is_cuda and t.dtype == dtype and t.dim() == 2 and t.stride(1) == 1, f"{name}: bad tensor"
+    assert t.stride(0) % mult == 0, f"{name}: row pitch {t.stride(0)} not a multiple of {mult}"
+
+
+# --------------------------------------------------------------------------------------------
+# weight shadows
+# --------------------------------------------------------------------------------------------
+class ShadowCache:
+    """bf16 shadows of fp32 master weights, refreshed when the parameter's version changes
+    (i.e. once per optimizer step).  QKV weights are stored de-interleaved."""
+
+    def __init__(self):
+        self._store = {}
+
+    def get(self, w: torch.Tensor, qkv: bool = False) -> torch.Tensor:
+        key = (w.data_ptr(), qkv)
+        ent = self._store.get(key)
+        tag = (w._version, w.untyped_storage()._cdata, tuple(w.shape))
+        if ent is not None and ent[1] == tag:
+            return ent[0]
+        w2 = w.detach().reshape(w.shape[0], -1)
+        assert w2.dtype == torch.float32 and w2.is_contiguous()
+        rows, cols = w2.shape
+        sh = ent[0] if (ent is not None and ent[0].shape[0] == rows and ent[0].device == w.device) else \
+            torch.empty((rows, round_up(cols, 8)), dtype=torch.bfloat16, device=w.device)
+        lib = _lib.load()
+        if qkv:
+            assert rows % 3 == 0
+            check(lib.cream_shadow_qkv(_p(w2), _p(sh), rows // 3, cols, w2.stride(0), sh.stride(0), _stream()),
+                  "cream_shadow_qkv")
+        else:
+            check(lib.cream_shadow_cast(_p(w2), _p(sh), rows, cols, w2.stride(0), sh.stride(0), _stream()),
+                  "cream_shadow_cast")
+        self._store[key] = (sh, tag)
+        return sh
+
+    def clear(self):
+        self._store.clear()
+
+
+SHADOWS = ShadowCache()
+
+
+# --------------------------------------------------------------------------------------------
+# GEMM
+# --------------------------------------------------------------------------------------------
+def gemm(M, N, K, a, lda, b, ldb, out, ldo, epi, *, groups=1, a_mn=0, b_mn=0, a_group_off=0,
+         b_group_rows=0, k_groups=1, k_group_len=0, out_row_mul=1, out_g_row=0, out_g_col=0, aux=None,
+         ldaux=0, bias=None, resid=None, ldr=0, row_scale=None, rows_per_scale=1, alpha=1.0, split_k=0):
+    d = GemmDesc()
+    d.M, d.N, d.K, d.groups = M, N, K, groups
+    d.a, d.lda, d.a_mn, d.a_group_off = _p(a), lda, a_mn, a_group_off
+    d.b, d.ldb, d.b_mn, d.b_group_rows = _p(b), ldb, b_mn, b_group_rows
+    d.k_groups, d.k_group_len = k_groups, k_group_len
+    d.epi = epi
+    d.out, d.ldo = _p(out), ldo
+    d.out_row_mul, d.out_g_row, d.out_g_col = out_row_mul, out_g_row, out_g_col
+    d.aux, d.ldaux = _p(aux), ldaux
+    d.bias = _p(bias)
+    d.resid, d.ldr = _p(resid), ldr
+    d.row_scale, d.rows_per_scale = _p(row_scale), rows_per_scale
+    d.alpha, d.split_k = alpha, split_k
+    check(_lib.load().cream_gemm_bf16(C.byref(d), _stream()), "cream_gemm_bf16")
+
+
+def linear_fwd(x, w_sh, n_out, k_in, bias=None, *, epi=EPI_BF16, out=None, aux=None, resid=None,
+               row_scale=None, rows_per_scale=1):
+    """y = x[:, :k_in] @ W[:n_out, :k_in]^T (+ bias[:n_out]) with the chosen epilogue
+    (Linear_super.py:52-54 on the sampled slice; the slice is only extents + pitches)."""
+    _check_2d(x, torch.bfloat16, "x", 8)
+    M = x.shape[0]
+    if out is None:
+        out = empty_bf16(M, n_out, x.device) if epi in (EPI_BF16, EPI_BF16_GELU) else empty_f32(M, n_out, x.device)
+    gemm(M, n_out, k_in, x, x.stride(0), w_sh, w_sh.stride(0), out, out.stride(0), epi,
+         aux=aux, ldaux=aux.stride(0) if aux is not None else 0, bias=bias,
+         resid=resid, ldr=resid.stride(0) if resid is not None else 0,
+         row_scale=row_scale, rows_per_scale=rows_per_scale)
+    return out
+
+
+def linear_dgrad(dy, w_sh, n_out, k_in, *, epi=EPI_BF16, aux=None, out=None):
+    """dx = dy[:, :n_out] @ W[:n_out, :k_in]  (B operand read MN-major straight from the shadow)."""
+    _check_2d(dy, torch.bfloat16, "dy", 8)
+    M = dy.shape[0]
+    if out is None:
+        out = empty_bf16(M, k_in, dy.device)
+    gemm(M, k_in, n_out, dy, dy.stride(0), w_sh, w_sh.stride(0), out, out.stride(0), epi, b_mn=1,
+         aux=aux, ldaux=aux.stride(0) if aux is not None else 0)
+    return out
+
+
+def linear_wgrad(dy, x, n_out, k_in, dw_full, alpha=1.0):
+    """dW[:n_out, :k_in] += dy^T x, accumulated in place in the full-size fp32 gradient."""
+    _check_2d(dy, torch.bfloat16, "dy", 8)
+    _check_2d(x, torch.bfloat16, "x", 8)
+    dw2 = dw_full.reshape(dw_full.shape[0], -1)
+    assert dw2.dtype == torch.float32 and dw2.is_contiguous()
+    gemm(n_out, k_in, dy.shape[0], dy, dy.stride(0), x, x.stride(0), dw2, dw2.stride(0), EPI_F32_ATOMIC,
+         a_mn=1, b_mn=1, alpha=alpha)
+
+
+def qkv_fwd(x, wq_sh, heads, k_in, rows_per_group, bias=None):
+    """qkv_super.forward (qkv_super.py:45-55): three row blocks of the de-interleaved shadow."""
+    _check_2d(x, torch.bfloat16, "x", 8)
+    qd = HEAD_DIM * heads
+    out = empty_bf16(x.shape[0], 3 * qd, x.device)
+    gemm(x.shape[0], qd, k_in, x, x.stride(0), wq_sh, wq_sh.stride(0), out, out.stride(0), EPI_BF16,
+         groups=3, b_group_rows=rows_per_group, out_g_col=qd, bias=bias)
+    return out
+
+
+def qkv_dgrad(dqkv, wq_sh, heads, k_in, rows_per_group):
+    _check_2d(dqkv, torch.bfloat16, "dqkv", 8)
+    qd = HEAD_DIM * heads
+    out = empty_bf16(dqkv.shape[0], k_in, dqkv.device)
+    gemm(dqkv.shape[0], k_in, 3 * qd, dqkv, dqkv.stride(0), wq_sh, wq_sh.stride(0), out, out.stride(0),
+         EPI_BF16, b_mn=1, k_groups=3, k_group_len=qd, b_group_rows=rows_per_group)
+    return out
+
+
+def qkv_wgrad(dqkv, x, heads, k_in, dw_full):
+    """dW[3j+i, :k_in] += dqkv[:, i*64h + j]^T x — written in the reference's interleaved rows."""
+    qd = HEAD_DIM * heads
+    assert dw_full.dtype == torch.float32 and dw_full.is_contiguous()
+    gemm(qd, k_in, dqkv.shape[0], dqkv, dqkv.stride(0), x, x.stride(0), dw_full, dw_full.stride(0),
+         EPI_F32_ATOMIC, groups=3, a_mn=1, b_mn=1, a_group_off=qd, out_row_mul=3, out_g_row=1)
+
+
+def bias_grad(dy, dbias_full):
+    _check_2d(dy, torch.bfloat16, "dy", 2)
+    check(_lib.load().cream_bias_grad(_p(dy), dy.stride(0), _p(dbias_full), dy.shape[0], dy.shape[1], _stream()),
+          "cream_bias_grad")
+
+
+def cast_scale(g, row_scale=None, rows_per_scale=1, dbias=None):
+    """bf16(row_scale * g) with optional fused bias gradient (column sums)."""
+    _check_2d(g, torch.float32, "g", 4)
+    rows, cols = g.shape
+    assert cols % 4 == 0
+    out = empty_bf16(rows, cols, g.device)
+    check(_lib.load().cream_cast_scale(_p(g), g.stride(0), _p(out), out.stride(0), _p(row_scale), rows_per_scale,
+                                       _p(dbias), rows, cols, _stream()), "cream_cast_scale")
+    return out
+
+
+# --------------------------------------------------------------------------------------------
+# LayerNorm
+# --------------------------------------------------------------------------------------------
+def layernorm_fwd(x, gamma, beta, eps, E, *, out_f32=False, save_stats=True):
+    _check_2d(x, torch.float32, "x", 1)
+    rows = x.shape[0]
+    out = empty_f32(rows, E, x.device) if out_f32 else empty_bf16(rows, E, x.device)
+    mean = torch.empty(rows, dtype=torch.float32, device=x.device) if save_stats else None
+    rstd = torch.empty(rows, dtype=torch.float32, device=x.device) if save_stats else None
+    check(_lib.load().cream_layernorm_fwd(_p(x), x.stride(0), _p(gamma), _p(beta), eps, _p(out), out.stride(0),
+                                          int(out_f32), _p(mean), _p(rstd), rows, E, _stream()),
+          "cream_layernorm_fwd")
+    return out, mean, rstd
+
+
+def layernorm_bwd(dy, x, gamma, mean, rstd, E, dgamma_full, dbeta_full, resid_grad=None):
+    dy_f32 = dy.dtype == torch.float32
+    rows = x.shape[0]
+    dx = empty_f32(rows, E, x.device)
+    check(_lib.load().cream_layernorm_bwd(_p(dy), dy.stride(0), int(dy_f32), _p(x), x.stride(0), _p(gamma),
+                                          _p(mean), _p(rstd), _p(resid_grad),
+                                          resid_grad.stride(0) if resid_grad is not None else 0, _p(dx),
+                                          dx.stride(0), _p(dgamma_full), _p(dbeta_full), rows, E, _stream()),
+          "cream_layernorm_bwd")
+    return dx
+
+
+# --------------------------------------------------------------------------------------------
+# relative-position tables
+# --------------------------------------------------------------------------------------------
+_INDEX_CACHE = {}
+
+
+def _u8_table(idx: np.ndarray, offset: int, device) -> torch.Tensor:
+    n = idx.shape[0]
+    ld = round_up(n, 16)
+    buf = np.zeros((n, ld), dtype=np.uint8)
+    buf[:, :n] = (idx + offset).astype(np.uint8)
+    return torch.from_numpy(buf).to(device)
+
+
+def autoformer_index_tables(n_tokens: int, max_rel: int, device):
+    """uint8 gather tables for the AutoFormer 2-D relative position (multihead_super.py:40-59):
+    idx_v in packed rows [0,32), idx_h offset into [32,64).  Built once per (N, device)."""
+    key = ("af", n_tokens, max_rel, str(device))
+    if key not in _INDEX_CACHE:
+        grid = int(round((n_tokens - 1) ** 0.5))
+        assert grid * grid + 1 == n_tokens, "AutoFormer relative position needs a square grid + cls"
+        assert 2 * max_rel + 2 <= 32, "table does not fit a 32-row half of the pack"
+        iv = np.empty((n_tokens, n_tokens), np.int32)
+        ih = np.empty((n_tokens, n_tokens), np.int32)
+        check(_lib.load().cream_autoformer_rel_index_host(grid, max_rel, iv.ctypes.data, ih.ctypes.data),
+              "cream_autoformer_rel_index_host")
+        _INDEX_CACHE[key] = (_u8_table(iv, 0, device), _u8_table(ih, 32, device), iv, ih)
+    return _INDEX_CACHE[key]
+
+
+def irpe_bucket_ids(method: int, height: int, width: int, skip: int, alpha: float, beta: float, gamma: float):
+    """int32 bucket ids + bucket count (irpe.py:291-415), host side, cached."""
+    key = ("irpe", method, height, width, skip, alpha, beta, gamma)
+    if key not in _INDEX_CACHE:
+        n = skip + height * width
+        ids = np.empty((n, n), np.int32)
+        nb = C.c_int(0)
+        check(_lib.load().cream_irpe_bucket_ids_host(method, height, width, skip, alpha, beta, gamma,
+                                                     ids.ctypes.data, C.byref(nb)), "cream_irpe_bucket_ids_host")
+        _INDEX_CACHE[key] = (ids, nb.value)
+    return _INDEX_CACHE[key]
+
+
+def irpe_index_table_u8(ids: np.ndarray, device) -> torch.Tensor:
+    key = ("irpe_u8", ids.tobytes(), str(device))
+    if key not in _INDEX_CACHE:
+        assert ids.max() < NB_PACK, "more than 64 buckets is not supported by the fused kernel"
+        _INDEX_CACHE[key] = _u8_table(ids, 0, device)
+    return _INDEX_CACHE[key]
+
+
+def pack_tables(dst, num_tables, src0, nb0, off0, strides0, src1=None, nb1=0, off1=0, strides1=(0, 0, 0)):
+    check(_lib.load().cream_pack_tables(_p(dst), num_tables, HEAD_DIM, _p(src0), nb0, off0, *strides0,
+                                        _p(src1), nb1, off1, *strides1, _stream()), "cream_pack_tables")
+
+
+def unpack_table_grads(dpack, num_tables, g0, nb0, off0, strides0, g1=None, nb1=0, off1=0, strides1=(0, 0, 0)):
+    check(_lib.load().cream_unpack_table_grads(_p(dpack), num_tables, HEAD_DIM, _p(g0), nb0, off0, *strides0,
+                                               _p(g1), nb1, off1, *strides1, _stream()),
+          "cream_unpack_table_grads")
+
+
+def new_pack(num_tables: int, device) -> torch.Tensor:
+    return torch.empty((num_tables, NB_PACK, HEAD_DIM), dtype=torch.bfloat16, device=device)
+
+
+# --------------------------------------------------------------------------------------------
+# attention
+# --------------------------------------------------------------------------------------------
+def _attn_desc(B, H, N, scale, qkv, tk, tv, per_head, idx, bias):
+    d = AttnDesc()
+    d.B, d.H, d.N, d.head_dim = B, H, N, HEAD_DIM
+    d.scale = scale
+    d.qkv, d.ld_qkv = _p(qkv), qkv.stride(0)
+    d.tk_pack, d.tv_pack, d.tables_per_head = _p(tk), _p(tv), int(per_head)
+    ia, ib, iva, ivb = idx
+    d.idx_a, d.idx_b, d.idx_va, d.idx_vb = _p(ia), _p(ib), _p(iva), _p(ivb)
+    first = next((t for t in idx if t is not None), None)
+    d.ld_idx = first.stride(0) if first is not None else 0
+    d.bias_pack = _p(bias)
+    return d
+
+
+def attention_fwd(qkv, B, H, N, scale, *, tk=None, tv=None, per_head=False, idx=(None, None, None, None),
+                  bias=None, need_lse=True):
+    """Fused attention forward.  qkv: (B*N, 3*H*64) bf16.  Returns (out (B*N, H*64) bf16, lse)."""
+    _check_2d(qkv, torch.bfloat16, "qkv", 8)
+    out = empty_bf16(B * N, H * HEAD_DIM, qkv.device)
+    lse = torch.empty((B, H, N), dtype=torch.float32, device=qkv.device) if need_lse else None
+    d = _attn_desc(B, H, N, scale, qkv, tk, tv, per_head, idx, bias)
+    d.out, d.ld_out, d.lse = _p(out), out.stride(0), _p(lse)
+    check(_lib.load().cream_attn_fwd(C.byref(d), _stream()), "cream_attn_fwd")
+    return out, lse
+
+
+def attention_bwd(qkv, out, lse, dout, B, H, N, scale, *, tk=None, tv=None, per_head=False,
+                  idx=(None, None, None, None), bias=None):
+    """Returns (dqkv bf16, dtk_pack fp32|None, dtv_pack fp32|None, dbias fp32|None)."""
+    _check_2d(dout, torch.bfloat16, "dout", 8)
+    dev = qkv.device
+    dqkv = empty_bf16(B * N, 3 * H * HEAD_DIM, dev)
+    T = H if per_head else 1
+    dtk = torch.zeros((T, NB_PACK, HEAD_DIM), dtype=torch.float32, device=dev) if tk is not None else None
+    dtv = torch.zeros((T, NB_PACK, HEAD_DIM), dtype=torch.float32, device=dev) if tv is not None else None
+    dbias = torch.zeros((T, NB_PACK), dtype=torch.float32, device=dev) if bias is not None else None
+    nbytes = _lib.load().cream_attn_bwd_workspace_bytes(B, H, N)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    d = _attn_desc(B, H, N, scale, qkv, tk, tv, per_head, idx, bias)
+    d.out, d.ld_out, d.lse = _p(out), out.stride(0), _p(lse)
+    d.dout, d.ld_dout = _p(dout), dout.stride(0)
+    d.dqkv, d.ld_dqkv = _p(dqkv), dqkv.stride(0)
+    d.dtk_pack, d.dtv_pack, d.dbias_pack = _p(dtk), _p(dtv), _p(dbias)
+    d.workspace, d.workspace_bytes = _p(ws), nbytes
+    check(_lib.load().cream_attn_bwd(C.byref(d), _stream()), "cream_attn_bwd")
+    return dqkv, dtk, dtv, dbias
+
+
+# --------------------------------------------------------------------------------------------
+# rpe_index (the reference's native op)
+# --------------------------------------------------------------------------------------------
+_DT = {torch.float32: _lib.DTYPE_F32, torch.float16: _lib.DTYPE_F16, torch.bfloat16: _lib.DTYPE_BF16,
+       torch.float64: _lib.DTYPE_F64}
+
+
+def rpe_index_forward(inp: torch.Tensor, index: torch.Tensor) -> torch.Tensor:
+    """rpe_index_cpp.forward_gpu (rpe_index_cuda.cu:54-94): same checks, same semantics."""
+    if not inp.is_cuda:
+        raise RuntimeError("input must be a GPU tensor")
+    if not index.is_cuda:
+        raise RuntimeError("index must be a GPU tensor")
+    if inp.dim() != 4:
+        raise RuntimeError("input must be a 4D tensor")
+    if index.dim() != 2:
+        raise RuntimeError("index must be a 2D tensor")
+    if index.dtype != torch.int32:
+        raise RuntimeError("index must be Int type")
+    if not index.is_contiguous():
+        raise RuntimeError("index should be contiguous")
+    if inp.dtype not in _DT:
+        raise RuntimeError(f"rpe_index: unsupported dtype {inp.dtype}")
+    B, H, _, nb = inp.shape
+    Lq, Lk = index.shape
+    out = torch.empty((B, H, Lq, Lk), dtype=inp.dtype, device=inp.device)
+    s = inp.stride()
+    with torch.cuda.device(inp.device):
+        check(_lib.load().cream_rpe_index_fwd(_p(inp), _p(index), _p(out), B, H, Lq, Lk, nb, s[0], s[1], s[2], s[3],
+                                              _DT[inp.dtype], _stream()), "cream_rpe_index_fwd")
+    return out
+
+
+def rpe_index_backward(grad_input: torch.Tensor, grad_output: torch.Tensor, index: torch.Tensor) -> None:
+    """rpe_index_cpp.backward_gpu (rpe_index_cuda.cu:96-140): accumulates into grad_input."""
+    if not (grad_input.is_cuda and grad_output.is_cuda and index.is_cuda):
+        raise RuntimeError("grad_input, grad_output and index must be GPU tensors")
+    if grad_input.dim() != 4 or grad_output.dim() != 4 or index.dim() != 2:
+        raise RuntimeError("input must be a 4D tensor / index must be a 2D tensor")
+    if index.dtype != torch.int32:
+        raise RuntimeError("index must be Int type")
+    gi = grad_input if grad_input.is_contiguous() else grad_input.contiguous()
+    go = grad_output.contiguous()
+    idx = index.contiguous()
+    B, H, Lq, Lk = go.shape
+    nb = gi.shape[3]
+    with torch.cuda.device(go.device):
+        check(_lib.load().cream_rpe_index_bwd(_p(gi), _p(go), _p(idx), B, H, Lq, Lk, nb, _DT[go.dtype], _stream()),
+              "cream_rpe_index_bwd")
+    if gi is not grad_input:
+        grad_input.copy_(gi)

@@ -137,6 +137,26 @@ def rel_pos_2d(table_v, table_h, n_tokens: int, max_rel: int, head_dim: int):
     return table_v[:, :head_dim][iv] + table_h[:, :head_dim][ih]
 
 
+def attention_core_autoformer(qkv5, tables, spec_max_rel: int, scale: float):
+    """Attention core of AttentionSuper.forward, multihead_super.py:135-154, on
+    qkv5 = qkv(x).reshape(B, N, 3, heads, hd).  tables = None or (k_v, k_h, v_v, v_h)."""
+    B, N, _, heads, hd = qkv5.shape
+    qkv = qkv5.permute(2, 0, 3, 1, 4)
+    q, k, v = qkv[0], qkv[1], qkv[2]
+    attn = (q @ k.transpose(-2, -1)) * scale
+    if tables is not None:
+        r_p_k = rel_pos_2d(tables[0], tables[1], N, spec_max_rel, hd)
+        attn = attn + (q.permute(2, 0, 1, 3).reshape(N, heads * B, -1) @ r_p_k.transpose(2, 1)) \
+            .transpose(1, 0).reshape(B, heads, N, N) * scale
+    attn = attn.softmax(dim=-1)
+    out = (attn @ v).transpose(1, 2).reshape(B, N, -1)
+    if tables is not None:
+        r_p_v = rel_pos_2d(tables[2], tables[3], N, spec_max_rel, hd)
+        attn_1 = attn.permute(2, 0, 1, 3).reshape(N, B * heads, -1)
+        out = out + (attn_1 @ r_p_v).transpose(1, 0).reshape(B, heads, N, -1).transpose(2, 1).reshape(B, N, -1)
+    return out
+
+
 def attention_super(x, sd, prefix: str, spec: SupernetSpec, E: int, heads: int):
     """AttentionSuper.forward with change_qkv=True, multihead_super.py:100-116, 133-160;
     QKV slice per qkv_super.py:45-55, 72-83."""
@@ -145,25 +165,12 @@ def attention_super(x, sd, prefix: str, spec: SupernetSpec, E: int, heads: int):
     w = sd[prefix + "qkv.weight"][:, :E]
     w_s = torch.cat([w[i:3 * qd:3, :] for i in range(3)], dim=0)  # rows {i, i+3, ...} < 3*qd
     b_s = sd[prefix + "qkv.bias"][:3 * qd] if spec.qkv_bias else None  # contiguous, NOT interleaved
-    qkv = F.linear(x, w_s, b_s).reshape(B, N, 3, heads, -1).permute(2, 0, 3, 1, 4)
-    q, k, v = qkv[0], qkv[1], qkv[2]
+    qkv5 = F.linear(x, w_s, b_s).reshape(B, N, 3, heads, -1)
     scale = (qd // heads) ** -0.5
-    attn = (q @ k.transpose(-2, -1)) * scale
-    hd = qd // heads
+    tables = None
     if spec.relative_position:
-        r_p_k = rel_pos_2d(sd[prefix + "rel_pos_embed_k.embeddings_table_v"],
-                           sd[prefix + "rel_pos_embed_k.embeddings_table_h"], N,
-                           spec.max_relative_position, hd)
-        attn = attn + (q.permute(2, 0, 1, 3).reshape(N, heads * B, -1) @ r_p_k.transpose(2, 1)) \
-            .transpose(1, 0).reshape(B, heads, N, N) * scale
-    attn = attn.softmax(dim=-1)
-    out = (attn @ v).transpose(1, 2).reshape(B, N, -1)
-    if spec.relative_position:
-        r_p_v = rel_pos_2d(sd[prefix + "rel_pos_embed_v.embeddings_table_v"],
-                           sd[prefix + "rel_pos_embed_v.embeddings_table_h"], N,
-                           spec.max_relative_position, hd)
-        attn_1 = attn.permute(2, 0, 1, 3).reshape(N, B * heads, -1)
-        out = out + (attn_1 @ r_p_v).transpose(1, 0).reshape(B, heads, N, -1).transpose(2, 1).reshape(B, N, -1)
+        tables = tuple(sd[prefix + f"rel_pos_embed_{kv}.embeddings_table_{vh}"] for kv in "kv" for vh in "vh")
+    out = attention_core_autoformer(qkv5, tables, spec.max_relative_position, scale)
     pw = sd[prefix + "proj.weight"][:E, :qd]   # Linear_super.py:71-75 top-left view
     pb = sd[prefix + "proj.bias"][:E]
     return F.linear(out, pw, pb)

@@ -1,0 +1,165 @@
+"""CPU-side checks (no GPU): the C-ABI library loads and exports every symbol declared in
+include/cream_b200.h, the host-side integer tables are bit exact against the reference's
+fixtures, and the host-side module mirror has the reference's surface (names, shapes,
+sampled-parameter counts, error behaviour)."""
+import ctypes
+import re
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import rel_index, vit_oracle as vo
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT / "tests" / "golden"))
+from make_golden import MICRO_SPECS  # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def lib():
+    import __graft_entry__ as ge
+    ge.build()
+    from cream_b200 import _lib
+    return _lib.load()
+
+
+def test_library_exports_every_declared_symbol(lib):
+    from cream_b200 import _lib
+    header = (ROOT / "include" / "cream_b200.h").read_text()
+    declared = set(re.findall(r"\b(cream_[a-z0-9_]+)\s*\(", header))
+    declared -= {"cream_gemm_desc", "cream_attn_desc"}
+    assert declared, "no declarations parsed"
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"{name} declared in include/cream_b200.h but not exported"
+    assert declared == set(_lib.SIGNATURES), f"binding table out of sync: {declared ^ set(_lib.SIGNATURES)}"
+    assert lib.cream_rpe_index_version() == b"1.2.0"          # rpe_index.py:5-8 asserts this
+    assert b"sm_100a" in lib.cream_version()
+
+
+def test_struct_layouts_match_header():
+    from cream_b200 import _lib
+    # natural alignment, same field order as the header: spot-check offsets that matter
+    assert _lib.GemmDesc.a.offset == 16 and _lib.GemmDesc.b.offset == 40
+    assert ctypes.sizeof(_lib.GemmDesc) % 8 == 0 and ctypes.sizeof(_lib.AttnDesc) % 8 == 0
+    assert _lib.AttnDesc.qkv.offset == 24
+
+
+def test_host_autoformer_index_bit_exact(lib, golden_dir):
+    t = np.load(golden_dir / "index_tables.npz")
+    for grid in (14, 4, 7):
+        n = grid * grid + 1
+        iv = np.empty((n, n), np.int32)
+        ih = np.empty((n, n), np.int32)
+        assert lib.cream_autoformer_rel_index_host(grid, 14, iv.ctypes.data, ih.ctypes.data) == 0
+        np.testing.assert_array_equal(iv, t[f"af_idx_v_{grid}"])
+        np.testing.assert_array_equal(ih, t[f"af_idx_h_{grid}"])
+
+
+@pytest.mark.parametrize("mname,mid", [("euc", 0), ("quant", 1), ("product", 3), ("rows", 41), ("cols", 42)])
+def test_host_irpe_bucket_ids_bit_exact(lib, golden_dir, mname, mid):
+    t = np.load(golden_dir / "index_tables.npz")
+    for (h, w, skip, ratio) in [(14, 14, 1, 1.9), (7, 7, 0, 1.9), (5, 9, 2, 1.9), (14, 14, 1, 3.3), (24, 24, 1, 1.9)]:
+        n = skip + h * w
+        out = np.empty((n, n), np.int32)
+        nb = ctypes.c_int(0)
+        assert lib.cream_irpe_bucket_ids_host(mid, h, w, skip, 1 * ratio, 2 * ratio, 8 * ratio, out.ctypes.data,
+                                              ctypes.byref(nb)) == 0
+        key = f"{mname}_{h}_{w}_{skip}_{ratio}"
+        assert nb.value == int(t["nb_" + key])
+        np.testing.assert_array_equal(out, t["ids_" + key])
+        ids, nb2 = rel_index.irpe_bucket_ids(mid, h, w, skip, 1 * ratio, 2 * ratio, 8 * ratio)
+        np.testing.assert_array_equal(out, ids)
+
+
+def test_host_table_argument_errors(lib):
+    assert lib.cream_autoformer_rel_index_host(0, 14, None, None) != 0
+    nb = ctypes.c_int(0)
+    out = np.empty((4, 4), np.int32)
+    assert lib.cream_irpe_bucket_ids_host(7, 2, 2, 0, 1.9, 3.8, 15.2, out.ctypes.data, ctypes.byref(nb)) != 0
+
+
+@pytest.mark.parametrize("name", list(MICRO_SPECS))
+def test_module_mirror_surface(golden_dir, name):
+    from cream_b200.autoformer.model.supernet_transformer import Vision_TransformerSuper
+    g = np.load(golden_dir / "supernet_micro.npz")
+    spec, batch, configs = MICRO_SPECS[name]
+    net = Vision_TransformerSuper(img_size=spec.img_size, embed_dim=spec.embed_dim, depth=spec.depth,
+                                  num_heads=spec.num_heads, mlp_ratio=spec.mlp_ratio, qkv_bias=True, gp=True,
+                                  relative_position=True, change_qkv=True, max_relative_position=14)
+    shapes = {k: tuple(v.shape) for k, v in net.state_dict().items()}
+    assert shapes == vo.param_shapes(spec), "state_dict names/shapes must equal the reference's"
+    net.load_state_dict(vo.init_params(spec, seed=7))
+    assert net.no_weight_decay() == {'pos_embed', 'cls_token', 'rel_pos_embed'}
+    assert isinstance(net.head, torch.nn.Linear) and isinstance(net.norm, torch.nn.LayerNorm)
+    for ci, cfg in enumerate(configs):
+        assert net.get_sampled_params_numel(cfg) == int(g[f"{name}_c{ci}_numel"])
+        assert net.get_sampled_params_numel(cfg) == vo.sampled_param_count(cfg, spec)
+        assert net.get_complexity(net.patch_embed_super.num_patches) > 0
+        assert net.blocks[cfg["layer_num"] - 1].is_identity_layer is False
+        if cfg["layer_num"] < spec.depth:
+            assert net.blocks[-1].is_identity_layer is True
+    with pytest.raises(RuntimeError):
+        net(torch.randn(1, 3, spec.img_size, spec.img_size))      # CPU tensors: fail loudly, no fallback
+
+
+def test_sampled_param_names_exclude_identity_layers():
+    from cream_b200 import engine
+    geo = engine.SupernetGeometry(embed_dim=128, depth=3, num_heads=2, mlp_ratio=4.0, img_size=64)
+    names = engine.sampled_param_names(geo, {"layer_num": 2, "embed_dim": [64, 64], "num_heads": [1, 1],
+                                             "mlp_ratio": [3.5, 4.0]})
+    assert not any(n.startswith("blocks.2.") for n in names)
+    assert set(names) <= set(vo.param_shapes(vo.SupernetSpec(128, 3, 2, 4.0, img_size=64)))
+    with pytest.raises(AssertionError):
+        engine.validate_config(geo, {"layer_num": 4, "embed_dim": [64] * 4, "num_heads": [1] * 4, "mlp_ratio": [4.0] * 4})
+
+
+def test_rpe_ops_drop_in_surface():
+    import cream_b200.rpe_ops.rpe_index as ri
+    import rpe_index_cpp  # registered under the reference's top-level module name
+    assert rpe_index_cpp.version() == "1.2.0" and ri.EXPECTED_VERSION == "1.2.0"
+    for fn in ("forward_cpu", "backward_cpu", "forward_gpu", "backward_gpu", "version"):
+        assert hasattr(rpe_index_cpp, fn)
+    with pytest.raises(RuntimeError):
+        ri.RPEIndexFunction.apply(torch.randn(1, 1, 3, 4), torch.zeros(3, 3, dtype=torch.int32))
+
+
+REF = Path("/root/reference")
+
+
+@pytest.mark.skipif(not REF.exists(), reason="reference checkout only exists in the build container")
+def test_reference_model_file_runs_unchanged_on_the_drop_in_modules():
+    """Import the reference's OWN supernet_transformer.py with `model.module.*` / `model.utils`
+    resolved to cream_b200's drop-ins: construction, state_dict, set_sample_config and the
+    sampled-parameter count must all work untouched (forward needs the GPU)."""
+    import importlib.util
+    import types
+    import cream_b200.autoformer.model as m
+    import cream_b200.autoformer.model.module as mm
+    import cream_b200.autoformer.model.utils as mu
+    from cream_b200.autoformer.model.module import Linear_super, embedding_super, layernorm_super, multihead_super, qkv_super
+    saved = {k: sys.modules.get(k) for k in list(sys.modules) if k == "model" or k.startswith("model.")}
+    try:
+        sys.modules["model"] = m
+        sys.modules["model.utils"] = mu
+        sys.modules["model.module"] = mm
+        for sub in (Linear_super, embedding_super, layernorm_super, multihead_super, qkv_super):
+            sys.modules["model.module." + sub.__name__.rsplit(".", 1)[1]] = sub
+        spec_ = importlib.util.spec_from_file_location("ref_supernet_transformer",
+                                                       REF / "AutoFormer" / "model" / "supernet_transformer.py")
+        ref_mod = importlib.util.module_from_spec(spec_)
+        sys.dont_write_bytecode = True
+        spec_.loader.exec_module(ref_mod)
+        spec, batch, configs = MICRO_SPECS["micro17"]
+        net = ref_mod.Vision_TransformerSuper(img_size=64, embed_dim=128, depth=3, num_heads=2, mlp_ratio=4.0,
+                                              qkv_bias=True, gp=True, relative_position=True, change_qkv=True,
+                                              max_relative_position=14)
+        assert {k: tuple(v.shape) for k, v in net.state_dict().items()} == vo.param_shapes(spec)
+        for cfg in configs:
+            assert net.get_sampled_params_numel(cfg) == vo.sampled_param_count(cfg, spec)
+    finally:
+        for k in [k for k in sys.modules if k == "model" or k.startswith("model.")]:
+            del sys.modules[k]
+        sys.modules.update({k: v for k, v in saved.items() if v is not None})
