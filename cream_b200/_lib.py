@@ -59,6 +59,7 @@ class AttnDesc(C.Structure):
 SIGNATURES = {
     "cream_version": (C.c_char_p, []),
     "cream_rpe_index_version": (C.c_char_p, []),
+    "cream_bind_device": (c_int, [c_int]),
     "cream_rpe_index_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
                                     c_i64, c_i64, c_i64, c_i64, c_int, c_void_p]),
     "cream_rpe_index_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
@@ -118,6 +119,10 @@ def load() -> C.CDLL:
 _ERR = {ERR_ARG: "invalid argument", ERR_CUDA: "CUDA error", ERR_UNSUPPORTED: "unsupported configuration"}
 
 
-def check(rc: int, what: str) -> None:
+LAUNCHES = [0]   # kernels enqueued through the C ABI (bench.py reports it as gpu_launches)
+
+
+def check(rc: int, what: str, kernels: int = 1) -> None:
+    LAUNCHES[0] += kernels
     if rc != OK:
         raise CreamError(f"{what} failed: {_ERR.get(rc, rc)} (see stderr of libcream_b200)")

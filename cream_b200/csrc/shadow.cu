@@ -40,6 +40,16 @@ shadow_cast_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ ds
 
 extern "C" const char* cream_version(void) { return "cream_b200 0.1.0 (sm_100a)"; }
 
+// The library links its own CUDA runtime instance; a host thread that has not touched it yet
+// (e.g. an autograd worker thread) must bind the caller's device before raw driver calls
+// (cuTensorMapEncodeTiled) or launches are made from it.
+extern "C" int cream_bind_device(int device) {
+  using namespace cb;
+  CB_CUDA_OK(cudaSetDevice(device));
+  CB_CUDA_OK(cudaFree(nullptr));
+  return CREAM_OK;
+}
+
 extern "C" int cream_shadow_cast(const float* src, void* dst, int64_t rows, int64_t cols,
                                  int64_t ld_src, int64_t ld_dst, void* stream_) {
   using namespace cb;

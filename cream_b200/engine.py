@@ -189,9 +189,11 @@ def forward(P: Dict[str, torch.Tensor], geo: SupernetGeometry, config: dict, ima
 
 
 def backward(P: Dict[str, torch.Tensor], geo: SupernetGeometry, saved: Saved, dlogits: torch.Tensor,
-             grads: Optional[Dict[str, torch.Tensor]] = None) -> Dict[str, torch.Tensor]:
+             grads: Optional[Dict[str, torch.Tensor]] = None, on_group_done=None) -> Dict[str, torch.Tensor]:
     """Backward of `forward`.  Returns {name: full-size fp32 grad} for the sampled parameters
-    (accumulating into `grads` when given, e.g. the .grad tensors themselves)."""
+    (accumulating into `grads` when given, e.g. views of flat all-reduce buckets).
+    on_group_done(name) is called with "head", "block<i>", "embed" as soon as every gradient
+    of that parameter group has been enqueued (the hook point for overlapped all-reduce)."""
     lib = _lib.load()
     config = saved.config
     dev = dlogits.device
@@ -219,6 +221,8 @@ def backward(P: Dict[str, torch.Tensor], geo: SupernetGeometry, saved: Saved, dl
           "cream_pool_bwd")
     g = ops.layernorm_bwd(dy, saved.x_last, P["norm.weight"], saved.mean_f, saved.rstd_f, E, G["norm.weight"],
                           G["norm.bias"])
+    if on_group_done is not None:
+        on_group_done("head")
 
     idx = (None, None, None, None)
     if geo.relative_position:
@@ -259,6 +263,8 @@ def backward(P: Dict[str, torch.Tensor], geo: SupernetGeometry, saved: Saved, dl
         g = ops.layernorm_bwd(dln1, s["x"], P[pre + "attn_layer_norm.weight"], s["mu1"], s["rs1"], E,
                               G[pre + "attn_layer_norm.weight"], G[pre + "attn_layer_norm.bias"], resid_grad=g1)
         saved.blocks[i] = None  # release activations as we go
+        if on_group_done is not None:
+            on_group_done("block%d" % i)
 
     # ---- embedding ----
     dpatch = ops.empty_bf16(B * T, E, dev)
@@ -268,6 +274,8 @@ def backward(P: Dict[str, torch.Tensor], geo: SupernetGeometry, saved: Saved, dl
     ops.bias_grad(dpatch, G["patch_embed_super.proj.bias"])
     kdim = geo.in_chans * geo.patch_size ** 2
     ops.linear_wgrad(dpatch, saved.cols, E, kdim, G["patch_embed_super.proj.weight"])
+    if on_group_done is not None:
+        on_group_done("embed")
     return G
 
 

@@ -7,6 +7,7 @@ of 8 elements (see `empty_bf16`).
 from __future__ import annotations
 
 import ctypes as C
+import threading
 from typing import Optional
 
 import numpy as np
@@ -18,9 +19,19 @@ from ._lib import (EPI_BF16, EPI_BF16_DGELU, EPI_BF16_GELU, EPI_F32, EPI_F32_ATO
 
 HEAD_DIM = 64
 NB_PACK = 64
+PROFILE = None   # set to a list to record (kind, start_event, end_event, flops, bytes) per launch
+
+
+_tls = threading.local()
 
 
 def _stream() -> int:
+    """Current torch stream handle; also binds this host thread (autograd workers included) to
+    torch's current device inside the library's own CUDA runtime instance."""
+    dev = torch.cuda.current_device()
+    if getattr(_tls, "dev", None) != dev:
+        check(_lib.load().cream_bind_device(dev), "cream_bind_device", kernels=0)
+        _tls.dev = dev
     return torch.cuda.current_stream().cuda_stream
 
 
@@ -122,6 +133,13 @@ def gemm(M, N, K, a, lda, b, ldb, out, ldo, epi, *, groups=1, a_mn=0, b_mn=0, a_
     d.resid, d.ldr = _p(resid), ldr
     d.row_scale, d.rows_per_scale = _p(row_scale), rows_per_scale
     d.alpha, d.split_k = alpha, split_k
+    if PROFILE is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        check(_lib.load().cream_gemm_bf16(C.byref(d), _stream()), "cream_gemm_bf16")
+        e1.record()
+        PROFILE.append(("gemm", e0, e1, 2.0 * M * N * K * groups, 0.0))
+        return
     check(_lib.load().cream_gemm_bf16(C.byref(d), _stream()), "cream_gemm_bf16")
 
 
@@ -257,7 +275,7 @@ def autoformer_index_tables(n_tokens: int, max_rel: int, device):
         iv = np.empty((n_tokens, n_tokens), np.int32)
         ih = np.empty((n_tokens, n_tokens), np.int32)
         check(_lib.load().cream_autoformer_rel_index_host(grid, max_rel, iv.ctypes.data, ih.ctypes.data),
-              "cream_autoformer_rel_index_host")
+              "cream_autoformer_rel_index_host", kernels=0)
         _INDEX_CACHE[key] = (_u8_table(iv, 0, device), _u8_table(ih, 32, device), iv, ih)
     return _INDEX_CACHE[key]
 
@@ -270,7 +288,7 @@ def irpe_bucket_ids(method: int, height: int, width: int, skip: int, alpha: floa
         ids = np.empty((n, n), np.int32)
         nb = C.c_int(0)
         check(_lib.load().cream_irpe_bucket_ids_host(method, height, width, skip, alpha, beta, gamma,
-                                                     ids.ctypes.data, C.byref(nb)), "cream_irpe_bucket_ids_host")
+                                                     ids.ctypes.data, C.byref(nb)), "cream_irpe_bucket_ids_host", kernels=0)
         _INDEX_CACHE[key] = (ids, nb.value)
     return _INDEX_CACHE[key]
 
@@ -323,6 +341,15 @@ def attention_fwd(qkv, B, H, N, scale, *, tk=None, tv=None, per_head=False, idx=
     lse = torch.empty((B, H, N), dtype=torch.float32, device=qkv.device) if need_lse else None
     d = _attn_desc(B, H, N, scale, qkv, tk, tv, per_head, idx, bias)
     d.out, d.ld_out, d.lse = _p(out), out.stride(0), _p(lse)
+    if PROFILE is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        check(_lib.load().cream_attn_fwd(C.byref(d), _stream()), "cream_attn_fwd")
+        e1.record()
+        nb = (NB_PACK if tk is not None else 0) + (NB_PACK if tv is not None else 0)
+        PROFILE.append(("attn_fwd", e0, e1, 4.0 * B * H * N * N * HEAD_DIM + 2.0 * B * H * N * HEAD_DIM * nb,
+                        4.0 * B * H * N * HEAD_DIM * 2))
+        return out, lse
     check(_lib.load().cream_attn_fwd(C.byref(d), _stream()), "cream_attn_fwd")
     return out, lse
 
@@ -345,7 +372,7 @@ def attention_bwd(qkv, out, lse, dout, B, H, N, scale, *, tk=None, tv=None, per_
     d.dqkv, d.ld_dqkv = _p(dqkv), dqkv.stride(0)
     d.dtk_pack, d.dtv_pack, d.dbias_pack = _p(dtk), _p(dtv), _p(dbias)
     d.workspace, d.workspace_bytes = _p(ws), nbytes
-    check(_lib.load().cream_attn_bwd(C.byref(d), _stream()), "cream_attn_bwd")
+    check(_lib.load().cream_attn_bwd(C.byref(d), _stream()), "cream_attn_bwd", kernels=2)
     return dqkv, dtk, dtv, dbias
 
 

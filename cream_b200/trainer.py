@@ -1,0 +1,138 @@
+"""Supernet training step on the fused engine, with data-parallel gradient all-reduce.
+
+`SupernetTrainer.step` is the body of the reference's hot loop
+(AutoFormer/supernet_engine.py:49-107): host batch -> device, sample a subnet
+(`sample_configs`, :13-24, identical on every rank because the Python RNG is seeded with the
+epoch, :36), set_sample_config, forward, loss, backward, optimizer step.  Differences that
+are B200-first rather than a translation:
+
+  * the whole sampled subnet is two engine calls (forward / backward), no autograd graph over
+    the model and no DDP graph walk for unused parameters: gradients land directly in views of
+    per-layer flat fp32 buckets and un-sampled layers simply keep `grad = None`
+    (the find_unused_parameters=True contract of supernet_train.py:288);
+  * each layer's bucket is all-reduced (NCCL over NVLink/NVSwitch, average) on a side stream as
+    soon as that layer's backward has been enqueued, overlapping the remaining backward;
+  * bf16 compute with fp32 masters instead of fp16 autocast + GradScaler (no loss scaling,
+    no per-step inf check / host sync);
+  * no host synchronisation inside a step unless the caller reads the loss.
+"""
+from __future__ import annotations
+
+import random
+from typing import Dict, List, Optional
+
+import torch
+import torch.distributed as dist
+import torch.nn.functional as F
+
+from . import engine, ops
+from .autoformer.model.supernet_transformer import Vision_TransformerSuper
+
+
+def sample_configs(choices: dict, rnd=random) -> dict:
+    """AutoFormer/supernet_engine.py:13-24 (same draw order from the same RNG)."""
+    config = {}
+    depth = rnd.choice(choices['depth'])
+    for dimension in ['mlp_ratio', 'num_heads']:
+        config[dimension] = [rnd.choice(choices[dimension]) for _ in range(depth)]
+    config['embed_dim'] = [rnd.choice(choices['embed_dim'])] * depth
+    config['layer_num'] = depth
+    return config
+
+
+class GradBuckets:
+    """Per-layer flat fp32 gradient buckets; parameters' .grad are views into them."""
+
+    def __init__(self, model: Vision_TransformerSuper):
+        named = dict(model.named_parameters())
+        self.groups: Dict[str, List[str]] = {"embed": [], "head": []}
+        for name in named:
+            if name.startswith("blocks."):
+                self.groups.setdefault("block%d" % int(name.split(".")[1]), []).append(name)
+            elif name in ("norm.weight", "norm.bias", "head.weight", "head.bias"):
+                self.groups["head"].append(name)
+            else:
+                self.groups["embed"].append(name)
+        self.flat: Dict[str, torch.Tensor] = {}
+        self.views: Dict[str, torch.Tensor] = {}
+        for gname, names in self.groups.items():
+            total = sum((named[n].numel() + 3) // 4 * 4 for n in names)
+            buf = torch.zeros(total, dtype=torch.float32, device=named[names[0]].device)
+            off = 0
+            for n in names:
+                p = named[n]
+                self.views[n] = buf[off:off + p.numel()].view(p.shape)
+                off += (p.numel() + 3) // 4 * 4
+            self.flat[gname] = buf
+
+    def group_of_layer(self, i: int) -> str:
+        return "block%d" % i
+
+
+class SupernetTrainer:
+    def __init__(self, model: Vision_TransformerSuper, choices: dict, lr: float = 5e-4, weight_decay: float = 0.05,
+                 process_group=None, grad_dtype: torch.dtype = torch.float32):
+        self.model = model
+        self.choices = choices
+        self.geo = model._geo
+        self.params = dict(model.named_parameters())
+        self.buckets = GradBuckets(model)
+        self.pg = process_group
+        self.world = dist.get_world_size(process_group) if (dist.is_available() and dist.is_initialized()) else 1
+        # timm create_optimizer('adamw') (supernet_train.py:296): no decay on 1-D params and the
+        # names in no_weight_decay(); torch's fused AdamW is the same update rule on device.
+        skip = model.no_weight_decay()
+        decay, no_decay = [], []
+        for n, p in self.params.items():
+            (no_decay if (p.ndim <= 1 or n.endswith(".bias") or any(s in n for s in skip)) else decay).append(p)
+        self.optimizer = torch.optim.AdamW([{"params": decay, "weight_decay": weight_decay},
+                                            {"params": no_decay, "weight_decay": 0.0}], lr=lr, fused=model.pos_embed.is_cuda)
+        self.comm_stream = torch.cuda.Stream() if (self.world > 1 and model.pos_embed.is_cuda) else None
+        self.last_config: Optional[dict] = None
+
+    # ------------------------------------------------------------------------------------
+    def _allreduce(self, gname: str):
+        if self.world == 1:
+            return
+        buf = self.buckets.flat[gname]
+        if self.comm_stream is None:          # CPU / gloo (host-logic tests)
+            dist.all_reduce(buf, group=self.pg)
+            buf.div_(self.world)
+            return
+        self.comm_stream.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(self.comm_stream):
+            dist.all_reduce(buf, op=dist.ReduceOp.AVG, group=self.pg)
+
+    def _backward(self, saved, dlogits):
+        """engine.backward with per-layer bucket all-reduce interleaved."""
+        cfg = saved.config
+        names = engine.sampled_param_names(self.geo, cfg)
+        used = {"embed", "head"} | {self.buckets.group_of_layer(i) for i in range(cfg["layer_num"])}
+        for g in used:
+            self.buckets.flat[g].zero_()
+        G = {n: self.buckets.views[n] for n in names}
+        engine.backward(self.params, self.geo, saved, dlogits, grads=G, on_group_done=self._allreduce)
+        if self.comm_stream is not None:
+            torch.cuda.current_stream().wait_stream(self.comm_stream)
+        sampled = set(names)
+        for n, p in self.params.items():
+            p.grad = self.buckets.views[n] if n in sampled else None
+
+    def step(self, images: torch.Tensor, targets: torch.Tensor, config: Optional[dict] = None,
+             rnd=random) -> torch.Tensor:
+        """One training step; returns the (device) loss tensor without synchronising."""
+        model = self.model
+        dev = model.pos_embed.device
+        images = images.to(dev, non_blocking=True)
+        targets = targets.to(dev, non_blocking=True)
+        cfg = config if config is not None else sample_configs(self.choices, rnd)
+        self.last_config = cfg
+        model.set_sample_config(cfg)
+        scales = model._drop_path_scales(images.shape[0], dev)
+        logits, saved = engine.forward(self.params, self.geo, cfg, images.float().contiguous(), scales, save=True)
+        lg = logits.detach().requires_grad_(True)
+        loss = F.cross_entropy(lg, targets)
+        (dlogits,) = torch.autograd.grad(loss, lg)
+        self._backward(saved, dlogits)
+        self.optimizer.step()
+        return loss.detach()

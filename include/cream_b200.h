@@ -39,6 +39,10 @@ extern "C" {
 /* Library version string, e.g. "cream_b200 0.1.0 (sm_100a)". */
 const char* cream_version(void);
 
+/* Bind the calling host thread to `device` inside the library's CUDA runtime (call once per
+ * thread / device change before any other entry point; cheap and idempotent). */
+int cream_bind_device(int device);
+
 /* Version of the rpe_index operator contract; the reference asserts "1.2.0"
  * (iRPE/DeiT-with-iRPE/rpe_ops/rpe_index.py:5-8, rpe_index.cpp:126-128). */
 const char* cream_rpe_index_version(void);

@@ -10,9 +10,15 @@ def rand(shape, seed, scale=1.0):
     return torch.from_numpy(np.random.default_rng(seed).standard_normal(shape, dtype=np.float32) * scale)
 
 
+def _np(x):
+    if isinstance(x, torch.Tensor):
+        return x.detach().double().cpu().numpy()
+    return np.asarray(x, dtype=np.float64)
+
+
 def rel_err(a, b) -> float:
-    a = np.asarray(a, dtype=np.float64)
-    b = np.asarray(b, dtype=np.float64)
+    a = _np(a)
+    b = _np(b)
     return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-30))
 
 
