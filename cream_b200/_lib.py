@@ -47,6 +47,7 @@ class AttnDesc(C.Structure):
         ("idx_a", c_void_p), ("idx_b", c_void_p), ("idx_va", c_void_p), ("idx_vb", c_void_p),
         ("ld_idx", c_int),
         ("bias_pack", c_void_p),
+        ("af_grid", c_int), ("af_max_rel", c_int),
         ("dout", c_void_p), ("ld_dout", c_i64),
         ("dqkv", c_void_p), ("ld_dqkv", c_i64),
         ("dtk_pack", c_void_p), ("dtv_pack", c_void_p),

@@ -146,25 +146,26 @@ class AutoformerAttentionFn(torch.autograd.Function):
         B, N, W3 = qkv.shape
         assert W3 == 3 * ops.HEAD_DIM * heads
         qkv2 = ops.as_bf16_2d(qkv)
-        tk = tv = None
+        tk = tv = af = None
         idx = (None, None, None, None)
         if tables:
             assert tables[0].shape[1] == ops.HEAD_DIM and tables[0].dtype == torch.float32
             iv, ih, _, _ = ops.autoformer_index_tables(N, max_rel, qkv.device)
             idx = (iv, ih, iv, ih)
+            af = (int(round((N - 1) ** 0.5)), max_rel)
             tk = _pack_pair(tables[0].detach(), tables[1].detach())
             tv = _pack_pair(tables[2].detach(), tables[3].detach())
-        out, lse = ops.attention_fwd(qkv2, B, heads, N, scale, tk=tk, tv=tv, idx=idx)
+        out, lse = ops.attention_fwd(qkv2, B, heads, N, scale, tk=tk, tv=tv, idx=idx, af=af)
         ctx.save_for_backward(qkv2, out, lse, tk, tv, *tables)
-        ctx.meta = (B, heads, N, scale, idx, qkv.dtype)
+        ctx.meta = (B, heads, N, scale, idx, qkv.dtype, af)
         return out.reshape(B, N, ops.HEAD_DIM * heads)
 
     @staticmethod
     def backward(ctx, dout):
         qkv2, out, lse, tk, tv, *tables = ctx.saved_tensors
-        B, heads, N, scale, idx, dtype = ctx.meta
+        B, heads, N, scale, idx, dtype, af = ctx.meta
         d2 = ops.as_bf16_2d(dout)
-        dqkv, dtk, dtv, _ = ops.attention_bwd(qkv2, out, lse, d2, B, heads, N, scale, tk=tk, tv=tv, idx=idx)
+        dqkv, dtk, dtv, _ = ops.attention_bwd(qkv2, out, lse, d2, B, heads, N, scale, tk=tk, tv=tv, idx=idx, af=af)
         grads = []
         if tables:
             for pair, dpack in ((tables[0:2], dtk), (tables[2:4], dtv)):

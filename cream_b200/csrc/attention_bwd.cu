@@ -16,8 +16,7 @@
 //
 // Round-1 note: the workspace round trip (2 x B*H*N*(Npad+64) bf16) costs about 3x the
 // algorithmic bytes of the fused ideal; fusing bwd_cols into bwd_rows is the next step.
-#include "common.cuh"
-#include "ptx.cuh"
+#include "attention_common.cuh"
 
 namespace cb {
 namespace {
@@ -26,12 +25,12 @@ constexpr int kD = 64;
 constexpr int kNB = 64;
 constexpr int kRowsThreads = 160;
 constexpr int kStride = 65;  // floats per row of the staged R / dPB / dR tiles
-constexpr float kLog2e = 1.4426950408889634f;
 
 struct BwdRowsParams {
   int B, H, N, Npad, ldw;
   float scale;
   int ctx_k, ctx_v, shared_tables;
+  int af_grid, af_max_rel;
   const uint8_t* idx_a; const uint8_t* idx_b; const uint8_t* idx_va; const uint8_t* idx_vb;
   int ldi;
   const float* bias;
@@ -43,29 +42,186 @@ struct BwdRowsParams {
   float* dbias;
 };
 
-__device__ __forceinline__ float fast_exp2(float x) {
-  float y;
-  asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
-__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8]) {
-  asm volatile(
-      "tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr),
-      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
-      : "memory");
+struct RowCtx {
+  uint32_t trow;        // TMEM address of this thread's lane
+  uint32_t s_r, s_dpb;  // shared addresses of this row's staged R (scaled) and dPB, fp32[kStride]
+  uint32_t s_pb, s_dr;  // shared addresses of this row's PB (xor-swizzled, 64 floats) and dR (kStride)
+  uint32_t s_bias;
+  int row, row_c, sw;
+  float delta, lsel;
+  int64_t wrow;
+};
+
+// dT / P of one query row, generic gather tables (see attention_fwd.cu for the forward twin).
+__device__ __forceinline__ void bwd_row_generic(const BwdRowsParams& p, const RowCtx& x) {
+  const int Npad = p.Npad;
+  for (int k = 0; k < kNB; ++k) { sts_f32(x.s_pb + 4 * k, 0.f); sts_f32(x.s_dr + 4 * k, 0.f); }
+  const uint8_t* ia = p.idx_a ? p.idx_a + static_cast<int64_t>(x.row_c) * p.ldi : nullptr;
+  const uint8_t* ib = p.idx_b ? p.idx_b + static_cast<int64_t>(x.row_c) * p.ldi : nullptr;
+  const uint8_t* iva = p.idx_va ? p.idx_va + static_cast<int64_t>(x.row_c) * p.ldi : nullptr;
+  const uint8_t* ivb = p.idx_vb ? p.idx_vb + static_cast<int64_t>(x.row_c) * p.ldi : nullptr;
+  const bool use_bias = p.bias != nullptr;
+  const bool want_dr = p.ctx_k || use_bias;
+  const int nchunks = Npad / 16;
+  for (int c = 0; c < nchunks; ++c) {
+    uint32_t rt[16], rp[16];
+    tmem_ld16(x.trow + c * 16, rt);
+    tmem_ld16(x.trow + 256 + c * 16, rp);
+    uint4 va = make_uint4(0, 0, 0, 0), vb = va, vva = va, vvb = va;
+    if (ia) va = __ldg(reinterpret_cast<const uint4*>(ia + c * 16));
+    if (ib) vb = __ldg(reinterpret_cast<const uint4*>(ib + c * 16));
+    if (iva) vva = __ldg(reinterpret_cast<const uint4*>(iva + c * 16));
+    if (ivb) vvb = __ldg(reinterpret_cast<const uint4*>(ivb + c * 16));
+    tmem_ld_wait();
+    const uint32_t wa[4] = {va.x, va.y, va.z, va.w}, wb[4] = {vb.x, vb.y, vb.z, vb.w};
+    const uint32_t wva[4] = {vva.x, vva.y, vva.z, vva.w}, wvb[4] = {vvb.x, vvb.y, vvb.z, vvb.w};
+    float pv[16], dt[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      const uint32_t a_id = byte_of(wa, k), b_id = byte_of(wb, k);
+      const uint32_t va_id = byte_of(wva, k), vb_id = byte_of(wvb, k);
+      float t = p.scale * __uint_as_float(rt[k]);
+      if (p.ctx_k) {
+        if (ia) t += lds_f32(x.s_r + 4 * a_id);
+        if (ib) t += lds_f32(x.s_r + 4 * b_id);
+      }
+      if (use_bias) t += lds_f32(x.s_bias + 4 * a_id);
+      float pr = fast_exp2(fmaf(t, kLog2e, -x.lsel));
+      if (c * 16 + k >= p.N || x.row >= p.N) pr = 0.f;
+      float dp = __uint_as_float(rp[k]);
+      if (p.ctx_v) {
+        if (iva) dp += lds_f32(x.s_dpb + 4 * va_id);
+        if (ivb) dp += lds_f32(x.s_dpb + 4 * vb_id);
+      }
+      const float d = pr * (dp - x.delta);
+      pv[k] = pr;
+      dt[k] = d;
+      if (p.ctx_v) {
+        if (iva) { const uint32_t a = x.s_pb + 4 * (va_id ^ x.sw); sts_f32(a, lds_f32(a) + pr); }
+        if (ivb) { const uint32_t a = x.s_pb + 4 * (vb_id ^ x.sw); sts_f32(a, lds_f32(a) + pr); }
+      }
+      if (want_dr) {
+        if (ia) { const uint32_t a = x.s_dr + 4 * a_id; sts_f32(a, lds_f32(a) + d); }
+        if (ib) { const uint32_t a = x.s_dr + 4 * b_id; sts_f32(a, lds_f32(a) + d); }
+      }
+    }
+    uint32_t pk[8], dk[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      pk[k] = pack_bf16x2(pv[2 * k], pv[2 * k + 1]);
+      dk[k] = pack_bf16x2(dt[2 * k], dt[2 * k + 1]);
+    }
+    tmem_st8(x.trow + c * 8, dk);   // dT (bf16x2) in place over T, A operand of the dQ MMA
+    if (x.row < p.N) {
+      uint4* wp = reinterpret_cast<uint4*>(p.ws_p + x.wrow + c * 16);
+      uint4* wd = reinterpret_cast<uint4*>(p.ws_dt + x.wrow + c * 16);
+      wp[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+      wp[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+      wd[0] = make_uint4(dk[0], dk[1], dk[2], dk[3]);
+      wd[1] = make_uint4(dk[4], dk[5], dk[6], dk[7]);
+    }
+  }
 }
 
-__device__ __forceinline__ uint32_t byte_of(const uint32_t (&w)[4], int k) {
-  return (w[k >> 2] >> (8 * (k & 3))) & 0xFF;
+// AutoFormer-structured twin (see softmax_af in attention_fwd.cu): the four gather operand
+// vectors and the four bucket-sum vectors of a row are registers; afterwards the bucket sums
+// are scattered ONCE into the shared rows the common tail reads.
+template <int G>
+__device__ __forceinline__ void bwd_row_af(const BwdRowsParams& p, const RowCtx& x) {
+  constexpr int N = G * G + 1;
+  constexpr int NPAD = (N + 15) / 16 * 16;
+  constexpr int NCH = NPAD / 16;
+  const int M1 = p.af_max_rel + 1;
+  const bool patch = x.row >= 1 && x.row < N;
+  const int qi = patch ? x.row - 1 : 0;
+  const int ri = qi / G, ci = qi - ri * G;
+  const float r0v = lds_f32(x.s_r), r0h = lds_f32(x.s_r + 4 * 32);
+  const float g0v = lds_f32(x.s_dpb), g0h = lds_f32(x.s_dpb + 4 * 32);
+  float rv[G], rh[G], gv[G], gh[G];
+#pragma unroll
+  for (int t = 0; t < G; ++t) {
+    rv[t] = patch ? lds_f32(x.s_r + 4 * (M1 - ri + t)) : r0v;
+    rh[t] = patch ? lds_f32(x.s_r + 4 * (32 + M1 - ci + t)) : r0h;
+    gv[t] = patch ? lds_f32(x.s_dpb + 4 * (M1 - ri + t)) : g0v;
+    gh[t] = patch ? lds_f32(x.s_dpb + 4 * (32 + M1 - ci + t)) : g0h;
+  }
+  float prow[G], pcol[G], drow[G], dcol[G], p0 = 0.f, d0 = 0.f, psum = 0.f, dsum = 0.f;
+#pragma unroll
+  for (int t = 0; t < G; ++t) { prow[t] = 0.f; pcol[t] = 0.f; drow[t] = 0.f; dcol[t] = 0.f; }
+  const bool live = x.row < N;
+#pragma unroll
+  for (int c = 0; c < NCH; ++c) {
+    uint32_t rt[16], rp[16];
+    tmem_ld16(x.trow + c * 16, rt);
+    tmem_ld16(x.trow + 256 + c * 16, rp);
+    tmem_ld_wait();
+    float pv[16], dt[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      const int j = c * 16 + k;
+      float t, dp = __uint_as_float(rp[k]);
+      if (j == 0) { t = fmaf(p.scale, __uint_as_float(rt[k]), r0v + r0h); dp += g0v + g0h; }
+      else if (j < N) {
+        t = fmaf(p.scale, __uint_as_float(rt[k]), rv[(j - 1) / G]) + rh[(j - 1) % G];
+        dp += gv[(j - 1) / G] + gh[(j - 1) % G];
+      } else { t = 0.f; }
+      float pr = fast_exp2(fmaf(t, kLog2e, -x.lsel));
+      if (j >= N || !live) pr = 0.f;
+      const float d = pr * (dp - x.delta);
+      pv[k] = pr;
+      dt[k] = d;
+      psum += pr;
+      dsum += d;
+      if (j == 0) { p0 = pr; d0 = d; }
+      else if (j < N) {
+        prow[(j - 1) / G] += pr; pcol[(j - 1) % G] += pr;
+        drow[(j - 1) / G] += d;  dcol[(j - 1) % G] += d;
+      }
+    }
+    uint32_t pk[8], dk[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      pk[k] = pack_bf16x2(pv[2 * k], pv[2 * k + 1]);
+      dk[k] = pack_bf16x2(dt[2 * k], dt[2 * k + 1]);
+    }
+    tmem_st8(x.trow + c * 8, dk);
+    if (live) {
+      uint4* wp = reinterpret_cast<uint4*>(p.ws_p + x.wrow + c * 16);
+      uint4* wd = reinterpret_cast<uint4*>(p.ws_dt + x.wrow + c * 16);
+      wp[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+      wp[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+      wd[0] = make_uint4(dk[0], dk[1], dk[2], dk[3]);
+      wd[1] = make_uint4(dk[4], dk[5], dk[6], dk[7]);
+    }
+  }
+  // scatter the register bucket sums into the shared rows read by the common tail
+  for (int k = 0; k < kNB; ++k) { sts_f32(x.s_pb + 4 * k, 0.f); sts_f32(x.s_dr + 4 * k, 0.f); }
+  if (patch) {
+#pragma unroll
+    for (int t = 0; t < G; ++t) {
+      sts_f32(x.s_pb + 4 * ((M1 - ri + t) ^ x.sw), prow[t]);
+      sts_f32(x.s_pb + 4 * ((32 + M1 - ci + t) ^ x.sw), pcol[t]);
+      sts_f32(x.s_dr + 4 * (M1 - ri + t), drow[t]);
+      sts_f32(x.s_dr + 4 * (32 + M1 - ci + t), dcol[t]);
+    }
+    sts_f32(x.s_pb + 4 * (0 ^ x.sw), p0);
+    sts_f32(x.s_pb + 4 * (32 ^ x.sw), p0);
+    sts_f32(x.s_dr, d0);
+    sts_f32(x.s_dr + 4 * 32, d0);
+  } else {
+    sts_f32(x.s_pb + 4 * (0 ^ x.sw), psum);
+    sts_f32(x.s_pb + 4 * (32 ^ x.sw), psum);
+    sts_f32(x.s_dr, dsum);
+    sts_f32(x.s_dr + 4 * 32, dsum);
+  }
 }
 
 __global__ void __launch_bounds__(kRowsThreads, 1)
 attn_bwd_rows_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_kv,
                      const __grid_constant__ CUtensorMap map_do, const __grid_constant__ CUtensorMap map_tk,
                      const __grid_constant__ CUtensorMap map_tv, const BwdRowsParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>(
-      (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  extern __shared__ __align__(1024) uint8_t smem[];
+  require_smem_alignment(smem);
   const int kv_bytes = p.Npad * 128;
   const int v_slot = max(kv_bytes, 26 * 1024);
   uint8_t* sQ = smem;                       // 16 KB
@@ -74,11 +230,11 @@ attn_bwd_rows_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
   uint8_t* sTK = sK + kv_bytes;
   uint8_t* sV = sTK + 8192;                 // [V ; TV]
   uint8_t* sTV = sV + v_slot;
-  float* sR = reinterpret_cast<float*>(sTV + 8192);
-  float* sdPB = sR + 128 * kStride;
-  float* sBias = sdPB + 128 * kStride;
-  float* sDbias = sBias + 64;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sDbias + 64);
+  uint8_t* sR = sTV + 8192;                 // fp32 [128][kStride]
+  uint8_t* sdPB = sR + 128 * kStride * 4;   // fp32 [128][kStride]
+  uint8_t* sBias = sdPB + 128 * kStride * 4;
+  uint8_t* sDbias = sBias + 64 * 4;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sDbias + 64 * 4);
   uint64_t* bar_ld = bars + 0;
   uint64_t* bar_r = bars + 1;
   uint64_t* bar_rfree = bars + 2;
@@ -86,8 +242,7 @@ attn_bwd_rows_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
   uint64_t* bar_p = bars + 4;
   uint64_t* bar_o = bars + 5;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
-  float* sPB = reinterpret_cast<float*>(sQ);   // 128 x 64 fp32, xor-swizzled, over sQ|sdO
-  float* sdR = reinterpret_cast<float*>(sV);   // 128 x 65 fp32 over sV|sTV
+  // overlays: PB (128 x 64 fp32, xor-swizzled) over sQ|sdO ; dR (128 x 65 fp32) over sV|sTV
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.x * 128, head = blockIdx.y, b = blockIdx.z;
@@ -109,8 +264,8 @@ attn_bwd_rows_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
   }
   if (warp == 0) tmem_alloc<512>(tmem_slot);
   if (threadIdx.x >= 32 && threadIdx.x < 96) {
-    sBias[threadIdx.x - 32] = p.bias ? p.bias[tab * 64 + threadIdx.x - 32] : 0.f;
-    sDbias[threadIdx.x - 32] = 0.f;
+    sts_f32(smem_u32(sBias) + 4 * (threadIdx.x - 32), p.bias ? p.bias[tab * 64 + threadIdx.x - 32] : 0.f);
+    sts_f32(smem_u32(sDbias) + 4 * (threadIdx.x - 32), 0.f);
   }
   tc_fence_before();
   __syncthreads();
@@ -166,10 +321,16 @@ attn_bwd_rows_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
     const int quarter = warp & 3;
     const int r_local = quarter * 32 + lane;
     const int row = m0 + r_local;
-    const int row_c = min(row, p.N - 1);
-    const uint32_t trow = tmem + (static_cast<uint32_t>(quarter * 32) << 16);
-    float* myR = sR + r_local * kStride;
-    float* mydPB = sdPB + r_local * kStride;
+    RowCtx x;
+    x.trow = tmem + (static_cast<uint32_t>(quarter * 32) << 16);
+    x.s_r = smem_u32(sR) + r_local * kStride * 4;
+    x.s_dpb = smem_u32(sdPB) + r_local * kStride * 4;
+    x.s_pb = smem_u32(sQ) + r_local * 64 * 4;
+    x.s_dr = smem_u32(sV) + r_local * kStride * 4;
+    x.s_bias = smem_u32(sBias);
+    x.row = row;
+    x.row_c = min(row, p.N - 1);
+    x.sw = r_local & 31;
 
     if (any_r) {
       mbar_wait(bar_r, 0);
@@ -178,16 +339,16 @@ attn_bwd_rows_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
       for (int c = 0; c < 2; ++c) {
         uint32_t raw[32];
         if (p.ctx_k) {
-          tmem_ld32(trow + c * 32, raw);
+          tmem_ld32(x.trow + c * 32, raw);
           tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < 32; ++i) myR[c * 32 + i] = p.scale * __uint_as_float(raw[i]);
+          for (int i = 0; i < 32; ++i) sts_f32(x.s_r + 4 * (c * 32 + i), p.scale * __uint_as_float(raw[i]));
         }
         if (p.ctx_v) {
-          tmem_ld32(trow + 64 + c * 32, raw);
+          tmem_ld32(x.trow + 64 + c * 32, raw);
           tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < 32; ++i) mydPB[c * 32 + i] = __uint_as_float(raw[i]);
+          for (int i = 0; i < 32; ++i) sts_f32(x.s_dpb + 4 * (c * 32 + i), __uint_as_float(raw[i]));
         }
       }
       tc_fence_before();
@@ -209,82 +370,15 @@ attn_bwd_rows_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
       }
       lse = p.lse[(static_cast<int64_t>(b) * p.H + head) * p.N + row];
     }
+    x.delta = delta;
+    x.lsel = lse * kLog2e;
+    x.wrow = ((static_cast<int64_t>(b) * p.H + head) * p.N + row) * p.ldw;
     mbar_wait(bar_s, 0);
     tc_fence_after();
 
-    // bucket-sum accumulators (thread-private rows; sPB xor-swizzled to fit 32 KB)
-    float* myPB = sPB + r_local * 64;
-    float* mydR = sdR + r_local * kStride;
-    const int sw = r_local & 31;
-    for (int k = 0; k < kNB; ++k) { myPB[k] = 0.f; mydR[k] = 0.f; }
+    if (p.af_grid == 14) bwd_row_af<14>(p, x);
+    else bwd_row_generic(p, x);
 
-    const uint8_t* ia = p.idx_a ? p.idx_a + static_cast<int64_t>(row_c) * p.ldi : nullptr;
-    const uint8_t* ib = p.idx_b ? p.idx_b + static_cast<int64_t>(row_c) * p.ldi : nullptr;
-    const uint8_t* iva = p.idx_va ? p.idx_va + static_cast<int64_t>(row_c) * p.ldi : nullptr;
-    const uint8_t* ivb = p.idx_vb ? p.idx_vb + static_cast<int64_t>(row_c) * p.ldi : nullptr;
-    const bool use_bias = p.bias != nullptr;
-    const bool want_dr = p.ctx_k || use_bias;
-    const float lsel = lse * kLog2e;
-    const int64_t wrow = ((static_cast<int64_t>(b) * p.H + head) * p.N + row) * p.ldw;
-    const int nchunks = Npad / 16;
-    for (int c = 0; c < nchunks; ++c) {
-      uint32_t rt[16], rp[16];
-      tmem_ld16(trow + c * 16, rt);
-      tmem_ld16(trow + 256 + c * 16, rp);
-      uint4 va = make_uint4(0, 0, 0, 0), vb = va, vva = va, vvb = va;
-      if (ia) va = __ldg(reinterpret_cast<const uint4*>(ia + c * 16));
-      if (ib) vb = __ldg(reinterpret_cast<const uint4*>(ib + c * 16));
-      if (iva) vva = __ldg(reinterpret_cast<const uint4*>(iva + c * 16));
-      if (ivb) vvb = __ldg(reinterpret_cast<const uint4*>(ivb + c * 16));
-      tmem_ld_wait();
-      const uint32_t wa[4] = {va.x, va.y, va.z, va.w}, wb[4] = {vb.x, vb.y, vb.z, vb.w};
-      const uint32_t wva[4] = {vva.x, vva.y, vva.z, vva.w}, wvb[4] = {vvb.x, vvb.y, vvb.z, vvb.w};
-      float pv[16], dt[16];
-#pragma unroll
-      for (int k = 0; k < 16; ++k) {
-        const uint32_t a_id = byte_of(wa, k), b_id = byte_of(wb, k);
-        const uint32_t va_id = byte_of(wva, k), vb_id = byte_of(wvb, k);
-        float t = p.scale * __uint_as_float(rt[k]);
-        if (p.ctx_k) {
-          if (ia) t += myR[a_id];
-          if (ib) t += myR[b_id];
-        }
-        if (use_bias) t += sBias[a_id];
-        float pr = fast_exp2(fmaf(t, kLog2e, -lsel));
-        if (c * 16 + k >= p.N || row >= p.N) pr = 0.f;
-        float dp = __uint_as_float(rp[k]);
-        if (p.ctx_v) {
-          if (iva) dp += mydPB[va_id];
-          if (ivb) dp += mydPB[vb_id];
-        }
-        const float d = pr * (dp - delta);
-        pv[k] = pr;
-        dt[k] = d;
-        if (p.ctx_v) {
-          if (iva) myPB[va_id ^ sw] += pr;
-          if (ivb) myPB[vb_id ^ sw] += pr;
-        }
-        if (want_dr) {
-          if (ia) mydR[a_id] += d;
-          if (ib) mydR[b_id] += d;
-        }
-      }
-      uint32_t pk[8], dk[8];
-#pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        pk[k] = pack_bf16x2(pv[2 * k], pv[2 * k + 1]);
-        dk[k] = pack_bf16x2(dt[2 * k], dt[2 * k + 1]);
-      }
-      tmem_st8(trow + c * 8, dk);   // dT (bf16x2) in place over T, A operand of the dQ MMA
-      if (row < p.N) {
-        uint4* wp = reinterpret_cast<uint4*>(p.ws_p + wrow + c * 16);
-        uint4* wd = reinterpret_cast<uint4*>(p.ws_dt + wrow + c * 16);
-        wp[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-        wp[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
-        wd[0] = make_uint4(dk[0], dk[1], dk[2], dk[3]);
-        wd[1] = make_uint4(dk[4], dk[5], dk[6], dk[7]);
-      }
-    }
     // bucket sums: PB -> workspace ; dR -> workspace + TMEM (A operand of the dQ MMA)
 #pragma unroll
     for (int c = 0; c < 2; ++c) {
@@ -292,13 +386,13 @@ attn_bwd_rows_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
 #pragma unroll
       for (int k = 0; k < 16; ++k) {
         const int b0 = c * 32 + 2 * k;
-        pk[k] = pack_bf16x2(myPB[b0 ^ sw], myPB[(b0 + 1) ^ sw]);
-        dk[k] = pack_bf16x2(mydR[b0], mydR[b0 + 1]);
+        pk[k] = pack_bf16x2(lds_f32(x.s_pb + 4 * (b0 ^ x.sw)), lds_f32(x.s_pb + 4 * ((b0 + 1) ^ x.sw)));
+        dk[k] = pack_bf16x2(lds_f32(x.s_dr + 4 * b0), lds_f32(x.s_dr + 4 * (b0 + 1)));
       }
-      if (p.ctx_k) tmem_st16(trow + Npad / 2 + c * 16, dk);
+      if (p.ctx_k) tmem_st16(x.trow + Npad / 2 + c * 16, dk);
       if (row < p.N) {
-        uint4* wp = reinterpret_cast<uint4*>(p.ws_p + wrow + Npad + c * 32);
-        uint4* wd = reinterpret_cast<uint4*>(p.ws_dt + wrow + Npad + c * 32);
+        uint4* wp = reinterpret_cast<uint4*>(p.ws_p + x.wrow + Npad + c * 32);
+        uint4* wd = reinterpret_cast<uint4*>(p.ws_dt + x.wrow + Npad + c * 32);
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           wp[q] = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
@@ -307,12 +401,13 @@ attn_bwd_rows_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
       }
     }
     if (p.dbias != nullptr && row < p.N) {
-      for (int k = 0; k < kNB; ++k) atomicAdd(&sDbias[k], mydR[k]);
+      for (int k = 0; k < kNB; ++k) atomicAdd(reinterpret_cast<float*>(sDbias) + k, lds_f32(x.s_dr + 4 * k));
     }
     tmem_st_wait();
     tc_fence_before();
     mbar_arrive(bar_p);
 
+    const uint32_t trow = x.trow;
     mbar_wait(bar_o, 0);
     tc_fence_after();
     __nv_bfloat16* qrow = p.dqkv + (static_cast<int64_t>(b) * p.N + row) * p.lddqkv + head * kD;
@@ -338,7 +433,8 @@ attn_bwd_rows_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
 
   tc_fence_before();
   __syncthreads();
-  if (p.dbias != nullptr && threadIdx.x < 64) atomicAdd(p.dbias + tab * 64 + threadIdx.x, sDbias[threadIdx.x]);
+  if (p.dbias != nullptr && threadIdx.x < 64)
+    atomicAdd(p.dbias + tab * 64 + threadIdx.x, lds_f32(smem_u32(sDbias) + 4 * threadIdx.x));
   if (warp == 0) {
     tc_fence_after();
     tmem_dealloc<512>(tmem);
@@ -368,9 +464,8 @@ __global__ void __launch_bounds__(kColsThreads, 1)
 attn_bwd_cols_kernel(const __grid_constant__ CUtensorMap map_wp, const __grid_constant__ CUtensorMap map_wd,
                      const __grid_constant__ CUtensorMap map_do, const __grid_constant__ CUtensorMap map_q,
                      const BwdColsParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>(
-      (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  extern __shared__ __align__(1024) uint8_t smem[];
+  require_smem_alignment(smem);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kColStages * kColStageBytes);
   uint64_t* full = bars;
   uint64_t* empty = bars + kColStages;
@@ -509,6 +604,11 @@ extern "C" int cream_attn_bwd(const cream_attn_desc* d, void* stream_) {
   p.ctx_k = ctx_k; p.ctx_v = ctx_v; p.shared_tables = d->tables_per_head ? 0 : 1;
   p.idx_a = d->idx_a; p.idx_b = d->idx_b; p.idx_va = d->idx_va; p.idx_vb = d->idx_vb; p.ldi = d->ld_idx;
   p.bias = d->bias_pack;
+  if (d->af_grid == 14 && d->af_max_rel >= 13 && d->af_grid * d->af_grid + 1 == d->N && ctx_k && ctx_v &&
+      !d->bias_pack && 2 * d->af_max_rel + 2 <= 32) {
+    p.af_grid = d->af_grid;
+    p.af_max_rel = d->af_max_rel;
+  }
   p.out = static_cast<const __nv_bfloat16*>(d->out); p.ldo = d->ld_out;
   p.dout = static_cast<const __nv_bfloat16*>(d->dout); p.lddo = d->ld_dout;
   p.lse = d->lse;
@@ -545,7 +645,7 @@ extern "C" int cream_attn_bwd(const cream_attn_desc* d, void* stream_) {
     CB_CUDA_OK(cudaFuncSetAttribute(attn_bwd_cols_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
-  const size_t smem_rows = 1024 + 2 * 16384 + static_cast<size_t>(Npad) * 128 + 8192 +
+  const size_t smem_rows = 2 * 16384 + static_cast<size_t>(Npad) * 128 + 8192 +
                            std::max<size_t>(Npad * 128, 26 * 1024) + 8192 + 2 * 128 * kStride * 4 + 2 * 64 * 4 + 128;
   CB_REQUIRE(smem_rows <= 227 * 1024, "shared memory budget");
   dim3 grid(ceil_div(d->N, 128), d->H, d->B);
@@ -560,7 +660,7 @@ extern "C" int cream_attn_bwd(const cream_attn_desc* d, void* stream_) {
   c.dqkv = static_cast<__nv_bfloat16*>(d->dqkv); c.lddqkv = d->ld_dqkv;
   c.dtk = ctx_k ? d->dtk_pack : nullptr;
   c.dtv = ctx_v ? d->dtv_pack : nullptr;
-  const size_t smem_cols = 1024 + kColStages * kColStageBytes + 256;
+  const size_t smem_cols = kColStages * kColStageBytes + 256;
   dim3 grid2(d->H, d->B);
   attn_bwd_cols_kernel<<<grid2, kColsThreads, smem_cols, stream>>>(*mwp, *mwd, *mdo64, *mq64, c);
   return check_last("attn_bwd_cols_kernel");

@@ -1,0 +1,70 @@
+// Shared helpers of the fused attention kernels: explicit shared-memory accessors (32-bit
+// shared addresses, so the compiler can never fall back to generic loads), exp2, packed
+// TMEM stores and index-byte extraction.
+#pragma once
+#include <cuda_fp16.h>
+
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace cb {
+
+constexpr float kLog2e = 1.4426950408889634f;
+
+__device__ __forceinline__ float lds_f32(uint32_t a) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ void sts_f32(uint32_t a, float v) {
+  asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t lds_u32(uint32_t a) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ void sts_u32(uint32_t a, uint32_t v) {
+  asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
+}
+__device__ __forceinline__ float4 lds_f32x4(uint32_t a) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ void sts_f32x4(uint32_t a, float4 v) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+               : "memory");
+}
+__device__ __forceinline__ float lds_f16(uint32_t a) {
+  unsigned short h;
+  asm volatile("ld.shared.u16 %0, [%1];" : "=h"(h) : "r"(a));
+  return __half2float(__ushort_as_half(h));
+}
+
+__device__ __forceinline__ float fast_exp2(float x) {
+  float y;
+  asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+      : "memory");
+}
+
+__device__ __forceinline__ uint32_t byte_of(const uint32_t (&w)[4], int k) {
+  return (w[k >> 2] >> (8 * (k & 3))) & 0xFF;
+}
+
+// Dynamic shared memory base, required to be 1024-byte aligned (128B-swizzle atoms).
+__device__ __forceinline__ void require_smem_alignment(const void* smem) {
+  if (threadIdx.x == 0 && (smem_u32(smem) & 1023u) != 0) {
+    printf("cream_b200: dynamic shared memory is not 1024-byte aligned\n");
+    __trap();
+  }
+}
+
+}  // namespace cb

@@ -19,10 +19,7 @@
 //   warps 1..4       : one thread per query row: R copy-out, softmax, epilogue
 // TMEM columns: S fp32 [0,Npad) -> P bf16x2 in place [0,Npad/2) | PB [Npad/2,Npad/2+32);
 //               R fp32 [192,256) (dead before S cols >= 192 are produced); O fp32 [192,256).
-#include <cuda_fp16.h>
-
-#include "common.cuh"
-#include "ptx.cuh"
+#include "attention_common.cuh"
 
 namespace cb {
 namespace {
@@ -31,14 +28,15 @@ constexpr int kD = 64;              // head dim
 constexpr int kNB = 64;             // packed bucket rows (two tables of <= 32, or one of <= 64)
 constexpr int kThreads = 160;
 constexpr int kRStride = 66;        // halfs per row of the staged R tile (bank spread)
-constexpr int kPBStride = 65;       // floats per row of the bucket-sum tile
-constexpr float kLog2e = 1.4426950408889634f;
+constexpr int kPBStride = 65;       // floats per row of the bucket-sum tile (generic gather path)
+constexpr int kPBStrideAF = 68;     // floats per row, 16-byte aligned rows (structured path)
 
 struct AttnFwdParams {
   int B, H, N, Npad;
   float scale;
   int ctx_k, ctx_v;                    // contextual tables on K / V present
   int shared_tables;                   // 1: one table pack for all heads
+  int af_grid, af_max_rel;             // AutoFormer structured mode (0 = generic index tables)
   const uint8_t* idx_a; const uint8_t* idx_b;   // K-side gather indices (N, ldi), values < 64
   const uint8_t* idx_va; const uint8_t* idx_vb; // V-side
   int ldi;
@@ -47,36 +45,210 @@ struct AttnFwdParams {
   float* lse;                          // (B, H, N)
 };
 
-__device__ __forceinline__ float fast_exp2(float x) {
-  float y;
-  asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
+// ---------------------------------------------------------------------------------------
+// Softmax over one query row held in TMEM (one thread per row), generic gather tables.
+//   pass 1: t = scale*S + R[idx_a] + R[idx_b] (+ bias[idx_a]); running max; t written back
+//   pass 2: p = exp(t - max); row sum; P -> bf16x2 in place; bucket sums PB[idx_v*] += p
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ void softmax_generic(const AttnFwdParams& p, uint32_t trow, uint32_t sr_row,
+                                                uint32_t spb_row, uint32_t sbias, int row_c, float& mx_out,
+                                                float& sum_out) {
+  const int Npad = p.Npad;
+  const int nchunks = Npad / 16;
+  const uint8_t* ia = p.idx_a ? p.idx_a + static_cast<int64_t>(row_c) * p.ldi : nullptr;
+  const uint8_t* ib = p.idx_b ? p.idx_b + static_cast<int64_t>(row_c) * p.ldi : nullptr;
+  const bool use_bias = p.bias != nullptr;
+  float mx = -INFINITY;
+  for (int c = 0; c < nchunks; ++c) {
+    uint32_t raw[16];
+    tmem_ld16(trow + c * 16, raw);
+    uint4 va = make_uint4(0, 0, 0, 0), vb = make_uint4(0, 0, 0, 0);
+    if (ia) va = __ldg(reinterpret_cast<const uint4*>(ia + c * 16));
+    if (ib) vb = __ldg(reinterpret_cast<const uint4*>(ib + c * 16));
+    tmem_ld_wait();
+    const uint32_t wa[4] = {va.x, va.y, va.z, va.w};
+    const uint32_t wb[4] = {vb.x, vb.y, vb.z, vb.w};
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      float t = p.scale * __uint_as_float(raw[k]);
+      const uint32_t a_id = byte_of(wa, k);
+      if (p.ctx_k) {
+        if (ia) t += lds_f16(sr_row + 2 * a_id);
+        if (ib) t += lds_f16(sr_row + 2 * byte_of(wb, k));
+      }
+      if (use_bias) t += lds_f32(sbias + 4 * a_id);
+      if (c * 16 + k >= p.N) t = -INFINITY;
+      mx = fmaxf(mx, t);
+      raw[k] = __float_as_uint(t);
+    }
+    tmem_st16(trow + c * 16, raw);
+  }
+  tmem_st_wait();
+
+  if (p.ctx_v) {
+    for (int k = 0; k < kNB; ++k) sts_f32(spb_row + 4 * k, 0.f);
+  }
+  const uint8_t* iva = p.idx_va ? p.idx_va + static_cast<int64_t>(row_c) * p.ldi : nullptr;
+  const uint8_t* ivb = p.idx_vb ? p.idx_vb + static_cast<int64_t>(row_c) * p.ldi : nullptr;
+  const float mxl = mx * kLog2e;
+  float sum = 0.f;
+  for (int c = 0; c < nchunks; ++c) {
+    uint32_t raw[16];
+    tmem_ld16(trow + c * 16, raw);
+    uint4 va = make_uint4(0, 0, 0, 0), vb = make_uint4(0, 0, 0, 0);
+    if (iva) va = __ldg(reinterpret_cast<const uint4*>(iva + c * 16));
+    if (ivb) vb = __ldg(reinterpret_cast<const uint4*>(ivb + c * 16));
+    tmem_ld_wait();
+    const uint32_t wa[4] = {va.x, va.y, va.z, va.w};
+    const uint32_t wb[4] = {vb.x, vb.y, vb.z, vb.w};
+    float pv[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      pv[k] = fast_exp2(fmaf(__uint_as_float(raw[k]), kLog2e, -mxl));
+      sum += pv[k];
+    }
+    if (p.ctx_v) {
+#pragma unroll
+      for (int k = 0; k < 16; ++k) {
+        // padded key columns have p == 0 exactly, so their (zero) ids are harmless
+        if (iva) { const uint32_t a = spb_row + 4 * byte_of(wa, k); sts_f32(a, lds_f32(a) + pv[k]); }
+        if (ivb) { const uint32_t a = spb_row + 4 * byte_of(wb, k); sts_f32(a, lds_f32(a) + pv[k]); }
+      }
+    }
+    uint32_t pk[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) pk[k] = pack_bf16x2(pv[2 * k], pv[2 * k + 1]);
+    tmem_st8(trow + c * 8, pk);
+  }
+  if (p.ctx_v) {
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      uint32_t pk[16];
+#pragma unroll
+      for (int k = 0; k < 16; ++k)
+        pk[k] = pack_bf16x2(lds_f32(spb_row + 4 * (c * 32 + 2 * k)), lds_f32(spb_row + 4 * (c * 32 + 2 * k + 1)));
+      tmem_st16(trow + Npad / 2 + c * 16, pk);
+    }
+  }
+  mx_out = mx;
+  sum_out = sum;
 }
 
-__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8]) {
-  asm volatile(
-      "tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr),
-      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
-      : "memory");
+// ---------------------------------------------------------------------------------------
+// AutoFormer-structured softmax (multihead_super.py:40-59): for a G x G patch grid + cls,
+//   idx_v[i,j] = rj - ri + M1,  idx_h[i,j] = cj - ci + M1   (i,j >= 1; M1 = max_rel + 1;
+//   the clamp never binds when G-1 <= max_rel), and bucket 0 for the cls row / column.
+// The 2*G gather operands of a row live in registers; with the column loop fully unrolled
+// (rj, cj) are compile-time, so the gather costs two FADDs per element and the value-side
+// bucket sums are row / column sums kept in registers (no shared-memory read-modify-write).
+// ---------------------------------------------------------------------------------------
+template <int G>
+__device__ __forceinline__ void softmax_af(const AttnFwdParams& p, uint32_t trow, uint32_t sr_row,
+                                           uint32_t spb_row, int row, float& mx_out, float& sum_out) {
+  constexpr int N = G * G + 1;
+  constexpr int NPAD = (N + 15) / 16 * 16;
+  constexpr int NCH = NPAD / 16;
+  const int M1 = p.af_max_rel + 1;
+  const bool patch = row >= 1 && row < N;
+  const int qi = patch ? row - 1 : 0;
+  const int ri = qi / G, ci = qi - ri * G;
+  const float r0v = lds_f16(sr_row), r0h = lds_f16(sr_row + 2 * 32);
+  const float r0 = r0v + r0h;
+  float rv[G], rh[G];
+#pragma unroll
+  for (int t = 0; t < G; ++t) {
+    rv[t] = patch ? lds_f16(sr_row + 2 * (M1 - ri + t)) : r0v;
+    rh[t] = patch ? lds_f16(sr_row + 2 * (32 + M1 - ci + t)) : r0h;
+  }
+  float mx = -INFINITY;
+#pragma unroll
+  for (int c = 0; c < NCH; ++c) {
+    uint32_t raw[16];
+    tmem_ld16(trow + c * 16, raw);
+    tmem_ld_wait();
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      const int j = c * 16 + k;
+      float t;
+      if (j >= N) t = -INFINITY;
+      else if (j == 0) t = fmaf(p.scale, __uint_as_float(raw[k]), r0);
+      else t = fmaf(p.scale, __uint_as_float(raw[k]), rv[(j - 1) / G]) + rh[(j - 1) % G];
+      mx = fmaxf(mx, t);
+      raw[k] = __float_as_uint(t);
+    }
+    tmem_st16(trow + c * 16, raw);
+  }
+  tmem_st_wait();
+
+  float prow[G], pcol[G], p0 = 0.f, sum = 0.f;
+#pragma unroll
+  for (int t = 0; t < G; ++t) { prow[t] = 0.f; pcol[t] = 0.f; }
+  const float mxl = mx * kLog2e;
+#pragma unroll
+  for (int c = 0; c < NCH; ++c) {
+    uint32_t raw[16];
+    tmem_ld16(trow + c * 16, raw);
+    tmem_ld_wait();
+    float pv[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      const int j = c * 16 + k;
+      pv[k] = fast_exp2(fmaf(__uint_as_float(raw[k]), kLog2e, -mxl));
+      sum += pv[k];
+      if (j == 0) p0 = pv[k];
+      else if (j < N) { prow[(j - 1) / G] += pv[k]; pcol[(j - 1) % G] += pv[k]; }
+    }
+    uint32_t pk[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) pk[k] = pack_bf16x2(pv[2 * k], pv[2 * k + 1]);
+    tmem_st8(trow + c * 8, pk);
+  }
+  // bucket sums -> (thread-private) shared row -> bf16x2 -> TMEM columns [NPAD/2, NPAD/2+32)
+#pragma unroll
+  for (int q = 0; q < 16; ++q) sts_f32x4(spb_row + 16 * q, make_float4(0.f, 0.f, 0.f, 0.f));
+  if (patch) {
+#pragma unroll
+    for (int t = 0; t < G; ++t) {
+      sts_f32(spb_row + 4 * (M1 - ri + t), prow[t]);
+      sts_f32(spb_row + 4 * (32 + M1 - ci + t), pcol[t]);
+    }
+    sts_f32(spb_row, p0);
+    sts_f32(spb_row + 4 * 32, p0);
+  } else {
+    sts_f32(spb_row, sum);
+    sts_f32(spb_row + 4 * 32, sum);
+  }
+#pragma unroll
+  for (int c = 0; c < 2; ++c) {
+    uint32_t pk[16];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const float4 v = lds_f32x4(spb_row + 4 * (c * 32 + 4 * q));
+      pk[2 * q] = pack_bf16x2(v.x, v.y);
+      pk[2 * q + 1] = pack_bf16x2(v.z, v.w);
+    }
+    tmem_st16(trow + NPAD / 2 + c * 16, pk);
+  }
+  mx_out = mx;
+  sum_out = sum;
 }
 
 __global__ void __launch_bounds__(kThreads, 2)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_kv,
                 const __grid_constant__ CUtensorMap map_tk, const __grid_constant__ CUtensorMap map_tv,
                 const AttnFwdParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>(
-      (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  extern __shared__ __align__(1024) uint8_t smem[];
+  require_smem_alignment(smem);
   const int kv_bytes = p.Npad * 128;
-  const int k_slot = max(kv_bytes, 9216);  // sQ + sTK + sK must hold the 128 x 65 fp32 PB overlay
+  const int k_slot = max(kv_bytes, 11 * 1024);  // sQ + sTK + sK must hold the 128 x 68 fp32 PB overlay
   uint8_t* sQ = smem;
   uint8_t* sTK = sQ + 16384;
   uint8_t* sK = sTK + 8192;
   uint8_t* sV = sK + k_slot;         // [V ; TV] contiguous rows
   uint8_t* sTV = sV + kv_bytes;
-  __half* sR = reinterpret_cast<__half*>(sTV + 8192);
-  float* sBias = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(sR) + 128 * kRStride * 2);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sBias + 64);
+  uint8_t* sR = sTV + 8192;          // fp16 [128][kRStride]
+  uint8_t* sBias = sR + 128 * kRStride * 2;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sBias + 64 * 4);
   uint64_t* bar_qk = bars + 0;
   uint64_t* bar_v = bars + 1;
   uint64_t* bar_r = bars + 2;
@@ -85,7 +257,6 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
   uint64_t* bar_p = bars + 5;
   uint64_t* bar_o = bars + 6;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
-  float* sPB = reinterpret_cast<float*>(smem);  // overlays sQ/sK/sTK once S is complete
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.x * 128, head = blockIdx.y, b = blockIdx.z;
@@ -107,7 +278,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
   }
   if (warp == 0) tmem_alloc<256>(tmem_slot);
   if (p.bias != nullptr && threadIdx.x >= 32 && threadIdx.x < 96)
-    sBias[threadIdx.x - 32] = p.bias[(p.shared_tables ? 0 : head) * 64 + threadIdx.x - 32];
+    sts_f32(smem_u32(sBias) + 4 * (threadIdx.x - 32),
+            p.bias[(p.shared_tables ? 0 : head) * 64 + threadIdx.x - 32]);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -176,9 +348,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
     const int r_local = quarter * 32 + lane;
     const int row = m0 + r_local;                 // query index within the image
     const int row_c = min(row, p.N - 1);          // clamp for index-table reads of padding rows
-    const uint32_t lane_base = static_cast<uint32_t>(quarter * 32) << 16;
-    const uint32_t trow = tmem + lane_base;
-    const __half* myR = sR + r_local * kRStride;
+    const uint32_t trow = tmem + (static_cast<uint32_t>(quarter * 32) << 16);
+    const uint32_t sr_row = smem_u32(sR) + r_local * kRStride * 2;
 
     if (p.ctx_k) {
       mbar_wait(bar_r, 0);
@@ -188,11 +359,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         uint32_t raw[32];
         tmem_ld32(trow + 192 + c * 32, raw);
         tmem_ld_wait();
-        __half2* dst = reinterpret_cast<__half2*>(sR + r_local * kRStride + c * 32);
 #pragma unroll
-        for (int i = 0; i < 16; ++i)
-          dst[i] = __floats2half2_rn(p.scale * __uint_as_float(raw[2 * i]),
-                                     p.scale * __uint_as_float(raw[2 * i + 1]));
+        for (int i = 0; i < 16; ++i) {
+          const __half2 h2 = __floats2half2_rn(p.scale * __uint_as_float(raw[2 * i]),
+                                               p.scale * __uint_as_float(raw[2 * i + 1]));
+          sts_u32(sr_row + 4 * (c * 16 + i), *reinterpret_cast<const uint32_t*>(&h2));
+        }
       }
       tc_fence_before();
       mbar_arrive(bar_rfree);
@@ -200,85 +372,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
     mbar_wait(bar_s, 0);
     tc_fence_after();
 
-    const int nchunks = Npad / 16;
-    const uint8_t* ia = p.idx_a ? p.idx_a + static_cast<int64_t>(row_c) * p.ldi : nullptr;
-    const uint8_t* ib = p.idx_b ? p.idx_b + static_cast<int64_t>(row_c) * p.ldi : nullptr;
-    const bool use_bias = p.bias != nullptr;
-
-    // ---- pass 1: t = scale*S + gathers ; running max ; write t back ----
-    float mx = -INFINITY;
-    for (int c = 0; c < nchunks; ++c) {
-      uint32_t raw[16];
-      tmem_ld16(trow + c * 16, raw);
-      uint4 va = make_uint4(0, 0, 0, 0), vb = make_uint4(0, 0, 0, 0);
-      if (ia) va = __ldg(reinterpret_cast<const uint4*>(ia + c * 16));
-      if (ib) vb = __ldg(reinterpret_cast<const uint4*>(ib + c * 16));
-      tmem_ld_wait();
-      const uint32_t wa[4] = {va.x, va.y, va.z, va.w};
-      const uint32_t wb[4] = {vb.x, vb.y, vb.z, vb.w};
-#pragma unroll
-      for (int k = 0; k < 16; ++k) {
-        float t = p.scale * __uint_as_float(raw[k]);
-        const uint32_t a_id = (wa[k >> 2] >> (8 * (k & 3))) & 0xFF;
-        if (p.ctx_k) {
-          if (ia) t += __half2float(myR[a_id]);
-          if (ib) t += __half2float(myR[(wb[k >> 2] >> (8 * (k & 3))) & 0xFF]);
-        }
-        if (use_bias) t += sBias[a_id];
-        if (c * 16 + k >= p.N) t = -INFINITY;
-        mx = fmaxf(mx, t);
-        raw[k] = __float_as_uint(t);
-      }
-      tmem_st16(trow + c * 16, raw);
-    }
-    tmem_st_wait();
-
-    // ---- pass 2: p = exp(t - max) ; row sum ; P (bf16) in place ; bucket sums ----
-    float* myPB = sPB + r_local * kPBStride;
-    if (p.ctx_v) {
-#pragma unroll 8
-      for (int k = 0; k < kNB; ++k) myPB[k] = 0.f;
-    }
-    const uint8_t* iva = p.idx_va ? p.idx_va + static_cast<int64_t>(row_c) * p.ldi : nullptr;
-    const uint8_t* ivb = p.idx_vb ? p.idx_vb + static_cast<int64_t>(row_c) * p.ldi : nullptr;
-    const float mxl = mx * kLog2e;
-    float sum = 0.f;
-    for (int c = 0; c < nchunks; ++c) {
-      uint32_t raw[16];
-      tmem_ld16(trow + c * 16, raw);
-      uint4 va = make_uint4(0, 0, 0, 0), vb = make_uint4(0, 0, 0, 0);
-      if (iva) va = __ldg(reinterpret_cast<const uint4*>(iva + c * 16));
-      if (ivb) vb = __ldg(reinterpret_cast<const uint4*>(ivb + c * 16));
-      tmem_ld_wait();
-      const uint32_t wa[4] = {va.x, va.y, va.z, va.w};
-      const uint32_t wb[4] = {vb.x, vb.y, vb.z, vb.w};
-      float pv[16];
-#pragma unroll
-      for (int k = 0; k < 16; ++k) {
-        pv[k] = fast_exp2(fmaf(__uint_as_float(raw[k]), kLog2e, -mxl));
-        sum += pv[k];
-      }
-      if (p.ctx_v) {
-#pragma unroll
-        for (int k = 0; k < 16; ++k) {
-          // padded key columns have p == 0 exactly, so their (arbitrary) ids are harmless
-          if (iva) myPB[(wa[k >> 2] >> (8 * (k & 3))) & 0xFF] += pv[k];
-          if (ivb) myPB[(wb[k >> 2] >> (8 * (k & 3))) & 0xFF] += pv[k];
-        }
-      }
-      uint32_t pk[8];
-#pragma unroll
-      for (int k = 0; k < 8; ++k) pk[k] = pack_bf16x2(pv[2 * k], pv[2 * k + 1]);
-      tmem_st8(trow + c * 8, pk);
-    }
-    if (p.ctx_v) {
-#pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        uint32_t pk[16];
-#pragma unroll
-        for (int k = 0; k < 16; ++k) pk[k] = pack_bf16x2(myPB[c * 32 + 2 * k], myPB[c * 32 + 2 * k + 1]);
-        tmem_st16(trow + Npad / 2 + c * 16, pk);
-      }
+    float mx, sum;
+    if (p.af_grid == 14) {
+      softmax_af<14>(p, trow, sr_row, smem_u32(smem) + r_local * kPBStrideAF * 4, row, mx, sum);
+    } else {
+      softmax_generic(p, trow, sr_row, smem_u32(smem) + r_local * kPBStride * 4, smem_u32(sBias), row_c, mx, sum);
     }
     tmem_st_wait();
     tc_fence_before();
@@ -348,6 +446,15 @@ extern "C" int cream_attn_fwd(const cream_attn_desc* d, void* stream_) {
   p.bias = d->bias_pack;
   p.out = static_cast<__nv_bfloat16*>(d->out); p.ldo = d->ld_out;
   p.lse = d->lse;
+  // structured AutoFormer gather: square grid + cls, both tables, clamp never binding
+  if (d->af_grid > 0) {
+    CB_REQUIRE(d->af_grid * d->af_grid + 1 == d->N && ctx_k && ctx_v && !d->bias_pack, "af mode needs N = g*g+1 and both table packs");
+    CB_REQUIRE(2 * d->af_max_rel + 2 <= 32, "af tables must fit 32 packed rows");
+    if (d->af_grid == 14 && d->af_max_rel >= d->af_grid - 1) {
+      p.af_grid = d->af_grid;
+      p.af_max_rel = d->af_max_rel;
+    }
+  }
 
   const uint64_t dims[3] = {static_cast<uint64_t>(3 * d->H * kD), static_cast<uint64_t>(d->N),
                             static_cast<uint64_t>(d->B)};
@@ -371,7 +478,7 @@ extern "C" int cream_attn_fwd(const cream_attn_desc* d, void* stream_) {
                                  : mq;
   if (!mq || !mkv || !mtk || !mtv) return CREAM_ERR_CUDA;
 
-  const size_t smem_bytes = 1024 + 16384 + std::max<size_t>(Npad * 128, 9216) +
+  const size_t smem_bytes = 16384 + std::max<size_t>(Npad * 128, 11 * 1024) +
                             static_cast<size_t>(Npad) * 128 + 2 * 8192 + 128 * kRStride * 2 + 64 * 4 + 128;
   static bool attr_set = false;
   if (!attr_set) {

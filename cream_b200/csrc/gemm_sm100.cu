@@ -54,13 +54,15 @@ struct WorkItem {
 };
 
 __device__ __forceinline__ WorkItem decode_work(const GemmKernelParams& p, int w) {
+  // N-fastest: the (group, n-tile) siblings of one M tile run on neighbouring CTAs at the same
+  // time, so the A tile (the activation stream) is fetched from HBM once and hit in L2 by the rest.
   WorkItem it;
-  it.mt = w % p.num_mt;
-  int rest = w / p.num_mt;
-  it.nt = rest % p.num_nt;
-  rest /= p.num_nt;
+  it.nt = w % p.num_nt;
+  int rest = w / p.num_nt;
   it.g = rest % p.groups;
-  const int ks = rest / p.groups;
+  rest /= p.groups;
+  it.mt = rest % p.num_mt;
+  const int ks = rest / p.num_mt;
   it.kb0 = ks * p.kb_per_split;
   it.kb1 = min(p.kb_total, it.kb0 + p.kb_per_split);
   return it;

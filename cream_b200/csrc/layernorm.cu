@@ -9,8 +9,8 @@
 namespace cb {
 namespace {
 
-constexpr int kWarps = 8;
-constexpr int kMaxPerLane = 24;  // supports E <= 768
+constexpr int kWarps = 4;
+constexpr int kMaxPerLane = 24;  // supports E <= 768 (kernels are instantiated for 8 / 16 / 24)
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
@@ -18,7 +18,7 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
-template <bool kOutF32>
+template <bool kOutF32, int kPer>
 __global__ void __launch_bounds__(kWarps * 32)
 ln_fwd_kernel(const float* __restrict__ x, int64_t ldx, const float* __restrict__ gamma,
               const float* __restrict__ beta, float eps, void* __restrict__ out, int64_t ldo,
@@ -28,10 +28,10 @@ ln_fwd_kernel(const float* __restrict__ x, int64_t ldx, const float* __restrict_
   for (int64_t r = static_cast<int64_t>(blockIdx.x) * kWarps + warp; r < rows;
        r += static_cast<int64_t>(gridDim.x) * kWarps) {
     const float* xr = x + r * ldx;
-    float v[kMaxPerLane];
+    float v[kPer];
     float s = 0.f;
 #pragma unroll
-    for (int i = 0; i < kMaxPerLane; ++i) {
+    for (int i = 0; i < kPer; ++i) {
       const int c = lane + i * 32;
       v[i] = (i < per && c < E) ? xr[c] : 0.f;
       s += v[i];
@@ -39,7 +39,7 @@ ln_fwd_kernel(const float* __restrict__ x, int64_t ldx, const float* __restrict_
     const float mu = warp_sum(s) / E;
     float q = 0.f;
 #pragma unroll
-    for (int i = 0; i < kMaxPerLane; ++i) {
+    for (int i = 0; i < kPer; ++i) {
       const int c = lane + i * 32;
       const float d = (i < per && c < E) ? v[i] - mu : 0.f;
       q += d * d;
@@ -50,7 +50,7 @@ ln_fwd_kernel(const float* __restrict__ x, int64_t ldx, const float* __restrict_
       if (rstd) rstd[r] = rs;
     }
 #pragma unroll
-    for (int i = 0; i < kMaxPerLane; ++i) {
+    for (int i = 0; i < kPer; ++i) {
       const int c = lane + i * 32;
       if (i < per && c < E) {
         const float y = (v[i] - mu) * rs * __ldg(gamma + c) + __ldg(beta + c);
@@ -63,7 +63,7 @@ ln_fwd_kernel(const float* __restrict__ x, int64_t ldx, const float* __restrict_
 
 // dX = resid_grad + rstd * (dy*g - mean(dy*g) - xhat * mean(dy*g*xhat)); dgamma/dbeta via
 // per-lane register partials -> shared -> global atomics.
-template <bool kDyF32>
+template <bool kDyF32, int kPer>
 __global__ void __launch_bounds__(kWarps * 32)
 ln_bwd_kernel(const void* __restrict__ dy, int64_t lddy, const float* __restrict__ x, int64_t ldx,
               const float* __restrict__ gamma, const float* __restrict__ mean,
@@ -75,17 +75,17 @@ ln_bwd_kernel(const void* __restrict__ dy, int64_t lddy, const float* __restrict
   const int per = (E + 31) >> 5;
   for (int i = threadIdx.x; i < 2 * E; i += blockDim.x) sacc[i] = 0.f;
   __syncthreads();
-  float pg[kMaxPerLane], pb[kMaxPerLane];
+  float pg[kPer], pb[kPer];
 #pragma unroll
-  for (int i = 0; i < kMaxPerLane; ++i) { pg[i] = 0.f; pb[i] = 0.f; }
+  for (int i = 0; i < kPer; ++i) { pg[i] = 0.f; pb[i] = 0.f; }
   for (int64_t r = static_cast<int64_t>(blockIdx.x) * kWarps + warp; r < rows;
        r += static_cast<int64_t>(gridDim.x) * kWarps) {
     const float mu = mean[r], rs = rstd[r];
     const float* xr = x + r * ldx;
-    float xh[kMaxPerLane], dg[kMaxPerLane];
+    float xh[kPer], dg[kPer];
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-    for (int i = 0; i < kMaxPerLane; ++i) {
+    for (int i = 0; i < kPer; ++i) {
       const int c = lane + i * 32;
       if (i < per && c < E) {
         const float d = kDyF32 ? static_cast<const float*>(dy)[r * lddy + c]
@@ -104,7 +104,7 @@ ln_bwd_kernel(const void* __restrict__ dy, int64_t lddy, const float* __restrict
     s1 = warp_sum(s1) / E;
     s2 = warp_sum(s2) / E;
 #pragma unroll
-    for (int i = 0; i < kMaxPerLane; ++i) {
+    for (int i = 0; i < kPer; ++i) {
       const int c = lane + i * 32;
       if (i < per && c < E) {
         float g = rs * (dg[i] - s1 - xh[i] * s2);
@@ -114,7 +114,7 @@ ln_bwd_kernel(const void* __restrict__ dy, int64_t lddy, const float* __restrict
     }
   }
 #pragma unroll
-  for (int i = 0; i < kMaxPerLane; ++i) {
+  for (int i = 0; i < kPer; ++i) {
     const int c = lane + i * 32;
     if (i < per && c < E) {
       atomicAdd(&sacc[c], pg[i]);
@@ -138,12 +138,13 @@ extern "C" int cream_layernorm_fwd(const float* x, int64_t ldx, const float* gam
   if (rows == 0) return CREAM_OK;
   CB_REQUIRE(x && gamma && beta && out && rows > 0, "null pointer");
   CB_REQUIRE(E >= 1 && E <= 32 * kMaxPerLane, "embed dim must be <= 768");
-  const int grid = static_cast<int>(std::min<int64_t>(ceil_div64(rows, kWarps), kNumSMs * 8));
+  const int grid = static_cast<int>(std::min<int64_t>(ceil_div64(rows, kWarps), kNumSMs * 16));
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  if (out_f32)
-    ln_fwd_kernel<true><<<grid, kWarps * 32, 0, stream>>>(x, ldx, gamma, beta, eps, out, ldo, mean, rstd, rows, E);
-  else
-    ln_fwd_kernel<false><<<grid, kWarps * 32, 0, stream>>>(x, ldx, gamma, beta, eps, out, ldo, mean, rstd, rows, E);
+#define CB_LN_FWD(F32, PER) \
+  ln_fwd_kernel<F32, PER><<<grid, kWarps * 32, 0, stream>>>(x, ldx, gamma, beta, eps, out, ldo, mean, rstd, rows, E)
+  if (out_f32) { if (E <= 256) CB_LN_FWD(true, 8); else if (E <= 512) CB_LN_FWD(true, 16); else CB_LN_FWD(true, 24); }
+  else { if (E <= 256) CB_LN_FWD(false, 8); else if (E <= 512) CB_LN_FWD(false, 16); else CB_LN_FWD(false, 24); }
+#undef CB_LN_FWD
   return check_last("ln_fwd_kernel");
 }
 
@@ -155,12 +156,14 @@ extern "C" int cream_layernorm_bwd(const void* dy, int64_t lddy, int dy_f32, con
   if (rows == 0) return CREAM_OK;
   CB_REQUIRE(dy && x && gamma && mean && rstd && dx && dgamma && dbeta, "null pointer");
   CB_REQUIRE(E >= 1 && E <= 32 * kMaxPerLane, "embed dim must be <= 768");
-  const int grid = static_cast<int>(std::min<int64_t>(ceil_div64(rows, kWarps), kNumSMs * 4));
+  const int grid = static_cast<int>(std::min<int64_t>(ceil_div64(rows, kWarps), kNumSMs * 8));
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   const size_t smem = 2 * E * sizeof(float);
-  if (dy_f32)
-    ln_bwd_kernel<true><<<grid, kWarps * 32, smem, stream>>>(dy, lddy, x, ldx, gamma, mean, rstd, resid_grad, ldrg, dx, lddx, dgamma, dbeta, rows, E);
-  else
-    ln_bwd_kernel<false><<<grid, kWarps * 32, smem, stream>>>(dy, lddy, x, ldx, gamma, mean, rstd, resid_grad, ldrg, dx, lddx, dgamma, dbeta, rows, E);
+#define CB_LN_BWD(F32, PER)                                                                             \
+  ln_bwd_kernel<F32, PER><<<grid, kWarps * 32, smem, stream>>>(dy, lddy, x, ldx, gamma, mean, rstd, resid_grad, \
+                                                            ldrg, dx, lddx, dgamma, dbeta, rows, E)
+  if (dy_f32) { if (E <= 256) CB_LN_BWD(true, 8); else if (E <= 512) CB_LN_BWD(true, 16); else CB_LN_BWD(true, 24); }
+  else { if (E <= 256) CB_LN_BWD(false, 8); else if (E <= 512) CB_LN_BWD(false, 16); else CB_LN_BWD(false, 24); }
+#undef CB_LN_BWD
   return check_last("ln_bwd_kernel");
 }

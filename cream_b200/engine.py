@@ -141,6 +141,7 @@ def forward(P: Dict[str, torch.Tensor], geo: SupernetGeometry, config: dict, ima
         iv, ih, _, _ = ops.autoformer_index_tables(N, geo.max_relative_position, dev)
         idx = (iv, ih, iv, ih)
     scale = 64 ** -0.5  # (64*h // h) ** -0.5 with change_qkv, multihead_super.py:110
+    af = (geo.grid, geo.max_relative_position) if geo.relative_position else None
 
     blocks = []
     for i in range(config["layer_num"]):
@@ -157,7 +158,7 @@ def forward(P: Dict[str, torch.Tensor], geo: SupernetGeometry, config: dict, ima
         if geo.relative_position:
             tk = _pack_af(*_tables(P, pre, "k"))
             tv = _pack_af(*_tables(P, pre, "v"))
-        att, lse = ops.attention_fwd(qkv, B, h, N, scale, tk=tk, tv=tv, idx=idx, need_lse=save)
+        att, lse = ops.attention_fwd(qkv, B, h, N, scale, tk=tk, tv=tv, idx=idx, need_lse=save, af=af)
         wp = sh.get(P[pre + "attn.proj.weight"])
         x1 = ops.linear_fwd(att, wp, E, qd, P[pre + "attn.proj.bias"], epi=EPI_F32_RESID, resid=x,
                             row_scale=dps[0] if dps is not None else None, rows_per_scale=N)
@@ -229,6 +230,7 @@ def backward(P: Dict[str, torch.Tensor], geo: SupernetGeometry, saved: Saved, dl
         iv, ih, _, _ = ops.autoformer_index_tables(N, geo.max_relative_position, dev)
         idx = (iv, ih, iv, ih)
     scale = 64 ** -0.5
+    af = (geo.grid, geo.max_relative_position) if geo.relative_position else None
 
     for i in reversed(range(config["layer_num"])):
         pre = f"blocks.{i}."
@@ -250,7 +252,7 @@ def backward(P: Dict[str, torch.Tensor], geo: SupernetGeometry, saved: Saved, dl
         ops.linear_wgrad(dy1, s["att"], E, qd, G[pre + "attn.proj.weight"])
         datt = ops.linear_dgrad(dy1, sh.get(P[pre + "attn.proj.weight"]), E, qd)
         dqkv, dtk, dtv, _ = ops.attention_bwd(s["qkv"], s["att"], s["lse"], datt, B, h, N, scale, tk=s["tk"],
-                                              tv=s["tv"], idx=idx)
+                                              tv=s["tv"], idx=idx, af=af)
         if geo.relative_position:
             for kv, dpack in (("k", dtk), ("v", dtv)):
                 gv = G[pre + f"attn.rel_pos_embed_{kv}.embeddings_table_v"]

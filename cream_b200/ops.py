@@ -319,8 +319,10 @@ def new_pack(num_tables: int, device) -> torch.Tensor:
 # --------------------------------------------------------------------------------------------
 # attention
 # --------------------------------------------------------------------------------------------
-def _attn_desc(B, H, N, scale, qkv, tk, tv, per_head, idx, bias):
+def _attn_desc(B, H, N, scale, qkv, tk, tv, per_head, idx, bias, af=None):
     d = AttnDesc()
+    if af is not None:
+        d.af_grid, d.af_max_rel = af
     d.B, d.H, d.N, d.head_dim = B, H, N, HEAD_DIM
     d.scale = scale
     d.qkv, d.ld_qkv = _p(qkv), qkv.stride(0)
@@ -334,12 +336,12 @@ def _attn_desc(B, H, N, scale, qkv, tk, tv, per_head, idx, bias):
 
 
 def attention_fwd(qkv, B, H, N, scale, *, tk=None, tv=None, per_head=False, idx=(None, None, None, None),
-                  bias=None, need_lse=True):
+                  bias=None, need_lse=True, af=None):
     """Fused attention forward.  qkv: (B*N, 3*H*64) bf16.  Returns (out (B*N, H*64) bf16, lse)."""
     _check_2d(qkv, torch.bfloat16, "qkv", 8)
     out = empty_bf16(B * N, H * HEAD_DIM, qkv.device)
     lse = torch.empty((B, H, N), dtype=torch.float32, device=qkv.device) if need_lse else None
-    d = _attn_desc(B, H, N, scale, qkv, tk, tv, per_head, idx, bias)
+    d = _attn_desc(B, H, N, scale, qkv, tk, tv, per_head, idx, bias, af)
     d.out, d.ld_out, d.lse = _p(out), out.stride(0), _p(lse)
     if PROFILE is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -355,7 +357,7 @@ def attention_fwd(qkv, B, H, N, scale, *, tk=None, tv=None, per_head=False, idx=
 
 
 def attention_bwd(qkv, out, lse, dout, B, H, N, scale, *, tk=None, tv=None, per_head=False,
-                  idx=(None, None, None, None), bias=None):
+                  idx=(None, None, None, None), bias=None, af=None):
     """Returns (dqkv bf16, dtk_pack fp32|None, dtv_pack fp32|None, dbias fp32|None)."""
     _check_2d(dout, torch.bfloat16, "dout", 8)
     dev = qkv.device
@@ -366,7 +368,7 @@ def attention_bwd(qkv, out, lse, dout, B, H, N, scale, *, tk=None, tv=None, per_
     dbias = torch.zeros((T, NB_PACK), dtype=torch.float32, device=dev) if bias is not None else None
     nbytes = _lib.load().cream_attn_bwd_workspace_bytes(B, H, N)
     ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
-    d = _attn_desc(B, H, N, scale, qkv, tk, tv, per_head, idx, bias)
+    d = _attn_desc(B, H, N, scale, qkv, tk, tv, per_head, idx, bias, af)
     d.out, d.ld_out, d.lse = _p(out), out.stride(0), _p(lse)
     d.dout, d.ld_dout = _p(dout), dout.stride(0)
     d.dqkv, d.ld_dqkv = _p(dqkv), dqkv.stride(0)

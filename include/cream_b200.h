@@ -162,6 +162,11 @@ typedef struct cream_attn_desc {
   const uint8_t* idx_a; const uint8_t* idx_b; const uint8_t* idx_va; const uint8_t* idx_vb;
   int ld_idx;
   const float* bias_pack;
+  /* AutoFormer structure hint: the idx tables are those of a af_grid x af_grid patch grid + cls
+   * with clamp af_max_rel (cream_autoformer_rel_index_host), v ids at packed rows [0,32) and
+   * h ids at [32,64).  Lets the kernel replace the table gather by register arithmetic.
+   * 0 = no hint (generic gather through idx_*). */
+  int af_grid, af_max_rel;
   /* ---- backward only (cream_attn_bwd) ---- */
   const void* dout; int64_t ld_dout;   /* bf16 (B*N, ld_dout)                              */
   void* dqkv; int64_t ld_dqkv;         /* bf16 (B*N, ld_dqkv), same column layout as qkv    */
