@@ -1,5 +1,5 @@
 // Sliced bf16 GEMM for sm_100a: TMA -> shared memory (128B swizzle) -> tcgen05.mma
-// (accumulators in TMEM, double buffered) -> epilogue warps (tcgen05.ld) -> global.
+// (accumulators in TMEM, double buffered) -> epilogue warps (tcgen05.ld) -> TMA store.
 //
 // Replaces the cuBLAS calls behind F.linear on the sampled-subnet path
 // (AutoFormer/model/module/Linear_super.py:52-54, qkv_super.py:53-55) and their
@@ -11,9 +11,14 @@
 //   warp 0      : TMA producer (one lane)
 //   warp 1      : tcgen05.mma issuer (one lane)
 //   warp 2      : TMEM allocator
-//   warps 4..11 : epilogue (two warps per TMEM lane quarter, alternating column chunks)
-#include "common.cuh"
-#include "ptx.cuh"
+//   warps 4..11 : epilogue.  The accumulator tile is drained in 128-byte-wide column blocks
+//                 (64 bf16 / 32 fp32 columns): TMEM -> registers -> epilogue math -> 128B-swizzled
+//                 shared staging tile -> ONE TMA store (or TMA reduce-add for the split-K weight
+//                 gradient) per block, double buffered.  Residual / GELU pre-activation operands of
+//                 the epilogue are TMA-prefetched into the same staging tile one block ahead, so the
+//                 epilogue issues no strided global accesses and needs no bounds predicates (the
+//                 tensor maps clip ragged M / N tails).
+#include "attention_common.cuh"  // explicit shared-memory accessors
 
 namespace cb {
 
@@ -25,7 +30,9 @@ constexpr int kMaxStages = 8;
 constexpr int kNumThreads = 384;  // 12 warps
 constexpr int kEpiWarp0 = 4;
 constexpr int kNumEpiWarps = 8;
+constexpr int kEpiThreads = kNumEpiWarps * 32;
 constexpr uint32_t kTmemCols = 512;  // 2 accumulator stages x 256 columns
+constexpr int kEpiSlotBytes = kBM * 128;  // one 128 rows x 128 B staging tile
 
 struct GemmKernelParams {
   int M, N, K, groups, BN;
@@ -35,15 +42,8 @@ struct GemmKernelParams {
   int num_stages;
   uint32_t stage_bytes, a_bytes, tx_bytes;
   int nb64;
-  int epi;
-  void* out;
-  int64_t ldo;
-  int out_row_mul, out_g_row, out_g_col;
-  void* aux;
-  int64_t ldaux;
+  int out_g_col;
   const float* bias;
-  const float* resid;
-  int64_t ldr;
   const float* row_scale;
   int rows_per_scale;
   float alpha;
@@ -68,134 +68,62 @@ __device__ __forceinline__ WorkItem decode_work(const GemmKernelParams& p, int w
   return it;
 }
 
-template <int EPI>
-__device__ __forceinline__ void epilogue_chunk(const GemmKernelParams& p, const uint32_t (&raw)[32],
-                                               int row, int g, int col0, int ncols) {
-  // row: global output row (already < M); col0: first column of this chunk within the
-  // group; ncols: number of valid columns (1..32).
-  const int64_t orow = static_cast<int64_t>(row) * p.out_row_mul + static_cast<int64_t>(g) * p.out_g_row;
-  const int ocol = col0 + g * p.out_g_col;
-  float v[32];
-#pragma unroll
-  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(raw[i]);
-
-  if constexpr (EPI != CREAM_EPI_F32_ATOMIC && EPI != CREAM_EPI_BF16_DGELU) {
-    if (p.bias != nullptr) {
-#pragma unroll
-      for (int i = 0; i < 32; ++i)
-        if (i < ncols) v[i] += __ldg(p.bias + ocol + i);
-    }
-  }
-
-  if constexpr (EPI == CREAM_EPI_BF16 || EPI == CREAM_EPI_BF16_GELU || EPI == CREAM_EPI_BF16_DGELU) {
-    __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(p.out) + orow * p.ldo + ocol;
-    if constexpr (EPI == CREAM_EPI_BF16_GELU) {
-      __nv_bfloat16* aux = reinterpret_cast<__nv_bfloat16*>(p.aux) + orow * p.ldaux + ocol;
-      if (ncols == 32) {
-        uint4* a4 = reinterpret_cast<uint4*>(aux);
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          uint4 u;
-          u.x = pack_bf16x2(v[8 * q + 0], v[8 * q + 1]);
-          u.y = pack_bf16x2(v[8 * q + 2], v[8 * q + 3]);
-          u.z = pack_bf16x2(v[8 * q + 4], v[8 * q + 5]);
-          u.w = pack_bf16x2(v[8 * q + 6], v[8 * q + 7]);
-          a4[q] = u;
-        }
-      } else {
-        for (int i = 0; i < ncols; ++i) aux[i] = __float2bfloat16_rn(v[i]);
-      }
-      // GELU acts on the bf16-rounded pre-activation (what backward will see).
-#pragma unroll
-      for (int i = 0; i < 32; ++i) v[i] = gelu_f(__bfloat162float(__float2bfloat16_rn(v[i])));
-    }
-    if constexpr (EPI == CREAM_EPI_BF16_DGELU) {
-      const __nv_bfloat16* aux =
-          reinterpret_cast<const __nv_bfloat16*>(p.aux) + orow * p.ldaux + ocol;
-      if (ncols == 32) {
-        const uint4* a4 = reinterpret_cast<const uint4*>(aux);
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const uint4 u = __ldg(a4 + q);
-          const float2 f0 = unpack_bf16x2(u.x), f1 = unpack_bf16x2(u.y);
-          const float2 f2 = unpack_bf16x2(u.z), f3 = unpack_bf16x2(u.w);
-          v[8 * q + 0] *= dgelu_f(f0.x);
-          v[8 * q + 1] *= dgelu_f(f0.y);
-          v[8 * q + 2] *= dgelu_f(f1.x);
-          v[8 * q + 3] *= dgelu_f(f1.y);
-          v[8 * q + 4] *= dgelu_f(f2.x);
-          v[8 * q + 5] *= dgelu_f(f2.y);
-          v[8 * q + 6] *= dgelu_f(f3.x);
-          v[8 * q + 7] *= dgelu_f(f3.y);
-        }
-      } else {
-        for (int i = 0; i < ncols; ++i) v[i] *= dgelu_f(__bfloat162float(aux[i]));
-      }
-    }
-    if (ncols == 32) {
-      uint4* o4 = reinterpret_cast<uint4*>(out);
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        uint4 u;
-        u.x = pack_bf16x2(v[8 * q + 0], v[8 * q + 1]);
-        u.y = pack_bf16x2(v[8 * q + 2], v[8 * q + 3]);
-        u.z = pack_bf16x2(v[8 * q + 4], v[8 * q + 5]);
-        u.w = pack_bf16x2(v[8 * q + 6], v[8 * q + 7]);
-        o4[q] = u;
-      }
-    } else {
-      for (int i = 0; i < ncols; ++i) out[i] = __float2bfloat16_rn(v[i]);
-    }
-  } else if constexpr (EPI == CREAM_EPI_F32_RESID) {
-    float* out = reinterpret_cast<float*>(p.out) + orow * p.ldo + ocol;
-    const float* res = p.resid + orow * p.ldr + ocol;
-    const float s = (p.row_scale != nullptr) ? __ldg(p.row_scale + row / p.rows_per_scale) : 1.0f;
-    if (ncols == 32) {
-      const float4* r4 = reinterpret_cast<const float4*>(res);
-      float4* o4 = reinterpret_cast<float4*>(out);
-#pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        const float4 r = __ldg(r4 + q);
-        float4 o;
-        o.x = fmaf(s, v[4 * q + 0], r.x);
-        o.y = fmaf(s, v[4 * q + 1], r.y);
-        o.z = fmaf(s, v[4 * q + 2], r.z);
-        o.w = fmaf(s, v[4 * q + 3], r.w);
-        o4[q] = o;
-      }
-    } else {
-      for (int i = 0; i < ncols; ++i) out[i] = fmaf(s, v[i], res[i]);
-    }
-  } else if constexpr (EPI == CREAM_EPI_F32) {
-    float* out = reinterpret_cast<float*>(p.out) + orow * p.ldo + ocol;
-    if (ncols == 32) {
-      float4* o4 = reinterpret_cast<float4*>(out);
-#pragma unroll
-      for (int q = 0; q < 8; ++q)
-        o4[q] = make_float4(v[4 * q + 0], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-    } else {
-      for (int i = 0; i < ncols; ++i) out[i] = v[i];
-    }
-  } else {  // CREAM_EPI_F32_ATOMIC
-    float* out = reinterpret_cast<float*>(p.out) + orow * p.ldo + ocol;
-#pragma unroll
-    for (int i = 0; i < 32; ++i)
-      if (i < ncols) atomicAdd(out + i, p.alpha * v[i]);
-  }
+// ---- TMA store / reduce (bulk async-group completion) ---------------------------------------
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, const void* smem, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(m)),
+               "r"(smem_u32(smem)), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
 }
+__device__ __forceinline__ void tma_reduce_add_3d(const CUtensorMap* m, const void* smem, int c0, int c1, int c2) {
+  asm volatile("cp.reduce.async.bulk.tensor.3d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(m)),
+               "r"(smem_u32(smem)), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void epi_barrier() {
+  asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
+}
+
+template <int EPI> struct EpiTraits {
+  static constexpr bool kOutBf16 = EPI == CREAM_EPI_BF16 || EPI == CREAM_EPI_BF16_GELU || EPI == CREAM_EPI_BF16_DGELU;
+  static constexpr int kCB = kOutBf16 ? 64 : 32;       // columns per 128-byte store block
+  static constexpr int kPerThread = kCB / 2;           // columns per thread (two warps per lane quarter)
+  static constexpr bool kLoads = EPI == CREAM_EPI_F32_RESID || EPI == CREAM_EPI_BF16_DGELU;
+  static constexpr bool kBias = EPI != CREAM_EPI_F32_ATOMIC && EPI != CREAM_EPI_BF16_DGELU;
+};
+
+__device__ __forceinline__ uint4 lds_u32x4(uint32_t a) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ void sts_u32x4(uint32_t a, uint4 v) {
+  asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ float bf16_round(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
 
 template <int EPI>
 __global__ void __launch_bounds__(kNumThreads, 1)
-gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a,
-                 const __grid_constant__ CUtensorMap tmap_b, const GemmKernelParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>(
-      (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + p.num_stages * p.stage_bytes);
+gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                 const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_aux,
+                 const GemmKernelParams p) {
+  using T = EpiTraits<EPI>;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  require_smem_alignment(smem);
+  uint8_t* epi_slots = smem + p.num_stages * p.stage_bytes;             // 2 x 16 KB, 1024-aligned
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(epi_slots + 2 * kEpiSlotBytes);
   uint64_t* empty_bar = full_bar + kMaxStages;
   uint64_t* tmem_full = empty_bar + kMaxStages;
   uint64_t* tmem_empty = tmem_full + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  uint64_t* ld_bar = tmem_empty + 2;                                    // [2] epilogue operand prefetch
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ld_bar + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -203,6 +131,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a,
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmap_a);
     prefetch_tmap(&tmap_b);
+    prefetch_tmap(&tmap_out);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < p.num_stages; ++s) {
@@ -212,6 +141,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a,
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tmem_full[a], 1);
       mbar_init(&tmem_empty[a], kNumEpiWarps);
+      mbar_init(&ld_bar[a], 1);
     }
     fence_mbar_init();
   }
@@ -286,35 +216,173 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a,
     }
   } else if (warp >= kEpiWarp0) {
     // ===================== epilogue =====================
-    const int ew = warp - kEpiWarp0;       // 0..7
-    const int quarter = warp & 3;          // TMEM lane quarter this warp may access
-    const int half = ew >> 2;              // which alternating column chunks
+    const int quarter = warp & 3;                    // TMEM lane quarter this warp may access
+    const int half = (warp - kEpiWarp0) >> 2;        // which half of the block's columns
+    const int r_local = quarter * 32 + lane;         // row within the tile
+    const bool issuer = threadIdx.x == kEpiWarp0 * 32;
+    const uint32_t slot0 = smem_u32(epi_slots);
+    // this thread's four 16-byte chunks in a staging tile: chunk u of row r sits at (u ^ (r & 7))
+    uint32_t chunk_off[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) chunk_off[q] = r_local * 128 + (((half * 4 + q) ^ (r_local & 7)) << 4);
+
     int acc = 0;
     uint32_t acc_phase = 0;
+    int slot = 0;                       // staging tile used by the next store job
+    uint32_t ld_phase[2] = {0, 0};
+
+    // operand prefetch (RESID / DGELU): block stream = (work item, column block) pairs
+    auto issue_load = [&](int w, int cb, int s) {
+      const WorkItem it = decode_work(p, w);
+      mbar_arrive_expect_tx(&ld_bar[s], kEpiSlotBytes);
+      tma_load_3d(epi_slots + s * kEpiSlotBytes, &tmap_aux, &ld_bar[s], it.nt * p.BN + cb * T::kCB, it.mt * kBM, it.g);
+    };
+    if (T::kLoads && issuer && static_cast<int>(blockIdx.x) < p.total_work) issue_load(blockIdx.x, 0, 0);
+
     for (int w = blockIdx.x; w < p.total_work; w += gridDim.x) {
       const WorkItem it = decode_work(p, w);
       const int m0 = it.mt * kBM, n0 = it.nt * p.BN;
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
-      const int row = m0 + quarter * 32 + lane;
+      const int row = m0 + r_local;
       const int tile_cols = min(p.BN, p.N - n0);
-      const int nchunks = (tile_cols + 31) >> 5;
-      for (int c = half; c < nchunks; c += 2) {
-        uint32_t raw[32];
-        const uint32_t taddr = tmem_base + acc * 256 + c * 32 + (static_cast<uint32_t>(quarter * 32) << 16);
-        tmem_ld32(taddr, raw);
-        tmem_ld_wait();
-        if (row < p.M) {
-          const int ncols = min(32, tile_cols - c * 32);
-          epilogue_chunk<EPI>(p, raw, row, it.g, n0 + c * 32, ncols);
+      const int nblocks = (tile_cols + T::kCB - 1) / T::kCB;
+      float rscale = 1.0f;
+      if constexpr (EPI == CREAM_EPI_F32_RESID) {
+        if (p.row_scale != nullptr && row < p.M) rscale = __ldg(p.row_scale + row / p.rows_per_scale);
+      }
+      for (int cb = 0; cb < nblocks; ++cb) {
+        const int col0 = n0 + cb * T::kCB + half * T::kPerThread;     // first column of this thread
+        const int ocol = col0 + it.g * p.out_g_col;
+        // ---- accumulator -> registers ----
+        float v[T::kPerThread];
+        {
+          const uint32_t taddr = tmem_base + acc * 256 + cb * T::kCB + half * T::kPerThread +
+                                 (static_cast<uint32_t>(quarter * 32) << 16);
+          if constexpr (T::kPerThread == 32) {
+            uint32_t raw[32];
+            tmem_ld32(taddr, raw);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(raw[i]);
+          } else {
+            uint32_t raw[16];
+            tmem_ld16(taddr, raw);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(raw[i]);
+          }
+        }
+        if constexpr (T::kBias) {
+          if (p.bias != nullptr) {
+            if (col0 + T::kPerThread <= p.N) {
+              const float4* b4 = reinterpret_cast<const float4*>(p.bias + ocol);
+#pragma unroll
+              for (int q = 0; q < T::kPerThread / 4; ++q) {
+                const float4 bb = __ldg(b4 + q);
+                v[4 * q + 0] += bb.x; v[4 * q + 1] += bb.y; v[4 * q + 2] += bb.z; v[4 * q + 3] += bb.w;
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < T::kPerThread; ++i)
+                if (col0 + i < p.N) v[i] += __ldg(p.bias + ocol + i);
+            }
+          }
+        }
+
+        // ---- acquire the staging tile ----
+        if constexpr (T::kLoads) {
+          if (issuer) {
+            bulk_wait_read<0>();                         // the other tile's store has drained
+            int nw = w, ncb = cb + 1;
+            if (ncb >= nblocks) { nw = w + gridDim.x; ncb = 0; }
+            if (nw < p.total_work) issue_load(nw, ncb, slot ^ 1);
+          }
+          mbar_wait(&ld_bar[slot], ld_phase[slot]);
+          ld_phase[slot] ^= 1;
+        } else {
+          if (issuer) bulk_wait_read<1>();               // at most the other tile still in flight
+          epi_barrier();
+        }
+        const uint32_t sbase = slot0 + slot * kEpiSlotBytes;
+
+        // ---- epilogue math + write to the staging tile ----
+        if constexpr (EPI == CREAM_EPI_F32_RESID) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float4 r = lds_f32x4(sbase + chunk_off[q]);
+            sts_f32x4(sbase + chunk_off[q], make_float4(fmaf(rscale, v[4 * q + 0], r.x), fmaf(rscale, v[4 * q + 1], r.y),
+                                                        fmaf(rscale, v[4 * q + 2], r.z), fmaf(rscale, v[4 * q + 3], r.w)));
+          }
+        } else if constexpr (EPI == CREAM_EPI_F32 || EPI == CREAM_EPI_F32_ATOMIC) {
+          const float a = (EPI == CREAM_EPI_F32_ATOMIC) ? p.alpha : 1.0f;
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            sts_f32x4(sbase + chunk_off[q], make_float4(a * v[4 * q + 0], a * v[4 * q + 1], a * v[4 * q + 2], a * v[4 * q + 3]));
+        } else {
+          if constexpr (EPI == CREAM_EPI_BF16_DGELU) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const uint4 u = lds_u32x4(sbase + chunk_off[q]);
+              const float2 f0 = unpack_bf16x2(u.x), f1 = unpack_bf16x2(u.y), f2 = unpack_bf16x2(u.z), f3 = unpack_bf16x2(u.w);
+              v[8 * q + 0] *= dgelu_f(f0.x); v[8 * q + 1] *= dgelu_f(f0.y);
+              v[8 * q + 2] *= dgelu_f(f1.x); v[8 * q + 3] *= dgelu_f(f1.y);
+              v[8 * q + 4] *= dgelu_f(f2.x); v[8 * q + 5] *= dgelu_f(f2.y);
+              v[8 * q + 6] *= dgelu_f(f3.x); v[8 * q + 7] *= dgelu_f(f3.y);
+            }
+          }
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            uint4 u;
+            u.x = pack_bf16x2(v[8 * q + 0], v[8 * q + 1]);
+            u.y = pack_bf16x2(v[8 * q + 2], v[8 * q + 3]);
+            u.z = pack_bf16x2(v[8 * q + 4], v[8 * q + 5]);
+            u.w = pack_bf16x2(v[8 * q + 6], v[8 * q + 7]);
+            sts_u32x4(sbase + chunk_off[q], u);
+          }
+        }
+        fence_proxy_async_smem();
+        epi_barrier();
+        if (issuer) {
+          const int c0 = n0 + cb * T::kCB;
+          if constexpr (EPI == CREAM_EPI_F32_ATOMIC) tma_reduce_add_3d(&tmap_out, epi_slots + slot * kEpiSlotBytes, c0, m0, it.g);
+          else if constexpr (EPI == CREAM_EPI_BF16_GELU) tma_store_3d(&tmap_aux, epi_slots + slot * kEpiSlotBytes, c0, m0, it.g);
+          else tma_store_3d(&tmap_out, epi_slots + slot * kEpiSlotBytes, c0, m0, it.g);
+          bulk_commit();
+        }
+        slot ^= 1;
+
+        if constexpr (EPI == CREAM_EPI_BF16_GELU) {
+          // second store job of the block: GELU of the bf16-rounded pre-activation (what backward sees)
+          if (issuer) bulk_wait_read<1>();
+          epi_barrier();
+          const uint32_t sb2 = slot0 + slot * kEpiSlotBytes;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            uint4 u;
+            u.x = pack_bf16x2(gelu_f(bf16_round(v[8 * q + 0])), gelu_f(bf16_round(v[8 * q + 1])));
+            u.y = pack_bf16x2(gelu_f(bf16_round(v[8 * q + 2])), gelu_f(bf16_round(v[8 * q + 3])));
+            u.z = pack_bf16x2(gelu_f(bf16_round(v[8 * q + 4])), gelu_f(bf16_round(v[8 * q + 5])));
+            u.w = pack_bf16x2(gelu_f(bf16_round(v[8 * q + 6])), gelu_f(bf16_round(v[8 * q + 7])));
+            sts_u32x4(sb2 + chunk_off[q], u);
+          }
+          fence_proxy_async_smem();
+          epi_barrier();
+          if (issuer) {
+            tma_store_3d(&tmap_out, epi_slots + slot * kEpiSlotBytes, n0 + cb * T::kCB, m0, it.g);
+            bulk_commit();
+          }
+          slot ^= 1;
         }
       }
+      // all TMEM reads of this accumulator are done
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[acc]);
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
+    if (issuer) bulk_wait_all();
   }
 
   tc_fence_before();
@@ -326,15 +394,15 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a,
 }
 
 template <int EPI>
-int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmKernelParams& p,
-                size_t smem_bytes, int grid, cudaStream_t stream) {
+int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const CUtensorMap& tx,
+                const GemmKernelParams& p, size_t smem_bytes, int grid, cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
     CB_CUDA_OK(cudaFuncSetAttribute(gemm_bf16_kernel<EPI>,
                                     cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
-  gemm_bf16_kernel<EPI><<<grid, kNumThreads, smem_bytes, stream>>>(ta, tb, p);
+  gemm_bf16_kernel<EPI><<<grid, kNumThreads, smem_bytes, stream>>>(ta, tb, to, tx, p);
   return check_last("gemm_bf16_kernel launch");
 }
 
@@ -349,8 +417,8 @@ extern "C" int cream_gemm_bf16(const cream_gemm_desc* d, void* stream_) {
   CB_REQUIRE(d->M > 0 && d->N > 0 && d->K > 0 && d->groups >= 1, "empty GEMM");
   CB_REQUIRE(d->a != nullptr && d->b != nullptr && d->out != nullptr, "null operand");
   CB_REQUIRE(d->lda % 8 == 0 && d->ldb % 8 == 0, "bf16 leading dims must be multiples of 8");
-  CB_REQUIRE((reinterpret_cast<uintptr_t>(d->a) & 15) == 0 &&
-                 (reinterpret_cast<uintptr_t>(d->b) & 15) == 0,
+  CB_REQUIRE((reinterpret_cast<uintptr_t>(d->a) & 15) == 0 && (reinterpret_cast<uintptr_t>(d->b) & 15) == 0 &&
+                 (reinterpret_cast<uintptr_t>(d->out) & 15) == 0,
              "operands must be 16-byte aligned");
   CB_REQUIRE(d->epi >= 0 && d->epi <= CREAM_EPI_F32, "bad epilogue");
   const bool out_bf16 = d->epi == CREAM_EPI_BF16 || d->epi == CREAM_EPI_BF16_GELU ||
@@ -361,8 +429,10 @@ extern "C" int cream_gemm_bf16(const cream_gemm_desc* d, void* stream_) {
     CB_REQUIRE(d->ldo % 4 == 0 && (d->out_g_col % 4) == 0, "fp32 out pitch/offset % 4");
   }
   if (d->epi == CREAM_EPI_BF16_GELU || d->epi == CREAM_EPI_BF16_DGELU)
-    CB_REQUIRE(d->aux != nullptr && d->ldaux % 8 == 0, "aux required");
-  if (d->epi == CREAM_EPI_F32_RESID) CB_REQUIRE(d->resid != nullptr && d->ldr % 4 == 0, "resid");
+    CB_REQUIRE(d->aux != nullptr && d->ldaux % 8 == 0 && (reinterpret_cast<uintptr_t>(d->aux) & 15) == 0, "aux required");
+  if (d->epi == CREAM_EPI_F32_RESID)
+    CB_REQUIRE(d->resid != nullptr && d->ldr % 4 == 0 && (reinterpret_cast<uintptr_t>(d->resid) & 15) == 0, "resid");
+  if (d->bias) CB_REQUIRE((reinterpret_cast<uintptr_t>(d->bias) & 15) == 0, "bias must be 16-byte aligned");
 
   GemmKernelParams p{};
   p.M = d->M; p.N = d->N; p.K = d->K; p.groups = d->groups;
@@ -397,15 +467,12 @@ extern "C" int cream_gemm_bf16(const cream_gemm_desc* d, void* stream_) {
   p.stage_bytes = p.a_bytes + p.nb64 * 8192;
   p.tx_bytes = p.a_bytes + (p.b_mn ? p.nb64 * 8192 : p.BN * kBK * 2);
   const size_t tail_bytes = 1024;  // barriers + tmem slot
-  p.num_stages = std::min<int>(kMaxStages, (227 * 1024 - 1024 - tail_bytes) / p.stage_bytes);
+  const size_t epi_bytes = 2 * kEpiSlotBytes;
+  p.num_stages = std::min<int>(kMaxStages, (227 * 1024 - epi_bytes - tail_bytes) / p.stage_bytes);
   CB_REQUIRE(p.num_stages >= 2, "not enough shared memory for 2 stages");
-  const size_t smem_bytes = 1024 + static_cast<size_t>(p.num_stages) * p.stage_bytes + tail_bytes;
-  p.epi = d->epi;
-  p.out = d->out; p.ldo = d->ldo;
-  p.out_row_mul = d->out_row_mul > 0 ? d->out_row_mul : 1;
-  p.out_g_row = d->out_g_row; p.out_g_col = d->out_g_col;
-  p.aux = d->aux; p.ldaux = d->ldaux;
-  p.bias = d->bias; p.resid = d->resid; p.ldr = d->ldr;
+  const size_t smem_bytes = static_cast<size_t>(p.num_stages) * p.stage_bytes + epi_bytes + tail_bytes;
+  p.out_g_col = d->out_g_col;
+  p.bias = d->bias;
   p.row_scale = d->row_scale; p.rows_per_scale = d->rows_per_scale > 0 ? d->rows_per_scale : 1;
   p.alpha = d->alpha == 0.0f ? 1.0f : d->alpha;
 
@@ -444,15 +511,31 @@ extern "C" int cream_gemm_bf16(const cream_gemm_desc* d, void* stream_) {
     tb = get_tensor_map(d->b, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, dims, strides, box,
                         CU_TENSOR_MAP_SWIZZLE_128B);
   }
-  if (ta == nullptr || tb == nullptr) return CREAM_ERR_CUDA;
+  // output (and epilogue operand) maps: element (n, m, g) at base + (m*row_mul + g*g_row)*ld + n + g*g_col
+  const int row_mul = d->out_row_mul > 0 ? d->out_row_mul : 1;
+  auto out_like_map = [&](const void* base, int64_t ld, bool bf16) -> const CUtensorMap* {
+    const uint64_t row_stride = static_cast<uint64_t>(row_mul) * ld;
+    uint64_t g_stride = static_cast<uint64_t>(d->out_g_row) * ld + d->out_g_col;
+    if (p.groups == 1 || g_stride == 0) g_stride = row_stride;
+    const uint64_t dims[3] = {static_cast<uint64_t>(d->N), static_cast<uint64_t>(d->M), static_cast<uint64_t>(p.groups)};
+    const uint64_t strides[3] = {1, row_stride, g_stride};
+    const uint32_t box[3] = {static_cast<uint32_t>(bf16 ? 64 : 32), kBM, 1};
+    return get_tensor_map(base, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, dims,
+                          strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
+  };
+  const CUtensorMap* to = out_like_map(d->out, d->ldo, out_bf16);
+  const CUtensorMap* tx = to;
+  if (d->epi == CREAM_EPI_BF16_GELU || d->epi == CREAM_EPI_BF16_DGELU) tx = out_like_map(d->aux, d->ldaux, true);
+  if (d->epi == CREAM_EPI_F32_RESID) tx = out_like_map(d->resid, d->ldr, false);
+  if (ta == nullptr || tb == nullptr || to == nullptr || tx == nullptr) return CREAM_ERR_CUDA;
 
   const int grid = std::min(p.total_work, kNumSMs);
   switch (d->epi) {
-    case CREAM_EPI_BF16: return launch_gemm<CREAM_EPI_BF16>(*ta, *tb, p, smem_bytes, grid, stream);
-    case CREAM_EPI_BF16_GELU: return launch_gemm<CREAM_EPI_BF16_GELU>(*ta, *tb, p, smem_bytes, grid, stream);
-    case CREAM_EPI_F32_RESID: return launch_gemm<CREAM_EPI_F32_RESID>(*ta, *tb, p, smem_bytes, grid, stream);
-    case CREAM_EPI_BF16_DGELU: return launch_gemm<CREAM_EPI_BF16_DGELU>(*ta, *tb, p, smem_bytes, grid, stream);
-    case CREAM_EPI_F32_ATOMIC: return launch_gemm<CREAM_EPI_F32_ATOMIC>(*ta, *tb, p, smem_bytes, grid, stream);
-    default: return launch_gemm<CREAM_EPI_F32>(*ta, *tb, p, smem_bytes, grid, stream);
+    case CREAM_EPI_BF16: return launch_gemm<CREAM_EPI_BF16>(*ta, *tb, *to, *tx, p, smem_bytes, grid, stream);
+    case CREAM_EPI_BF16_GELU: return launch_gemm<CREAM_EPI_BF16_GELU>(*ta, *tb, *to, *tx, p, smem_bytes, grid, stream);
+    case CREAM_EPI_F32_RESID: return launch_gemm<CREAM_EPI_F32_RESID>(*ta, *tb, *to, *tx, p, smem_bytes, grid, stream);
+    case CREAM_EPI_BF16_DGELU: return launch_gemm<CREAM_EPI_BF16_DGELU>(*ta, *tb, *to, *tx, p, smem_bytes, grid, stream);
+    case CREAM_EPI_F32_ATOMIC: return launch_gemm<CREAM_EPI_F32_ATOMIC>(*ta, *tb, *to, *tx, p, smem_bytes, grid, stream);
+    default: return launch_gemm<CREAM_EPI_F32>(*ta, *tb, *to, *tx, p, smem_bytes, grid, stream);
   }
 }
