@@ -112,84 +112,106 @@ pool_bwd_kernel(const __nv_bfloat16* __restrict__ dp, int64_t lddp, float* __res
 }
 
 // out_bf16[r,c] = bf16(scale[r / rows_per] * in[r,c]); optional fused bias gradient
-// dbias[c] += sum_r out[r,c] (per-thread partials over a column strip -> global atomics).
-__global__ void __launch_bounds__(128)
+// dbias[c] += sum_r out[r,c].  Block = 32 column threads (x4 columns) x 8 row lanes; the row lanes
+// are reduced through shared memory so that only gridDim.y atomics hit each dbias address.
+__global__ void __launch_bounds__(256)
 cast_scale_kernel(const float* __restrict__ in, int64_t ldi, __nv_bfloat16* __restrict__ out, int64_t ldo,
                   const float* __restrict__ scale, int rows_per, float* __restrict__ dbias, int64_t rows,
                   int cols) {
-  // blockDim.x covers a strip of columns (x4); rows strided by gridDim.y, 4 rows in flight
-  const int c = (blockIdx.x * blockDim.x + threadIdx.x) << 2;
-  if (c >= cols) return;
+  __shared__ float red[8][32][4];
+  const int c = (blockIdx.x * 32 + threadIdx.x) << 2;
+  const bool live = c < cols;
   float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-  const int64_t stride = gridDim.y;
-  for (int64_t r0 = blockIdx.y; r0 < rows; r0 += 4 * stride) {
-    float4 v[4];
-    float s[4];
+  const int64_t stride = static_cast<int64_t>(gridDim.y) * 8;
+  if (live) {
+    for (int64_t r0 = static_cast<int64_t>(blockIdx.y) * 8 + threadIdx.y; r0 < rows; r0 += 2 * stride) {
+      float4 v[2];
+      float s[2];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int64_t r = r0 + u * stride;
-      if (r < rows) {
-        v[u] = __ldg(reinterpret_cast<const float4*>(in + r * ldi + c));
-        s[u] = scale ? __ldg(scale + r / rows_per) : 1.0f;
+      for (int u = 0; u < 2; ++u) {
+        const int64_t r = r0 + u * stride;
+        if (r < rows) {
+          v[u] = __ldg(reinterpret_cast<const float4*>(in + r * ldi + c));
+          s[u] = scale ? __ldg(scale + r / rows_per) : 1.0f;
+        }
       }
-    }
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int64_t r = r0 + u * stride;
-      if (r < rows) {
-        const __nv_bfloat162 lo = __floats2bfloat162_rn(s[u] * v[u].x, s[u] * v[u].y);
-        const __nv_bfloat162 hi = __floats2bfloat162_rn(s[u] * v[u].z, s[u] * v[u].w);
-        uint2 o;
-        o.x = *reinterpret_cast<const uint32_t*>(&lo);
-        o.y = *reinterpret_cast<const uint32_t*>(&hi);
-        *reinterpret_cast<uint2*>(out + r * ldo + c) = o;
-        a0 += __bfloat162float(lo.x); a1 += __bfloat162float(lo.y);
-        a2 += __bfloat162float(hi.x); a3 += __bfloat162float(hi.y);
-      }
-    }
-  }
-  if (dbias) {
-    atomicAdd(dbias + c, a0);
-    if (c + 1 < cols) atomicAdd(dbias + c + 1, a1);
-    if (c + 2 < cols) atomicAdd(dbias + c + 2, a2);
-    if (c + 3 < cols) atomicAdd(dbias + c + 3, a3);
-  }
-}
-
-// dbias[c] += sum_r dy[r,c]  (bf16 input, 8 columns per thread, 4 rows in flight)
-__global__ void __launch_bounds__(128)
-colsum_kernel(const __nv_bfloat16* __restrict__ dy, int64_t ld, float* __restrict__ dbias, int64_t rows,
-              int cols) {
-  const int c = (blockIdx.x * blockDim.x + threadIdx.x) << 3;
-  if (c >= cols) return;
-  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-  const int64_t stride = gridDim.y;
-  const bool vec = (c + 8 <= cols) && ((ld & 7) == 0);
-  for (int64_t r0 = blockIdx.y; r0 < rows; r0 += 4 * stride) {
-    uint4 v[4];
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int64_t r = r0 + u * stride;
-      v[u] = make_uint4(0, 0, 0, 0);
-      if (r < rows) {
-        if (vec) v[u] = __ldg(reinterpret_cast<const uint4*>(dy + r * ld + c));
-        else {
-          __nv_bfloat16 tmp[8];
-          for (int k = 0; k < 8; ++k) tmp[k] = (c + k < cols) ? dy[r * ld + c + k] : __float2bfloat16_rn(0.f);
-          v[u] = *reinterpret_cast<uint4*>(tmp);
+      for (int u = 0; u < 2; ++u) {
+        const int64_t r = r0 + u * stride;
+        if (r < rows) {
+          const __nv_bfloat162 lo = __floats2bfloat162_rn(s[u] * v[u].x, s[u] * v[u].y);
+          const __nv_bfloat162 hi = __floats2bfloat162_rn(s[u] * v[u].z, s[u] * v[u].w);
+          uint2 o;
+          o.x = *reinterpret_cast<const uint32_t*>(&lo);
+          o.y = *reinterpret_cast<const uint32_t*>(&hi);
+          *reinterpret_cast<uint2*>(out + r * ldo + c) = o;
+          a0 += __bfloat162float(lo.x); a1 += __bfloat162float(lo.y);
+          a2 += __bfloat162float(hi.x); a3 += __bfloat162float(hi.y);
         }
       }
     }
+  }
+  if (dbias == nullptr) return;
+  red[threadIdx.y][threadIdx.x][0] = a0; red[threadIdx.y][threadIdx.x][1] = a1;
+  red[threadIdx.y][threadIdx.x][2] = a2; red[threadIdx.y][threadIdx.x][3] = a3;
+  __syncthreads();
+  if (threadIdx.y == 0 && live) {
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const float2 f0 = unpack_bf16x2(v[u].x), f1 = unpack_bf16x2(v[u].y), f2 = unpack_bf16x2(v[u].z), f3 = unpack_bf16x2(v[u].w);
-      acc[0] += f0.x; acc[1] += f0.y; acc[2] += f1.x; acc[3] += f1.y;
-      acc[4] += f2.x; acc[5] += f2.y; acc[6] += f3.x; acc[7] += f3.y;
+    for (int k = 0; k < 4; ++k) {
+      float t = 0.f;
+#pragma unroll
+      for (int y = 0; y < 8; ++y) t += red[y][threadIdx.x][k];
+      if (c + k < cols) atomicAdd(dbias + c + k, t);
+    }
+  }
+}
+
+// dbias[c] += sum_r dy[r,c]  (bf16 input).  Block = 32 column threads (x8 columns) x 8 row lanes.
+__global__ void __launch_bounds__(256)
+colsum_kernel(const __nv_bfloat16* __restrict__ dy, int64_t ld, float* __restrict__ dbias, int64_t rows,
+              int cols) {
+  __shared__ float red[8][32][8];
+  const int c = (blockIdx.x * 32 + threadIdx.x) << 3;
+  const bool live = c < cols;
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  const int64_t stride = static_cast<int64_t>(gridDim.y) * 8;
+  const bool vec = (c + 8 <= cols) && ((ld & 7) == 0);
+  if (live) {
+    for (int64_t r0 = static_cast<int64_t>(blockIdx.y) * 8 + threadIdx.y; r0 < rows; r0 += 2 * stride) {
+      uint4 v[2];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int64_t r = r0 + u * stride;
+        v[u] = make_uint4(0, 0, 0, 0);
+        if (r < rows) {
+          if (vec) v[u] = __ldg(reinterpret_cast<const uint4*>(dy + r * ld + c));
+          else {
+            __nv_bfloat16 tmp[8];
+            for (int k = 0; k < 8; ++k) tmp[k] = (c + k < cols) ? dy[r * ld + c + k] : __float2bfloat16_rn(0.f);
+            v[u] = *reinterpret_cast<uint4*>(tmp);
+          }
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const float2 f0 = unpack_bf16x2(v[u].x), f1 = unpack_bf16x2(v[u].y), f2 = unpack_bf16x2(v[u].z), f3 = unpack_bf16x2(v[u].w);
+        acc[0] += f0.x; acc[1] += f0.y; acc[2] += f1.x; acc[3] += f1.y;
+        acc[4] += f2.x; acc[5] += f2.y; acc[6] += f3.x; acc[7] += f3.y;
+      }
     }
   }
 #pragma unroll
-  for (int k = 0; k < 8; ++k)
-    if (c + k < cols) atomicAdd(dbias + c + k, acc[k]);
+  for (int k = 0; k < 8; ++k) red[threadIdx.y][threadIdx.x][k] = acc[k];
+  __syncthreads();
+  if (threadIdx.y == 0 && live) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      float t = 0.f;
+#pragma unroll
+      for (int y = 0; y < 8; ++y) t += red[y][threadIdx.x][k];
+      if (c + k < cols) atomicAdd(dbias + c + k, t);
+    }
+  }
 }
 
 struct PackSrc {
@@ -291,7 +313,7 @@ extern "C" int cream_cast_scale(const float* in, int64_t ldi, void* out_bf16, in
   if (rows == 0 || cols == 0) return CREAM_OK;
   CB_REQUIRE(in && out_bf16, "null pointer");
   CB_REQUIRE(ldi % 4 == 0 && ldo % 4 == 0 && cols % 4 == 0, "cols and pitches must be multiples of 4");
-  dim3 block(128), grid(ceil_div(cols / 4, 128), static_cast<unsigned>(std::min<int64_t>(ceil_div64(rows, 4), kNumSMs * 8)));
+  dim3 block(32, 8), grid(ceil_div(cols / 4, 32), static_cast<unsigned>(std::min<int64_t>(ceil_div64(rows, 16), kNumSMs * 2)));
   cast_scale_kernel<<<grid, block, 0, static_cast<cudaStream_t>(stream)>>>(
       in, ldi, static_cast<__nv_bfloat16*>(out_bf16), ldo, row_scale, rows_per_scale > 0 ? rows_per_scale : 1,
       dbias, rows, cols);
@@ -302,7 +324,7 @@ extern "C" int cream_bias_grad(const void* dy_bf16, int64_t ld, float* dbias, in
                                void* stream) {
   if (rows == 0 || cols == 0) return CREAM_OK;
   CB_REQUIRE(dy_bf16 && dbias && ld % 2 == 0, "bad args");
-  dim3 block(128), grid(ceil_div(ceil_div(cols, 8), 128), static_cast<unsigned>(std::min<int64_t>(ceil_div64(rows, 4), kNumSMs * 16)));
+  dim3 block(32, 8), grid(ceil_div(ceil_div(cols, 8), 32), static_cast<unsigned>(std::min<int64_t>(ceil_div64(rows, 16), kNumSMs * 2)));
   colsum_kernel<<<grid, block, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const __nv_bfloat16*>(dy_bf16), ld, dbias, rows, cols);
   return check_last("colsum_kernel");

@@ -113,6 +113,7 @@ template <int EPI>
 __global__ void __launch_bounds__(kNumThreads, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                  const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_aux,
+                 const __grid_constant__ CUtensorMap tmap_out_h, const __grid_constant__ CUtensorMap tmap_aux_h,
                  const GemmKernelParams p) {
   using T = EpiTraits<EPI>;
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -222,9 +223,19 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     const bool issuer = threadIdx.x == kEpiWarp0 * 32;
     const uint32_t slot0 = smem_u32(epi_slots);
     // this thread's four 16-byte chunks in a staging tile: chunk u of row r sits at (u ^ (r & 7))
-    uint32_t chunk_off[4];
+    uint32_t chunk_full[4], chunk_half[4];
 #pragma unroll
-    for (int q = 0; q < 4; ++q) chunk_off[q] = r_local * 128 + (((half * 4 + q) ^ (r_local & 7)) << 4);
+    for (int q = 0; q < 4; ++q) {
+      chunk_full[q] = r_local * 128 + (((half * 4 + q) ^ (r_local & 7)) << 4);
+      chunk_half[q] = r_local * 64 + (q << 4);   // dense 64-byte rows (no swizzle), half-0 threads only
+    }
+    // A tile whose width is an odd multiple of half a store block ends in a HALF block: it must not
+    // spill into the neighbouring N tile, so it moves through the un-swizzled half-width maps.
+    auto is_half_block = [&](const WorkItem& it, int cb) {
+      const int n0 = it.nt * p.BN;
+      const int tile_cols = min(p.BN, p.N - n0);
+      return (tile_cols - cb * T::kCB) == T::kCB / 2 && (n0 + tile_cols) < p.N;
+    };
 
     int acc = 0;
     uint32_t acc_phase = 0;
@@ -234,8 +245,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     // operand prefetch (RESID / DGELU): block stream = (work item, column block) pairs
     auto issue_load = [&](int w, int cb, int s) {
       const WorkItem it = decode_work(p, w);
-      mbar_arrive_expect_tx(&ld_bar[s], kEpiSlotBytes);
-      tma_load_3d(epi_slots + s * kEpiSlotBytes, &tmap_aux, &ld_bar[s], it.nt * p.BN + cb * T::kCB, it.mt * kBM, it.g);
+      const bool hb = is_half_block(it, cb);
+      mbar_arrive_expect_tx(&ld_bar[s], hb ? kEpiSlotBytes / 2 : kEpiSlotBytes);
+      tma_load_3d(epi_slots + s * kEpiSlotBytes, hb ? &tmap_aux_h : &tmap_aux, &ld_bar[s],
+                  it.nt * p.BN + cb * T::kCB, it.mt * kBM, it.g);
     };
     if (T::kLoads && issuer && static_cast<int>(blockIdx.x) < p.total_work) issue_load(blockIdx.x, 0, 0);
 
@@ -305,8 +318,14 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           epi_barrier();
         }
         const uint32_t sbase = slot0 + slot * kEpiSlotBytes;
+        const bool hb = is_half_block(it, cb);
+        const bool active = !hb || half == 0;             // half-1 threads hold columns of the next tile
+        uint32_t chunk_off[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) chunk_off[q] = hb ? chunk_half[q] : chunk_full[q];
 
         // ---- epilogue math + write to the staging tile ----
+        if (active) {
         if constexpr (EPI == CREAM_EPI_F32_RESID) {
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
@@ -341,13 +360,16 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             sts_u32x4(sbase + chunk_off[q], u);
           }
         }
+        }  // active
         fence_proxy_async_smem();
         epi_barrier();
         if (issuer) {
           const int c0 = n0 + cb * T::kCB;
-          if constexpr (EPI == CREAM_EPI_F32_ATOMIC) tma_reduce_add_3d(&tmap_out, epi_slots + slot * kEpiSlotBytes, c0, m0, it.g);
-          else if constexpr (EPI == CREAM_EPI_BF16_GELU) tma_store_3d(&tmap_aux, epi_slots + slot * kEpiSlotBytes, c0, m0, it.g);
-          else tma_store_3d(&tmap_out, epi_slots + slot * kEpiSlotBytes, c0, m0, it.g);
+          const CUtensorMap* mo = hb ? &tmap_out_h : &tmap_out;
+          const CUtensorMap* mx = hb ? &tmap_aux_h : &tmap_aux;
+          if constexpr (EPI == CREAM_EPI_F32_ATOMIC) tma_reduce_add_3d(mo, epi_slots + slot * kEpiSlotBytes, c0, m0, it.g);
+          else if constexpr (EPI == CREAM_EPI_BF16_GELU) tma_store_3d(mx, epi_slots + slot * kEpiSlotBytes, c0, m0, it.g);
+          else tma_store_3d(mo, epi_slots + slot * kEpiSlotBytes, c0, m0, it.g);
           bulk_commit();
         }
         slot ^= 1;
@@ -357,6 +379,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           if (issuer) bulk_wait_read<1>();
           epi_barrier();
           const uint32_t sb2 = slot0 + slot * kEpiSlotBytes;
+          if (active) {
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             uint4 u;
@@ -366,10 +389,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             u.w = pack_bf16x2(gelu_f(bf16_round(v[8 * q + 6])), gelu_f(bf16_round(v[8 * q + 7])));
             sts_u32x4(sb2 + chunk_off[q], u);
           }
+          }
           fence_proxy_async_smem();
           epi_barrier();
           if (issuer) {
-            tma_store_3d(&tmap_out, epi_slots + slot * kEpiSlotBytes, n0 + cb * T::kCB, m0, it.g);
+            tma_store_3d(hb ? &tmap_out_h : &tmap_out, epi_slots + slot * kEpiSlotBytes, n0 + cb * T::kCB, m0, it.g);
             bulk_commit();
           }
           slot ^= 1;
@@ -395,14 +419,15 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 
 template <int EPI>
 int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const CUtensorMap& tx,
-                const GemmKernelParams& p, size_t smem_bytes, int grid, cudaStream_t stream) {
+                const CUtensorMap& toh, const CUtensorMap& txh, const GemmKernelParams& p, size_t smem_bytes,
+                int grid, cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
     CB_CUDA_OK(cudaFuncSetAttribute(gemm_bf16_kernel<EPI>,
                                     cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
-  gemm_bf16_kernel<EPI><<<grid, kNumThreads, smem_bytes, stream>>>(ta, tb, to, tx, p);
+  gemm_bf16_kernel<EPI><<<grid, kNumThreads, smem_bytes, stream>>>(ta, tb, to, tx, toh, txh, p);
   return check_last("gemm_bf16_kernel launch");
 }
 
@@ -436,8 +461,10 @@ extern "C" int cream_gemm_bf16(const cream_gemm_desc* d, void* stream_) {
 
   GemmKernelParams p{};
   p.M = d->M; p.N = d->N; p.K = d->K; p.groups = d->groups;
+  const bool out_is_bf16 = d->epi == CREAM_EPI_BF16 || d->epi == CREAM_EPI_BF16_GELU || d->epi == CREAM_EPI_BF16_DGELU;
   const int nt = ceil_div(d->N, 256);
-  p.BN = std::min(256, round_up(ceil_div(d->N, nt), 16));
+  // tile width: a multiple of half a store block (32 bf16 / 16 fp32 columns)
+  p.BN = std::min(256, round_up(ceil_div(d->N, nt), out_is_bf16 ? 32 : 16));
   p.num_nt = ceil_div(d->N, p.BN);
   p.num_mt = ceil_div(d->M, kBM);
   p.a_mn = d->a_mn ? 1 : 0;
@@ -513,29 +540,37 @@ extern "C" int cream_gemm_bf16(const cream_gemm_desc* d, void* stream_) {
   }
   // output (and epilogue operand) maps: element (n, m, g) at base + (m*row_mul + g*g_row)*ld + n + g*g_col
   const int row_mul = d->out_row_mul > 0 ? d->out_row_mul : 1;
-  auto out_like_map = [&](const void* base, int64_t ld, bool bf16) -> const CUtensorMap* {
+  auto out_like_map = [&](const void* base, int64_t ld, bool bf16, bool half_width) -> const CUtensorMap* {
     const uint64_t row_stride = static_cast<uint64_t>(row_mul) * ld;
     uint64_t g_stride = static_cast<uint64_t>(d->out_g_row) * ld + d->out_g_col;
     if (p.groups == 1 || g_stride == 0) g_stride = row_stride;
     const uint64_t dims[3] = {static_cast<uint64_t>(d->N), static_cast<uint64_t>(d->M), static_cast<uint64_t>(p.groups)};
     const uint64_t strides[3] = {1, row_stride, g_stride};
-    const uint32_t box[3] = {static_cast<uint32_t>(bf16 ? 64 : 32), kBM, 1};
+    const uint32_t full = bf16 ? 64 : 32;
+    const uint32_t box[3] = {half_width ? full / 2 : full, kBM, 1};
     return get_tensor_map(base, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, dims,
-                          strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
+                          strides, box, half_width ? CU_TENSOR_MAP_SWIZZLE_NONE : CU_TENSOR_MAP_SWIZZLE_128B);
   };
-  const CUtensorMap* to = out_like_map(d->out, d->ldo, out_bf16);
-  const CUtensorMap* tx = to;
-  if (d->epi == CREAM_EPI_BF16_GELU || d->epi == CREAM_EPI_BF16_DGELU) tx = out_like_map(d->aux, d->ldaux, true);
-  if (d->epi == CREAM_EPI_F32_RESID) tx = out_like_map(d->resid, d->ldr, false);
-  if (ta == nullptr || tb == nullptr || to == nullptr || tx == nullptr) return CREAM_ERR_CUDA;
+  const CUtensorMap* to = out_like_map(d->out, d->ldo, out_bf16, false);
+  const CUtensorMap* toh = out_like_map(d->out, d->ldo, out_bf16, true);
+  const CUtensorMap *tx = to, *txh = toh;
+  if (d->epi == CREAM_EPI_BF16_GELU || d->epi == CREAM_EPI_BF16_DGELU) {
+    tx = out_like_map(d->aux, d->ldaux, true, false);
+    txh = out_like_map(d->aux, d->ldaux, true, true);
+  }
+  if (d->epi == CREAM_EPI_F32_RESID) {
+    tx = out_like_map(d->resid, d->ldr, false, false);
+    txh = out_like_map(d->resid, d->ldr, false, true);
+  }
+  if (!ta || !tb || !to || !tx || !toh || !txh) return CREAM_ERR_CUDA;
 
   const int grid = std::min(p.total_work, kNumSMs);
   switch (d->epi) {
-    case CREAM_EPI_BF16: return launch_gemm<CREAM_EPI_BF16>(*ta, *tb, *to, *tx, p, smem_bytes, grid, stream);
-    case CREAM_EPI_BF16_GELU: return launch_gemm<CREAM_EPI_BF16_GELU>(*ta, *tb, *to, *tx, p, smem_bytes, grid, stream);
-    case CREAM_EPI_F32_RESID: return launch_gemm<CREAM_EPI_F32_RESID>(*ta, *tb, *to, *tx, p, smem_bytes, grid, stream);
-    case CREAM_EPI_BF16_DGELU: return launch_gemm<CREAM_EPI_BF16_DGELU>(*ta, *tb, *to, *tx, p, smem_bytes, grid, stream);
-    case CREAM_EPI_F32_ATOMIC: return launch_gemm<CREAM_EPI_F32_ATOMIC>(*ta, *tb, *to, *tx, p, smem_bytes, grid, stream);
-    default: return launch_gemm<CREAM_EPI_F32>(*ta, *tb, *to, *tx, p, smem_bytes, grid, stream);
+    case CREAM_EPI_BF16: return launch_gemm<CREAM_EPI_BF16>(*ta, *tb, *to, *tx, *toh, *txh, p, smem_bytes, grid, stream);
+    case CREAM_EPI_BF16_GELU: return launch_gemm<CREAM_EPI_BF16_GELU>(*ta, *tb, *to, *tx, *toh, *txh, p, smem_bytes, grid, stream);
+    case CREAM_EPI_F32_RESID: return launch_gemm<CREAM_EPI_F32_RESID>(*ta, *tb, *to, *tx, *toh, *txh, p, smem_bytes, grid, stream);
+    case CREAM_EPI_BF16_DGELU: return launch_gemm<CREAM_EPI_BF16_DGELU>(*ta, *tb, *to, *tx, *toh, *txh, p, smem_bytes, grid, stream);
+    case CREAM_EPI_F32_ATOMIC: return launch_gemm<CREAM_EPI_F32_ATOMIC>(*ta, *tb, *to, *tx, *toh, *txh, p, smem_bytes, grid, stream);
+    default: return launch_gemm<CREAM_EPI_F32>(*ta, *tb, *to, *tx, *toh, *txh, p, smem_bytes, grid, stream);
   }
 }

@@ -63,8 +63,10 @@ ln_fwd_kernel(const float* __restrict__ x, int64_t ldx, const float* __restrict_
 
 // dX = resid_grad + rstd * (dy*g - mean(dy*g) - xhat * mean(dy*g*xhat)); dgamma/dbeta via
 // per-lane register partials -> shared -> global atomics.
+constexpr int kBwdWarps = 8;
+
 template <bool kDyF32, int kPer>
-__global__ void __launch_bounds__(kWarps * 32)
+__global__ void __launch_bounds__(kBwdWarps * 32)
 ln_bwd_kernel(const void* __restrict__ dy, int64_t lddy, const float* __restrict__ x, int64_t ldx,
               const float* __restrict__ gamma, const float* __restrict__ mean,
               const float* __restrict__ rstd, const float* __restrict__ resid_grad, int64_t ldrg,
@@ -78,8 +80,8 @@ ln_bwd_kernel(const void* __restrict__ dy, int64_t lddy, const float* __restrict
   float pg[kPer], pb[kPer];
 #pragma unroll
   for (int i = 0; i < kPer; ++i) { pg[i] = 0.f; pb[i] = 0.f; }
-  for (int64_t r = static_cast<int64_t>(blockIdx.x) * kWarps + warp; r < rows;
-       r += static_cast<int64_t>(gridDim.x) * kWarps) {
+  for (int64_t r = static_cast<int64_t>(blockIdx.x) * kBwdWarps + warp; r < rows;
+       r += static_cast<int64_t>(gridDim.x) * kBwdWarps) {
     const float mu = mean[r], rs = rstd[r];
     const float* xr = x + r * ldx;
     float xh[kPer], dg[kPer];
@@ -156,11 +158,13 @@ extern "C" int cream_layernorm_bwd(const void* dy, int64_t lddy, int dy_f32, con
   if (rows == 0) return CREAM_OK;
   CB_REQUIRE(dy && x && gamma && mean && rstd && dx && dgamma && dbeta, "null pointer");
   CB_REQUIRE(E >= 1 && E <= 32 * kMaxPerLane, "embed dim must be <= 768");
-  const int grid = static_cast<int>(std::min<int64_t>(ceil_div64(rows, kWarps), kNumSMs * 8));
+  // few, fat blocks: every block ends with 2*E global atomics, so the block count bounds the
+  // per-address contention on dgamma / dbeta (1184 blocks made this kernel 4x slower than HBM)
+  const int grid = static_cast<int>(std::min<int64_t>(ceil_div64(rows, kBwdWarps), kNumSMs * 2));
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   const size_t smem = 2 * E * sizeof(float);
 #define CB_LN_BWD(F32, PER)                                                                             \
-  ln_bwd_kernel<F32, PER><<<grid, kWarps * 32, smem, stream>>>(dy, lddy, x, ldx, gamma, mean, rstd, resid_grad, \
+  ln_bwd_kernel<F32, PER><<<grid, kBwdWarps * 32, smem, stream>>>(dy, lddy, x, ldx, gamma, mean, rstd, resid_grad, \
                                                             ldrg, dx, lddx, dgamma, dbeta, rows, E)
   if (dy_f32) { if (E <= 256) CB_LN_BWD(true, 8); else if (E <= 512) CB_LN_BWD(true, 16); else CB_LN_BWD(true, 24); }
   else { if (E <= 256) CB_LN_BWD(false, 8); else if (E <= 512) CB_LN_BWD(false, 16); else CB_LN_BWD(false, 24); }
