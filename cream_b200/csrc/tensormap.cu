@@ -53,6 +53,19 @@ struct KeyHash {
 std::mutex g_mu;
 std::unordered_map<Key, CUtensorMap*, KeyHash> g_cache;
 
+// Callers receive a pointer into a per-thread ring of COPIES, never into the cache itself, so
+// evicting the cache cannot invalidate a map another entry point is about to launch with.
+constexpr int kRing = 32;  // >= 2x the maps any single C-ABI call requests
+struct alignas(64) MapSlot { CUtensorMap m; };
+thread_local MapSlot t_ring[kRing];
+thread_local unsigned t_ring_pos = 0;
+
+const CUtensorMap* hand_out(const CUtensorMap* cached) {
+  MapSlot& s = t_ring[t_ring_pos++ % kRing];
+  std::memcpy(&s.m, cached, sizeof(CUtensorMap));
+  return &s.m;
+}
+
 size_t elem_bytes(CUtensorMapDataType t) {
   switch (t) {
     case CU_TENSOR_MAP_DATA_TYPE_BFLOAT16:
@@ -79,7 +92,7 @@ const CUtensorMap* get_tensor_map(const void* base, CUtensorMapDataType dtype, i
   }
   std::lock_guard<std::mutex> lock(g_mu);
   auto it = g_cache.find(key);
-  if (it != g_cache.end()) return it->second;
+  if (it != g_cache.end()) return hand_out(it->second);
 
   EncodeFn enc = resolve_encode();
   if (enc == nullptr) return nullptr;
@@ -109,12 +122,12 @@ const CUtensorMap* get_tensor_map(const void* base, CUtensorMapDataType dtype, i
     free(m);
     return nullptr;
   }
-  if (g_cache.size() > 4096) {  // bounded: a supernet uses a few dozen maps
+  if (g_cache.size() > 16384) {  // bounded; weights need a few dozen maps, activation buffers recycle
     for (auto& kv : g_cache) free(kv.second);
     g_cache.clear();
   }
   g_cache.emplace(key, m);
-  return m;
+  return hand_out(m);
 }
 
 }  // namespace cb
