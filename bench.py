@@ -216,6 +216,16 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item()), flops, attn_flops, _lib.LAUNCHES[0] - launches0, loss_host
 
+    # allocator priming (initialisation, not a step of the workload): the largest and the smallest
+    # subnet once each, so the caching allocator owns its pools before any timed or warm-up step
+    # (the search space changes every activation shape from step to step).
+    ss = SEARCH_SPACE["S"]
+    for pick in (max, min):
+        d = pick(ss["depth"])
+        trainer.step(dev_imgs[0], dev_tgts[0], config={"layer_num": d, "embed_dim": [pick(ss["embed_dim"])] * d,
+                                                       "num_heads": [pick(ss["num_heads"])] * d,
+                                                       "mlp_ratio": [pick(ss["mlp_ratio"])] * d})
+    torch.cuda.synchronize()
     # identical config stream on every rank (supernet_engine.py:36 seeds `random` with the epoch)
     rnd = random.Random(0)
     timed(W, False, rnd)                                   # warm-up (untimed)
