@@ -55,7 +55,7 @@ struct RowCtx {
 // dT / P of one query row, generic gather tables (see attention_fwd.cu for the forward twin).
 __device__ __forceinline__ void bwd_row_generic(const BwdRowsParams& p, const RowCtx& x) {
   const int Npad = p.Npad;
-  for (int k = 0; k < kNB; ++k) { sts_f32(x.s_pb + 4 * k, 0.f); sts_f32(x.s_dr + 4 * k, 0.f); }
+  for (int k = 0; k < kNB; ++k) { sts_f32(x.s_pb + 4 * (k ^ x.sw), 0.f); sts_f32(x.s_dr + 4 * k, 0.f); }
   const uint8_t* ia = p.idx_a ? p.idx_a + static_cast<int64_t>(x.row_c) * p.ldi : nullptr;
   const uint8_t* ib = p.idx_b ? p.idx_b + static_cast<int64_t>(x.row_c) * p.ldi : nullptr;
   const uint8_t* iva = p.idx_va ? p.idx_va + static_cast<int64_t>(x.row_c) * p.ldi : nullptr;
@@ -195,7 +195,7 @@ __device__ __forceinline__ void bwd_row_af(const BwdRowsParams& p, const RowCtx&
     }
   }
   // scatter the register bucket sums into the shared rows read by the common tail
-  for (int k = 0; k < kNB; ++k) { sts_f32(x.s_pb + 4 * k, 0.f); sts_f32(x.s_dr + 4 * k, 0.f); }
+  for (int k = 0; k < kNB; ++k) { sts_f32(x.s_pb + 4 * (k ^ x.sw), 0.f); sts_f32(x.s_dr + 4 * k, 0.f); }
   if (patch) {
 #pragma unroll
     for (int t = 0; t < G; ++t) {
