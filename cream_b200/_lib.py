@@ -88,6 +88,9 @@ SIGNATURES = {
     "cream_bias_grad": (c_int, [c_void_p, c_i64, c_void_p, c_i64, c_int, c_void_p]),
     "cream_pack_tables": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_i64, c_i64, c_i64,
                                   c_void_p, c_int, c_int, c_i64, c_i64, c_i64, c_void_p]),
+    "cream_pack_tables_batch": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_i64, c_i64, c_void_p]),
+    "cream_unpack_table_grads_batch": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_i64, c_i64,
+                                               c_void_p]),
     "cream_unpack_table_grads": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_i64, c_i64, c_i64,
                                          c_void_p, c_int, c_int, c_i64, c_i64, c_i64, c_void_p]),
 }

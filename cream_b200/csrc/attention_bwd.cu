@@ -23,7 +23,8 @@ namespace {
 
 constexpr int kD = 64;
 constexpr int kNB = 64;
-constexpr int kRowsThreads = 160;
+constexpr int kRowsThreads = 288;  // warp 0: TMA + MMA issue; warps 1..8: two threads per query row
+constexpr int kRowThreads = 256;
 constexpr int kStride = 65;  // floats per row of the staged R / dPB / dR tiles
 
 struct BwdRowsParams {
@@ -42,12 +43,14 @@ struct BwdRowsParams {
   float* dbias;
 };
 
+__device__ __forceinline__ void rows_barrier() { asm volatile("bar.sync 2, %0;" ::"n"(kRowThreads) : "memory"); }
+
 struct RowCtx {
   uint32_t trow;        // TMEM address of this thread's lane
   uint32_t s_r, s_dpb;  // shared addresses of this row's staged R (scaled) and dPB, fp32[kStride]
   uint32_t s_pb, s_dr;  // shared addresses of this row's PB (xor-swizzled, 64 floats) and dR (kStride)
   uint32_t s_bias;
-  int row, row_c, sw;
+  int row, row_c, sw, half;
   float delta, lsel;
   int64_t wrow;
 };
@@ -55,6 +58,7 @@ struct RowCtx {
 // dT / P of one query row, generic gather tables (see attention_fwd.cu for the forward twin).
 __device__ __forceinline__ void bwd_row_generic(const BwdRowsParams& p, const RowCtx& x) {
   const int Npad = p.Npad;
+  if (x.half != 0) { rows_barrier(); rows_barrier(); return; }   // keep the barrier schedule of the pair
   for (int k = 0; k < kNB; ++k) { sts_f32(x.s_pb + 4 * (k ^ x.sw), 0.f); sts_f32(x.s_dr + 4 * k, 0.f); }
   const uint8_t* ia = p.idx_a ? p.idx_a + static_cast<int64_t>(x.row_c) * p.ldi : nullptr;
   const uint8_t* ib = p.idx_b ? p.idx_b + static_cast<int64_t>(x.row_c) * p.ldi : nullptr;
@@ -121,6 +125,8 @@ __device__ __forceinline__ void bwd_row_generic(const BwdRowsParams& p, const Ro
       wd[1] = make_uint4(dk[4], dk[5], dk[6], dk[7]);
     }
   }
+  rows_barrier();
+  rows_barrier();
 }
 
 // AutoFormer-structured twin (see softmax_af in attention_fwd.cu): the four gather operand
@@ -149,8 +155,10 @@ __device__ __forceinline__ void bwd_row_af(const BwdRowsParams& p, const RowCtx&
 #pragma unroll
   for (int t = 0; t < G; ++t) { prow[t] = 0.f; pcol[t] = 0.f; drow[t] = 0.f; dcol[t] = 0.f; }
   const bool live = x.row < N;
+  constexpr int kSplit = (NCH + 1) / 2;   // half 0: chunks [0, kSplit), half 1: [kSplit, NCH)
 #pragma unroll
   for (int c = 0; c < NCH; ++c) {
+    if ((c < kSplit) != (x.half == 0)) continue;
     uint32_t rt[16], rp[16];
     tmem_ld16(x.trow + c * 16, rt);
     tmem_ld16(x.trow + 256 + c * 16, rp);
@@ -194,26 +202,49 @@ __device__ __forceinline__ void bwd_row_af(const BwdRowsParams& p, const RowCtx&
       wd[1] = make_uint4(dk[4], dk[5], dk[6], dk[7]);
     }
   }
-  // scatter the register bucket sums into the shared rows read by the common tail
-  for (int k = 0; k < kNB; ++k) { sts_f32(x.s_pb + 4 * (k ^ x.sw), 0.f); sts_f32(x.s_dr + 4 * k, 0.f); }
-  if (patch) {
+  // scatter the register bucket sums into the shared rows read by the common tail: the thread
+  // owning the first column half initialises the row, its partner adds its partial sums.
+  if (x.half == 0) {
+    for (int k = 0; k < kNB; ++k) { sts_f32(x.s_pb + 4 * (k ^ x.sw), 0.f); sts_f32(x.s_dr + 4 * k, 0.f); }
+    if (patch) {
 #pragma unroll
-    for (int t = 0; t < G; ++t) {
-      sts_f32(x.s_pb + 4 * ((M1 - ri + t) ^ x.sw), prow[t]);
-      sts_f32(x.s_pb + 4 * ((32 + M1 - ci + t) ^ x.sw), pcol[t]);
-      sts_f32(x.s_dr + 4 * (M1 - ri + t), drow[t]);
-      sts_f32(x.s_dr + 4 * (32 + M1 - ci + t), dcol[t]);
+      for (int t = 0; t < G; ++t) {
+        sts_f32(x.s_pb + 4 * ((M1 - ri + t) ^ x.sw), prow[t]);
+        sts_f32(x.s_pb + 4 * ((32 + M1 - ci + t) ^ x.sw), pcol[t]);
+        sts_f32(x.s_dr + 4 * (M1 - ri + t), drow[t]);
+        sts_f32(x.s_dr + 4 * (32 + M1 - ci + t), dcol[t]);
+      }
+      sts_f32(x.s_pb + 4 * (0 ^ x.sw), p0);
+      sts_f32(x.s_pb + 4 * (32 ^ x.sw), p0);
+      sts_f32(x.s_dr, d0);
+      sts_f32(x.s_dr + 4 * 32, d0);
+    } else {
+      sts_f32(x.s_pb + 4 * (0 ^ x.sw), psum);
+      sts_f32(x.s_pb + 4 * (32 ^ x.sw), psum);
+      sts_f32(x.s_dr, dsum);
+      sts_f32(x.s_dr + 4 * 32, dsum);
     }
-    sts_f32(x.s_pb + 4 * (0 ^ x.sw), p0);
-    sts_f32(x.s_pb + 4 * (32 ^ x.sw), p0);
-    sts_f32(x.s_dr, d0);
-    sts_f32(x.s_dr + 4 * 32, d0);
-  } else {
-    sts_f32(x.s_pb + 4 * (0 ^ x.sw), psum);
-    sts_f32(x.s_pb + 4 * (32 ^ x.sw), psum);
-    sts_f32(x.s_dr, dsum);
-    sts_f32(x.s_dr + 4 * 32, dsum);
   }
+  rows_barrier();
+  if (x.half == 1) {
+    auto add = [](uint32_t a, float v) { sts_f32(a, lds_f32(a) + v); };
+    if (patch) {
+#pragma unroll
+      for (int t = 0; t < G; ++t) {
+        add(x.s_pb + 4 * ((M1 - ri + t) ^ x.sw), prow[t]);
+        add(x.s_pb + 4 * ((32 + M1 - ci + t) ^ x.sw), pcol[t]);
+        add(x.s_dr + 4 * (M1 - ri + t), drow[t]);
+        add(x.s_dr + 4 * (32 + M1 - ci + t), dcol[t]);
+      }
+      // j == 0 (cls key) lives in the first half: p0 / d0 are zero here
+    } else {
+      add(x.s_pb + 4 * (0 ^ x.sw), psum);
+      add(x.s_pb + 4 * (32 ^ x.sw), psum);
+      add(x.s_dr, dsum);
+      add(x.s_dr + 4 * 32, dsum);
+    }
+  }
+  rows_barrier();
 }
 
 __global__ void __launch_bounds__(kRowsThreads, 1)
@@ -256,9 +287,9 @@ attn_bwd_rows_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
     prefetch_tmap(&map_do);
     mbar_init(bar_ld, 1);
     mbar_init(bar_r, 1);
-    mbar_init(bar_rfree, 128);
+    mbar_init(bar_rfree, kRowThreads);
     mbar_init(bar_s, 1);
-    mbar_init(bar_p, 128);
+    mbar_init(bar_p, kRowThreads);
     mbar_init(bar_o, 1);
     fence_mbar_init();
   }
@@ -319,9 +350,11 @@ attn_bwd_rows_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
     }
   } else {
     const int quarter = warp & 3;
+    const int half = (warp - 1) >> 2;            // which column half of the row this thread owns
     const int r_local = quarter * 32 + lane;
     const int row = m0 + r_local;
     RowCtx x;
+    x.half = half;
     x.trow = tmem + (static_cast<uint32_t>(quarter * 32) << 16);
     x.s_r = smem_u32(sR) + r_local * kStride * 4;
     x.s_dpb = smem_u32(sdPB) + r_local * kStride * 4;
@@ -335,8 +368,8 @@ attn_bwd_rows_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
     if (any_r) {
       mbar_wait(bar_r, 0);
       tc_fence_after();
-#pragma unroll
-      for (int c = 0; c < 2; ++c) {
+      {
+        const int c = half;                      // each thread of the pair stages 32 of the 64 buckets
         uint32_t raw[32];
         if (p.ctx_k) {
           tmem_ld32(x.trow + c * 32, raw);
@@ -353,6 +386,7 @@ attn_bwd_rows_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
       }
       tc_fence_before();
       mbar_arrive(bar_rfree);
+      rows_barrier();                            // both halves of R / dPB staged before anyone gathers
     }
 
     // delta_i = dO_i . O_i and lse_i straight from global (256 B per row)
@@ -380,8 +414,8 @@ attn_bwd_rows_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
     else bwd_row_generic(p, x);
 
     // bucket sums: PB -> workspace ; dR -> workspace + TMEM (A operand of the dQ MMA)
-#pragma unroll
-    for (int c = 0; c < 2; ++c) {
+    {
+      const int c = half;
       uint32_t pk[16], dk[16];
 #pragma unroll
       for (int k = 0; k < 16; ++k) {
@@ -400,7 +434,7 @@ attn_bwd_rows_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
         }
       }
     }
-    if (p.dbias != nullptr && row < p.N) {
+    if (p.dbias != nullptr && row < p.N && half == 0) {
       for (int k = 0; k < kNB; ++k) atomicAdd(reinterpret_cast<float*>(sDbias) + k, lds_f32(x.s_dr + 4 * k));
     }
     tmem_st_wait();
@@ -411,8 +445,8 @@ attn_bwd_rows_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
     mbar_wait(bar_o, 0);
     tc_fence_after();
     __nv_bfloat16* qrow = p.dqkv + (static_cast<int64_t>(b) * p.N + row) * p.lddqkv + head * kD;
-#pragma unroll
-    for (int c = 0; c < 2; ++c) {
+    {
+      const int c = half;
       uint32_t raw[32];
       tmem_ld32(trow + 192 + c * 32, raw);
       tmem_ld_wait();

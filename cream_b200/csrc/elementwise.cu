@@ -255,6 +255,44 @@ unpack_grads_kernel(const float* __restrict__ dpack, PackSrc s0, PackSrc s1, int
   }
 }
 
+constexpr int kMaxBatchPacks = 64;
+struct PackBatch {
+  const float* src0[kMaxBatchPacks];
+  const float* src1[kMaxBatchPacks];
+  float* grad0[kMaxBatchPacks];
+  float* grad1[kMaxBatchPacks];
+};
+
+// One launch for every (layer, k|v) pack of a step: pack p <- rows [0,nb) from src0[p], rows
+// [row_off1, row_off1+nb) from src1[p] (tables (nb, D) with element strides), zeros elsewhere.
+__global__ void __launch_bounds__(256)
+pack_tables_batch_kernel(__nv_bfloat16* __restrict__ dst, const __grid_constant__ PackBatch b, int nb,
+                         int row_off1, int64_t stride_b, int64_t stride_d, int D) {
+  const int p = blockIdx.x;
+  for (int i = threadIdx.x; i < 64 * 64; i += blockDim.x) {
+    const int r = i >> 6, d = i & 63;
+    float v = 0.f;
+    if (d < D) {
+      if (r < nb) v = b.src0[p][r * stride_b + d * stride_d];
+      else if (b.src1[p] != nullptr && r >= row_off1 && r < row_off1 + nb) v = b.src1[p][(r - row_off1) * stride_b + d * stride_d];
+    }
+    dst[(static_cast<int64_t>(p) * 64 + r) * 64 + d] = __float2bfloat16_rn(v);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+unpack_grads_batch_kernel(const float* __restrict__ dpack, const __grid_constant__ PackBatch b, int nb,
+                          int row_off1, int64_t stride_b, int64_t stride_d, int D) {
+  const int p = blockIdx.x;
+  for (int i = threadIdx.x; i < 64 * 64; i += blockDim.x) {
+    const int r = i >> 6, d = i & 63;
+    if (d >= D) continue;
+    const float v = dpack[(static_cast<int64_t>(p) * 64 + r) * 64 + d];
+    if (r < nb) b.grad0[p][r * stride_b + d * stride_d] += v;
+    else if (b.grad1[p] != nullptr && r >= row_off1 && r < row_off1 + nb) b.grad1[p][(r - row_off1) * stride_b + d * stride_d] += v;
+  }
+}
+
 }  // namespace
 }  // namespace cb
 
@@ -354,4 +392,34 @@ extern "C" int cream_unpack_table_grads(const float* dpack, int num_tables, int 
   unpack_grads_kernel<<<num_tables, 256, 0, static_cast<cudaStream_t>(stream)>>>(dpack, a, b, stride_t0,
                                                                               stride_t1, head_dim);
   return check_last("unpack_grads_kernel");
+}
+
+extern "C" int cream_pack_tables_batch(void* dst_bf16, int n_packs, int head_dim, const float* const* src0_host,
+                                       const float* const* src1_host, int nb, int row_off1, int64_t stride_b,
+                                       int64_t stride_d, void* stream) {
+  CB_REQUIRE(dst_bf16 && src0_host && n_packs > 0 && n_packs <= kMaxBatchPacks, "1..64 packs per call");
+  CB_REQUIRE(head_dim > 0 && head_dim <= 64 && nb > 0 && nb <= 64 && row_off1 + nb <= 64 && row_off1 >= nb, "pack geometry");
+  PackBatch b{};
+  for (int i = 0; i < n_packs; ++i) {
+    b.src0[i] = src0_host[i];
+    b.src1[i] = src1_host ? src1_host[i] : nullptr;
+  }
+  pack_tables_batch_kernel<<<n_packs, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<__nv_bfloat16*>(dst_bf16), b, nb, row_off1, stride_b, stride_d, head_dim);
+  return check_last("pack_tables_batch_kernel");
+}
+
+extern "C" int cream_unpack_table_grads_batch(const float* dpack, int n_packs, int head_dim, float* const* grad0_host,
+                                              float* const* grad1_host, int nb, int row_off1, int64_t stride_b,
+                                              int64_t stride_d, void* stream) {
+  CB_REQUIRE(dpack && grad0_host && n_packs > 0 && n_packs <= kMaxBatchPacks, "1..64 packs per call");
+  CB_REQUIRE(head_dim > 0 && head_dim <= 64 && nb > 0 && nb <= 64 && row_off1 + nb <= 64 && row_off1 >= nb, "pack geometry");
+  PackBatch b{};
+  for (int i = 0; i < n_packs; ++i) {
+    b.grad0[i] = grad0_host[i];
+    b.grad1[i] = grad1_host ? grad1_host[i] : nullptr;
+  }
+  unpack_grads_batch_kernel<<<n_packs, 256, 0, static_cast<cudaStream_t>(stream)>>>(dpack, b, nb, row_off1, stride_b,
+                                                                                  stride_d, head_dim);
+  return check_last("unpack_grads_batch_kernel");
 }

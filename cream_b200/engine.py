@@ -143,6 +143,10 @@ def forward(P: Dict[str, torch.Tensor], geo: SupernetGeometry, config: dict, ima
     scale = 64 ** -0.5  # (64*h // h) ** -0.5 with change_qkv, multihead_super.py:110
     af = (geo.grid, geo.max_relative_position) if geo.relative_position else None
 
+    packs = None
+    if geo.relative_position:   # every (layer, k|v) table pair packed in ONE launch
+        packs = ops.pack_tables_batch([_tables(P, f"blocks.{i}.", kv) for i in range(config["layer_num"]) for kv in "kv"], dev)
+
     blocks = []
     for i in range(config["layer_num"]):
         pre = f"blocks.{i}."
@@ -156,8 +160,7 @@ def forward(P: Dict[str, torch.Tensor], geo: SupernetGeometry, config: dict, ima
         qkv = ops.qkv_fwd(ln1, wq, h, E, Es, P[pre + "attn.qkv.bias"])
         tk = tv = None
         if geo.relative_position:
-            tk = _pack_af(*_tables(P, pre, "k"))
-            tv = _pack_af(*_tables(P, pre, "v"))
+            tk, tv = packs[2 * i:2 * i + 1], packs[2 * i + 1:2 * i + 2]
         att, lse = ops.attention_fwd(qkv, B, h, N, scale, tk=tk, tv=tv, idx=idx, need_lse=save, af=af)
         wp = sh.get(P[pre + "attn.proj.weight"])
         x1 = ops.linear_fwd(att, wp, E, qd, P[pre + "attn.proj.bias"], epi=EPI_F32_RESID, resid=x,
@@ -232,6 +235,10 @@ def backward(P: Dict[str, torch.Tensor], geo: SupernetGeometry, saved: Saved, dl
     scale = 64 ** -0.5
     af = (geo.grid, geo.max_relative_position) if geo.relative_position else None
 
+    dpacks = None
+    if geo.relative_position:
+        dpacks = torch.zeros((2 * config["layer_num"], ops.NB_PACK, ops.HEAD_DIM), dtype=torch.float32, device=dev)
+
     for i in reversed(range(config["layer_num"])):
         pre = f"blocks.{i}."
         s = saved.blocks[i]
@@ -251,14 +258,15 @@ def backward(P: Dict[str, torch.Tensor], geo: SupernetGeometry, saved: Saved, dl
         dy1 = ops.cast_scale(g1, dps[0] if dps is not None else None, N, dbias=G[pre + "attn.proj.bias"])
         ops.linear_wgrad(dy1, s["att"], E, qd, G[pre + "attn.proj.weight"])
         datt = ops.linear_dgrad(dy1, sh.get(P[pre + "attn.proj.weight"]), E, qd)
-        dqkv, dtk, dtv, _ = ops.attention_bwd(s["qkv"], s["att"], s["lse"], datt, B, h, N, scale, tk=s["tk"],
-                                              tv=s["tv"], idx=idx, af=af)
-        if geo.relative_position:
-            for kv, dpack in (("k", dtk), ("v", dtv)):
-                gv = G[pre + f"attn.rel_pos_embed_{kv}.embeddings_table_v"]
-                gh = G[pre + f"attn.rel_pos_embed_{kv}.embeddings_table_h"]
-                ops.unpack_table_grads(dpack, 1, gv, gv.shape[0], 0, (0, gv.stride(0), gv.stride(1)),
-                                       gh, gh.shape[0], 32, (0, gh.stride(0), gh.stride(1)))
+        dqkv, _, _, _ = ops.attention_bwd(s["qkv"], s["att"], s["lse"], datt, B, h, N, scale, tk=s["tk"],
+                                          tv=s["tv"], idx=idx, af=af,
+                                          dtk=dpacks[2 * i:2 * i + 1] if dpacks is not None else None,
+                                          dtv=dpacks[2 * i + 1:2 * i + 2] if dpacks is not None else None)
+        if geo.relative_position and on_group_done is not None:
+            # table gradients of this layer must be final before its bucket is reduced
+            ops.unpack_table_grads_batch(dpacks[2 * i:2 * i + 2], [
+                (G[pre + f"attn.rel_pos_embed_{kv}.embeddings_table_v"], G[pre + f"attn.rel_pos_embed_{kv}.embeddings_table_h"])
+                for kv in "kv"])
         ops.bias_grad(dqkv, G[pre + "attn.qkv.bias"])
         ops.qkv_wgrad(dqkv, s["ln1"], h, E, G[pre + "attn.qkv.weight"])
         dln1 = ops.qkv_dgrad(dqkv, sh.get(P[pre + "attn.qkv.weight"], qkv=True), h, E, Es)
@@ -267,6 +275,11 @@ def backward(P: Dict[str, torch.Tensor], geo: SupernetGeometry, saved: Saved, dl
         saved.blocks[i] = None  # release activations as we go
         if on_group_done is not None:
             on_group_done("block%d" % i)
+
+    if geo.relative_position and on_group_done is None:   # single launch for all layers
+        ops.unpack_table_grads_batch(dpacks, [
+            (G[f"blocks.{i}.attn.rel_pos_embed_{kv}.embeddings_table_v"], G[f"blocks.{i}.attn.rel_pos_embed_{kv}.embeddings_table_h"])
+            for i in range(config["layer_num"]) for kv in "kv"])
 
     # ---- embedding ----
     dpatch = ops.empty_bf16(B * T, E, dev)

@@ -312,6 +312,32 @@ def unpack_table_grads(dpack, num_tables, g0, nb0, off0, strides0, g1=None, nb1=
           "cream_unpack_table_grads")
 
 
+def _ptr_array(tensors):
+    arr = (C.c_void_p * len(tensors))()
+    for i, t in enumerate(tensors):
+        arr[i] = t.data_ptr() if t is not None else None
+    return arr
+
+
+def pack_tables_batch(pairs, device) -> torch.Tensor:
+    """pairs: list of (table_a, table_b) fp32 (nb, 64) tensors -> (len, 64, 64) bf16 packs, one launch."""
+    t0 = pairs[0][0]
+    nb = t0.shape[0]
+    dst = torch.empty((len(pairs), NB_PACK, HEAD_DIM), dtype=torch.bfloat16, device=device)
+    a0, a1 = _ptr_array([p[0] for p in pairs]), _ptr_array([p[1] for p in pairs])
+    check(_lib.load().cream_pack_tables_batch(_p(dst), len(pairs), HEAD_DIM, a0, a1, nb, 32, t0.stride(0), t0.stride(1),
+                                              _stream()), "cream_pack_tables_batch")
+    return dst
+
+
+def unpack_table_grads_batch(dpacks: torch.Tensor, grad_pairs) -> None:
+    g0 = grad_pairs[0][0]
+    a0, a1 = _ptr_array([p[0] for p in grad_pairs]), _ptr_array([p[1] for p in grad_pairs])
+    check(_lib.load().cream_unpack_table_grads_batch(_p(dpacks), len(grad_pairs), HEAD_DIM, a0, a1, g0.shape[0], 32,
+                                                     g0.stride(0), g0.stride(1), _stream()),
+          "cream_unpack_table_grads_batch")
+
+
 def new_pack(num_tables: int, device) -> torch.Tensor:
     return torch.empty((num_tables, NB_PACK, HEAD_DIM), dtype=torch.bfloat16, device=device)
 
@@ -357,14 +383,17 @@ def attention_fwd(qkv, B, H, N, scale, *, tk=None, tv=None, per_head=False, idx=
 
 
 def attention_bwd(qkv, out, lse, dout, B, H, N, scale, *, tk=None, tv=None, per_head=False,
-                  idx=(None, None, None, None), bias=None, af=None):
-    """Returns (dqkv bf16, dtk_pack fp32|None, dtv_pack fp32|None, dbias fp32|None)."""
+                  idx=(None, None, None, None), bias=None, af=None, dtk=None, dtv=None):
+    """Returns (dqkv bf16, dtk_pack fp32|None, dtv_pack fp32|None, dbias fp32|None).  dtk / dtv may
+    be caller-provided zeroed (T, 64, 64) fp32 accumulators."""
     _check_2d(dout, torch.bfloat16, "dout", 8)
     dev = qkv.device
     dqkv = empty_bf16(B * N, 3 * H * HEAD_DIM, dev)
     T = H if per_head else 1
-    dtk = torch.zeros((T, NB_PACK, HEAD_DIM), dtype=torch.float32, device=dev) if tk is not None else None
-    dtv = torch.zeros((T, NB_PACK, HEAD_DIM), dtype=torch.float32, device=dev) if tv is not None else None
+    if dtk is None and tk is not None:
+        dtk = torch.zeros((T, NB_PACK, HEAD_DIM), dtype=torch.float32, device=dev)
+    if dtv is None and tv is not None:
+        dtv = torch.zeros((T, NB_PACK, HEAD_DIM), dtype=torch.float32, device=dev)
     dbias = torch.zeros((T, NB_PACK), dtype=torch.float32, device=dev) if bias is not None else None
     nbytes = _lib.load().cream_attn_bwd_workspace_bytes(B, H, N)
     ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)

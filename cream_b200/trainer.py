@@ -111,7 +111,8 @@ class SupernetTrainer:
         for g in used:
             self.buckets.flat[g].zero_()
         G = {n: self.buckets.views[n] for n in names}
-        engine.backward(self.params, self.geo, saved, dlogits, grads=G, on_group_done=self._allreduce)
+        engine.backward(self.params, self.geo, saved, dlogits, grads=G,
+                        on_group_done=self._allreduce if self.world > 1 else None)
         if self.comm_stream is not None:
             torch.cuda.current_stream().wait_stream(self.comm_stream)
         sampled = set(names)

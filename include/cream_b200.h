@@ -233,6 +233,17 @@ int cream_unpack_table_grads(const float* dpack, int num_tables, int head_dim, f
                              float* grad1, int nb1, int row_off1, int64_t stride_t1, int64_t stride_b1,
                              int64_t stride_d1, void* stream);
 
+/* Batched variants: one launch for all (layer, k|v) packs of a step (<= 64).  src*_host /
+ * grad*_host are HOST arrays of n_packs DEVICE pointers to (nb, head_dim) tables with element
+ * strides (stride_b, stride_d); table 0 goes to rows [0,nb), table 1 (may be NULL) to
+ * rows [row_off1, row_off1+nb).  dst / dpack are (n_packs, 64, 64). */
+int cream_pack_tables_batch(void* dst_bf16, int n_packs, int head_dim, const float* const* src0_host,
+                            const float* const* src1_host, int nb, int row_off1, int64_t stride_b,
+                            int64_t stride_d, void* stream);
+int cream_unpack_table_grads_batch(const float* dpack, int n_packs, int head_dim, float* const* grad0_host,
+                                   float* const* grad1_host, int nb, int row_off1, int64_t stride_b,
+                                   int64_t stride_d, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
