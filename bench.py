@@ -263,11 +263,19 @@ def main():
     peak_tf = peaks.get("bf16_tflops_sustained", 1400.0)
     peak_src = "measured (MEASURED_PEAKS.json bf16_tflops_sustained)" if peaks else "fallback (B200_PROFILING.md)"
     hbm = peaks.get("hbm_gbs", 6650.0)
+    traffic = None
+    tfile = ROOT / "profiles" / "ncu_traffic.json"
+    if tfile.exists():   # dram__bytes_read+write per launch from the committed `ncu --set full` capture
+        tj = json.loads(tfile.read_text())
+        gl = [v for k, v in tj.items() if k.startswith("gemm_bf16_kernel")]
+        if gl:
+            traffic = sum(v["dram_bytes_per_launch"] * v["launches"] for v in gl) / sum(v["launches"] for v in gl)
     gsec, gfl, _, gcnt = agg.get("gemm", [1e-9, 0, 0, 0])
     asec, afl, aby, acnt = agg.get("attn_fwd", [1e-9, 0, 0, 0])
     roofline = {"kernel": "gemm_bf16_kernel (all sliced linears: fwd, dgrad, wgrad)", "bound": "tensor",
                 "achieved": gfl / gsec / 1e12, "peak": peak_tf, "unit": "TFLOP/s",
-                "frac": gfl / gsec / 1e12 / peak_tf, "traffic": None, "launches": gcnt,
+                "frac": gfl / gsec / 1e12 / peak_tf, "traffic": traffic,
+                "traffic_note": "avg DRAM bytes per launch over the gemm launches in profiles/ncu_traffic.json", "launches": gcnt,
                 "avg_launch_us": gsec / max(gcnt, 1) * 1e6, "peak_source": peak_src}
     attn = {"kernel": "attn_fwd_kernel (fused QK^T + RPE gather + softmax + PV)", "bound": "hbm",
             "achieved": aby / asec / 1e9, "peak": hbm, "unit": "GB/s", "frac": aby / asec / 1e9 / hbm,

@@ -156,6 +156,10 @@ __device__ __forceinline__ void bwd_row_af(const BwdRowsParams& p, const RowCtx&
   for (int t = 0; t < G; ++t) { prow[t] = 0.f; pcol[t] = 0.f; drow[t] = 0.f; dcol[t] = 0.f; }
   const bool live = x.row < N;
   constexpr int kSplit = (NCH + 1) / 2;   // half 0: chunks [0, kSplit), half 1: [kSplit, NCH)
+  // The packed dT of chunk c overwrites T columns [8c, 8c+8).  For the second half those columns
+  // belong to chunks its PARTNER may not have read yet, so it keeps its packed dT in registers and
+  // stores them after the pair barrier below.
+  uint32_t keep[NCH - kSplit][8];
 #pragma unroll
   for (int c = 0; c < NCH; ++c) {
     if ((c < kSplit) != (x.half == 0)) continue;
@@ -192,7 +196,12 @@ __device__ __forceinline__ void bwd_row_af(const BwdRowsParams& p, const RowCtx&
       pk[k] = pack_bf16x2(pv[2 * k], pv[2 * k + 1]);
       dk[k] = pack_bf16x2(dt[2 * k], dt[2 * k + 1]);
     }
-    tmem_st8(x.trow + c * 8, dk);
+    if (c < kSplit) {
+      tmem_st8(x.trow + c * 8, dk);
+    } else {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) keep[c >= kSplit ? c - kSplit : 0][k] = dk[k];
+    }
     if (live) {
       uint4* wp = reinterpret_cast<uint4*>(p.ws_p + x.wrow + c * 16);
       uint4* wd = reinterpret_cast<uint4*>(p.ws_dt + x.wrow + c * 16);
@@ -227,6 +236,8 @@ __device__ __forceinline__ void bwd_row_af(const BwdRowsParams& p, const RowCtx&
   }
   rows_barrier();
   if (x.half == 1) {
+#pragma unroll
+    for (int c = kSplit; c < NCH; ++c) tmem_st8(x.trow + c * 8, keep[c - kSplit]);
     auto add = [](uint32_t a, float v) { sts_f32(a, lds_f32(a) + v); };
     if (patch) {
 #pragma unroll
@@ -507,16 +518,18 @@ attn_bwd_cols_kernel(const __grid_constant__ CUtensorMap map_wp, const __grid_co
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int head = blockIdx.x, b = blockIdx.y;
-  const int bh = b * p.H + head;
   const int nkb = ceil_div(p.N, 64);
   const int mtiles = ceil_div(p.Npad + kNB, 128);  // <= 3
+  const int nboxes = 2 * mtiles;                    // 64-column boxes actually consumed per workspace
+  const int items = p.B * p.H;                      // persistent: item = (batch, head)
+  uint64_t* acc_free = done + 1;                    // epilogue -> MMA: TMEM accumulators drained
 
   if (threadIdx.x == 0) {
     prefetch_tmap(&map_wp);
     prefetch_tmap(&map_wd);
     for (int s = 0; s < kColStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
     mbar_init(done, 1);
+    mbar_init(acc_free, 4);
     fence_mbar_init();
   }
   if (warp == 2) tmem_alloc<512>(tmem_slot);
@@ -526,74 +539,91 @@ attn_bwd_cols_kernel(const __grid_constant__ CUtensorMap map_wp, const __grid_co
   const uint32_t tmem = *tmem_slot;
 
   if (warp == 0 && lane == 0) {
-    for (int kb = 0; kb < nkb; ++kb) {
-      const int s = kb % kColStages;
-      mbar_wait(&empty[s], ((kb / kColStages) & 1) ^ 1);
-      uint8_t* st = smem + s * kColStageBytes;
-      mbar_arrive_expect_tx(&full[s], kColStageBytes);
-      for (int c = 0; c < 6; ++c) {
-        tma_load_3d(st + c * 8192, &map_wp, &full[s], c * 64, kb * 64, bh);
-        tma_load_3d(st + (6 + c) * 8192, &map_wd, &full[s], c * 64, kb * 64, bh);
+    // loads run ahead across items: the next item streams in while this one is drained
+    int it = 0;
+    for (int w = blockIdx.x; w < items; w += gridDim.x) {
+      const int b = w / p.H, head = w - b * p.H;
+      for (int kb = 0; kb < nkb; ++kb, ++it) {
+        const int s = it % kColStages;
+        mbar_wait(&empty[s], ((it / kColStages) & 1) ^ 1);
+        uint8_t* st = smem + s * kColStageBytes;
+        mbar_arrive_expect_tx(&full[s], (2 * nboxes + 2) * 8192);
+        for (int c = 0; c < nboxes; ++c) {
+          tma_load_3d(st + c * 8192, &map_wp, &full[s], c * 64, kb * 64, w);
+          tma_load_3d(st + (6 + c) * 8192, &map_wd, &full[s], c * 64, kb * 64, w);
+        }
+        tma_load_3d(st + 12 * 8192, &map_do, &full[s], head * kD, kb * 64, b);
+        tma_load_3d(st + 13 * 8192, &map_q, &full[s], head * kD, kb * 64, b);
       }
-      tma_load_3d(st + 12 * 8192, &map_do, &full[s], head * kD, kb * 64, b);
-      tma_load_3d(st + 13 * 8192, &map_q, &full[s], head * kD, kb * 64, b);
     }
   } else if (warp == 1 && lane == 0) {
     const uint32_t idesc = umma_idesc_bf16(128, kD, 1, 1);
-    for (int kb = 0; kb < nkb; ++kb) {
-      const int s = kb % kColStages;
-      mbar_wait(&full[s], (kb / kColStages) & 1);
+    int it = 0, n = 0;
+    for (int w = blockIdx.x; w < items; w += gridDim.x, ++n) {
+      mbar_wait(acc_free, (n & 1) ^ 1);             // previous item's accumulators have been read
       tc_fence_after();
-      const uint32_t st = smem_u32(smem + s * kColStageBytes);
-      for (int mt = 0; mt < mtiles; ++mt) {
+      for (int kb = 0; kb < nkb; ++kb, ++it) {
+        const int s = it % kColStages;
+        mbar_wait(&full[s], (it / kColStages) & 1);
+        tc_fence_after();
+        const uint32_t st = smem_u32(smem + s * kColStageBytes);
+        for (int mt = 0; mt < mtiles; ++mt) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const uint32_t acc = (kb > 0 || k > 0) ? 1u : 0u;
-          // A: two 64-wide MN chunks (LBO = 8192) of 64 K-rows; B: one chunk.
-          umma_ss(tmem + mt * 64, umma_smem_desc_sw128(st + (2 * mt) * 8192 + k * 2048, 8192, 1024),
-                  umma_smem_desc_sw128(st + 12 * 8192 + k * 2048, 8192, 1024), idesc, acc);
-          umma_ss(tmem + 192 + mt * 64, umma_smem_desc_sw128(st + (6 + 2 * mt) * 8192 + k * 2048, 8192, 1024),
-                  umma_smem_desc_sw128(st + 13 * 8192 + k * 2048, 8192, 1024), idesc, acc);
+          for (int k = 0; k < 4; ++k) {
+            const uint32_t acc = (kb > 0 || k > 0) ? 1u : 0u;
+            // A: two 64-wide MN chunks (LBO = 8192) of 64 K-rows; B: one chunk.
+            umma_ss(tmem + mt * 64, umma_smem_desc_sw128(st + (2 * mt) * 8192 + k * 2048, 8192, 1024),
+                    umma_smem_desc_sw128(st + 12 * 8192 + k * 2048, 8192, 1024), idesc, acc);
+            umma_ss(tmem + 192 + mt * 64, umma_smem_desc_sw128(st + (6 + 2 * mt) * 8192 + k * 2048, 8192, 1024),
+                    umma_smem_desc_sw128(st + 13 * 8192 + k * 2048, 8192, 1024), idesc, acc);
+          }
         }
+        umma_commit(&empty[s]);
       }
-      umma_commit(&empty[s]);
+      umma_commit(done);
     }
-    umma_commit(done);
   } else if (warp >= 2) {
     const int quarter = warp & 3;
-    mbar_wait(done, 0);
-    tc_fence_after();
     const uint32_t trow = tmem + (static_cast<uint32_t>(quarter * 32) << 16);
-    const int tab = p.shared_tables ? 0 : head;
-    for (int which = 0; which < 2; ++which) {          // 0: dV / dTV   1: dK / dTK
-      const float mul = which ? p.scale : 1.0f;
-      float* dtab = which ? p.dtk : p.dtv;
-      const int col0 = ((which ? 1 : 2) * p.H + head) * kD;
-      for (int mt = 0; mt < mtiles; ++mt) {
-        const int m = mt * 128 + quarter * 32 + lane;
+    int n = 0;
+    for (int w = blockIdx.x; w < items; w += gridDim.x, ++n) {
+      const int b = w / p.H, head = w - b * p.H;
+      mbar_wait(done, n & 1);
+      tc_fence_after();
+      const int tab = p.shared_tables ? 0 : head;
+      for (int which = 0; which < 2; ++which) {          // 0: dV / dTV   1: dK / dTK
+        const float mul = which ? p.scale : 1.0f;
+        float* dtab = which ? p.dtk : p.dtv;
+        const int col0 = ((which ? 1 : 2) * p.H + head) * kD;
+        for (int mt = 0; mt < mtiles; ++mt) {
+          const int m = mt * 128 + quarter * 32 + lane;
 #pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          uint32_t raw[32];
-          tmem_ld32(trow + which * 192 + mt * 64 + c * 32, raw);
-          tmem_ld_wait();
-          if (m < p.N) {
-            uint4* o4 = reinterpret_cast<uint4*>(p.dqkv + (static_cast<int64_t>(b) * p.N + m) * p.lddqkv + col0 + c * 32);
+          for (int c = 0; c < 2; ++c) {
+            uint32_t raw[32];
+            tmem_ld32(trow + which * 192 + mt * 64 + c * 32, raw);
+            tmem_ld_wait();
+            if (m < p.N) {
+              uint4* o4 = reinterpret_cast<uint4*>(p.dqkv + (static_cast<int64_t>(b) * p.N + m) * p.lddqkv + col0 + c * 32);
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              uint4 u;
-              u.x = pack_bf16x2(mul * __uint_as_float(raw[8 * q + 0]), mul * __uint_as_float(raw[8 * q + 1]));
-              u.y = pack_bf16x2(mul * __uint_as_float(raw[8 * q + 2]), mul * __uint_as_float(raw[8 * q + 3]));
-              u.z = pack_bf16x2(mul * __uint_as_float(raw[8 * q + 4]), mul * __uint_as_float(raw[8 * q + 5]));
-              u.w = pack_bf16x2(mul * __uint_as_float(raw[8 * q + 6]), mul * __uint_as_float(raw[8 * q + 7]));
-              o4[q] = u;
+              for (int q = 0; q < 4; ++q) {
+                uint4 u;
+                u.x = pack_bf16x2(mul * __uint_as_float(raw[8 * q + 0]), mul * __uint_as_float(raw[8 * q + 1]));
+                u.y = pack_bf16x2(mul * __uint_as_float(raw[8 * q + 2]), mul * __uint_as_float(raw[8 * q + 3]));
+                u.z = pack_bf16x2(mul * __uint_as_float(raw[8 * q + 4]), mul * __uint_as_float(raw[8 * q + 5]));
+                u.w = pack_bf16x2(mul * __uint_as_float(raw[8 * q + 6]), mul * __uint_as_float(raw[8 * q + 7]));
+                o4[q] = u;
+              }
+            } else if (m >= p.Npad && m < p.Npad + kNB && dtab != nullptr) {
+              float* dst = dtab + (static_cast<int64_t>(tab) * kNB + (m - p.Npad)) * kD + c * 32;
+#pragma unroll
+              for (int i = 0; i < 32; ++i) atomicAdd(dst + i, mul * __uint_as_float(raw[i]));
             }
-          } else if (m >= p.Npad && m < p.Npad + kNB && dtab != nullptr) {
-            float* dst = dtab + (static_cast<int64_t>(tab) * kNB + (m - p.Npad)) * kD + c * 32;
-#pragma unroll
-            for (int i = 0; i < 32; ++i) atomicAdd(dst + i, mul * __uint_as_float(raw[i]));
           }
         }
       }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(acc_free);
     }
   }
   tc_fence_before();
@@ -695,7 +725,7 @@ extern "C" int cream_attn_bwd(const cream_attn_desc* d, void* stream_) {
   c.dtk = ctx_k ? d->dtk_pack : nullptr;
   c.dtv = ctx_v ? d->dtv_pack : nullptr;
   const size_t smem_cols = kColStages * kColStageBytes + 256;
-  dim3 grid2(d->H, d->B);
+  const int grid2 = std::min(d->B * d->H, kNumSMs);
   attn_bwd_cols_kernel<<<grid2, kColsThreads, smem_cols, stream>>>(*mwp, *mwd, *mdo64, *mq64, c);
   return check_last("attn_bwd_cols_kernel");
 }
