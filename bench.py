@@ -191,6 +191,8 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    host_ms = [0.0]
+
     def timed(n_steps, from_host, rnd):
         flops = attn_flops = 0.0
         barrier()
@@ -198,6 +200,7 @@ def main():
         launches0 = _lib.LAUNCHES[0]
         e0.record()
         loss_host = 0.0
+        t_host0 = time.perf_counter()
         for s in range(n_steps):
             i = s % n_host
             if from_host:
@@ -209,6 +212,7 @@ def main():
             flops += 3.0 * f * B
             attn_flops += 3.0 * a * B
         e1.record()
+        host_ms[0] = (time.perf_counter() - t_host0) * 1e3 / max(n_steps, 1)   # enqueue time only (no sync yet)
         barrier()
         ms = e0.elapsed_time(e1)
         t = torch.tensor([ms], device=dev, dtype=torch.float64)
@@ -233,6 +237,7 @@ def main():
     if sampler:
         sampler.start()
     ms, flops, attn_flops, launches, _ = timed(K, False, rnd)
+    host_enqueue_ms = host_ms[0]
     clocks = sampler.stop() if sampler else None
     timed(2, True, rnd)
     ms_e2e, _, _, _, last_loss = timed(K, True, rnd)
@@ -293,6 +298,7 @@ def main():
         "e2e": {"value": imgs / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": B * 3 * 224 * 224 * 4 + B * 8,
                 "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / K, "last_loss": last_loss},
         "gpu_launches": launches,
+        "host_enqueue_ms_per_step": host_enqueue_ms,
         "clocks": clocks,
         "roofline": roofline,
         "attention": attn,
