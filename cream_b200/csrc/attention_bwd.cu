@@ -25,7 +25,8 @@ constexpr int kD = 64;
 constexpr int kNB = 64;
 constexpr int kRowsThreads = 288;  // warp 0: TMA + MMA issue; warps 1..8: two threads per query row
 constexpr int kRowThreads = 256;
-constexpr int kStride = 65;  // floats per row of the staged R / dPB / dR tiles
+constexpr int kStride = 66;  // floats per row of the staged R / dPB / dR tiles (66: the structured
+                             // gathers of 32 consecutive rows spread over the banks, <= 2-way)
 
 struct BwdRowsParams {
   int B, H, N, Npad, ldw;
@@ -48,7 +49,7 @@ __device__ __forceinline__ void rows_barrier() { asm volatile("bar.sync 2, %0;" 
 struct RowCtx {
   uint32_t trow;        // TMEM address of this thread's lane
   uint32_t s_r, s_dpb;  // shared addresses of this row's staged R (scaled) and dPB, fp32[kStride]
-  uint32_t s_pb, s_dr;  // shared addresses of this row's PB (xor-swizzled, 64 floats) and dR (kStride)
+  uint32_t s_pb, s_dr;  // shared addresses of this row's PB (64 floats, rotated by sw) and dR (kStride)
   uint32_t s_bias;
   int row, row_c, sw, half;
   float delta, lsel;
@@ -59,7 +60,7 @@ struct RowCtx {
 __device__ __forceinline__ void bwd_row_generic(const BwdRowsParams& p, const RowCtx& x) {
   const int Npad = p.Npad;
   if (x.half != 0) { rows_barrier(); rows_barrier(); return; }   // keep the barrier schedule of the pair
-  for (int k = 0; k < kNB; ++k) { sts_f32(x.s_pb + 4 * (k ^ x.sw), 0.f); sts_f32(x.s_dr + 4 * k, 0.f); }
+  for (int k = 0; k < kNB; ++k) { sts_f32(x.s_pb + 4 * ((k + x.sw) & 63), 0.f); sts_f32(x.s_dr + 4 * k, 0.f); }
   const uint8_t* ia = p.idx_a ? p.idx_a + static_cast<int64_t>(x.row_c) * p.ldi : nullptr;
   const uint8_t* ib = p.idx_b ? p.idx_b + static_cast<int64_t>(x.row_c) * p.ldi : nullptr;
   const uint8_t* iva = p.idx_va ? p.idx_va + static_cast<int64_t>(x.row_c) * p.ldi : nullptr;
@@ -101,8 +102,8 @@ __device__ __forceinline__ void bwd_row_generic(const BwdRowsParams& p, const Ro
       pv[k] = pr;
       dt[k] = d;
       if (p.ctx_v) {
-        if (iva) { const uint32_t a = x.s_pb + 4 * (va_id ^ x.sw); sts_f32(a, lds_f32(a) + pr); }
-        if (ivb) { const uint32_t a = x.s_pb + 4 * (vb_id ^ x.sw); sts_f32(a, lds_f32(a) + pr); }
+        if (iva) { const uint32_t a = x.s_pb + 4 * ((va_id + x.sw) & 63); sts_f32(a, lds_f32(a) + pr); }
+        if (ivb) { const uint32_t a = x.s_pb + 4 * ((vb_id + x.sw) & 63); sts_f32(a, lds_f32(a) + pr); }
       }
       if (want_dr) {
         if (ia) { const uint32_t a = x.s_dr + 4 * a_id; sts_f32(a, lds_f32(a) + d); }
@@ -214,22 +215,22 @@ __device__ __forceinline__ void bwd_row_af(const BwdRowsParams& p, const RowCtx&
   // scatter the register bucket sums into the shared rows read by the common tail: the thread
   // owning the first column half initialises the row, its partner adds its partial sums.
   if (x.half == 0) {
-    for (int k = 0; k < kNB; ++k) { sts_f32(x.s_pb + 4 * (k ^ x.sw), 0.f); sts_f32(x.s_dr + 4 * k, 0.f); }
+    for (int k = 0; k < kNB; ++k) { sts_f32(x.s_pb + 4 * ((k + x.sw) & 63), 0.f); sts_f32(x.s_dr + 4 * k, 0.f); }
     if (patch) {
 #pragma unroll
       for (int t = 0; t < G; ++t) {
-        sts_f32(x.s_pb + 4 * ((M1 - ri + t) ^ x.sw), prow[t]);
-        sts_f32(x.s_pb + 4 * ((32 + M1 - ci + t) ^ x.sw), pcol[t]);
+        sts_f32(x.s_pb + 4 * (((M1 - ri + t) + x.sw) & 63), prow[t]);
+        sts_f32(x.s_pb + 4 * (((32 + M1 - ci + t) + x.sw) & 63), pcol[t]);
         sts_f32(x.s_dr + 4 * (M1 - ri + t), drow[t]);
         sts_f32(x.s_dr + 4 * (32 + M1 - ci + t), dcol[t]);
       }
-      sts_f32(x.s_pb + 4 * (0 ^ x.sw), p0);
-      sts_f32(x.s_pb + 4 * (32 ^ x.sw), p0);
+      sts_f32(x.s_pb + 4 * ((0 + x.sw) & 63), p0);
+      sts_f32(x.s_pb + 4 * ((32 + x.sw) & 63), p0);
       sts_f32(x.s_dr, d0);
       sts_f32(x.s_dr + 4 * 32, d0);
     } else {
-      sts_f32(x.s_pb + 4 * (0 ^ x.sw), psum);
-      sts_f32(x.s_pb + 4 * (32 ^ x.sw), psum);
+      sts_f32(x.s_pb + 4 * ((0 + x.sw) & 63), psum);
+      sts_f32(x.s_pb + 4 * ((32 + x.sw) & 63), psum);
       sts_f32(x.s_dr, dsum);
       sts_f32(x.s_dr + 4 * 32, dsum);
     }
@@ -242,15 +243,15 @@ __device__ __forceinline__ void bwd_row_af(const BwdRowsParams& p, const RowCtx&
     if (patch) {
 #pragma unroll
       for (int t = 0; t < G; ++t) {
-        add(x.s_pb + 4 * ((M1 - ri + t) ^ x.sw), prow[t]);
-        add(x.s_pb + 4 * ((32 + M1 - ci + t) ^ x.sw), pcol[t]);
+        add(x.s_pb + 4 * (((M1 - ri + t) + x.sw) & 63), prow[t]);
+        add(x.s_pb + 4 * (((32 + M1 - ci + t) + x.sw) & 63), pcol[t]);
         add(x.s_dr + 4 * (M1 - ri + t), drow[t]);
         add(x.s_dr + 4 * (32 + M1 - ci + t), dcol[t]);
       }
       // j == 0 (cls key) lives in the first half: p0 / d0 are zero here
     } else {
-      add(x.s_pb + 4 * (0 ^ x.sw), psum);
-      add(x.s_pb + 4 * (32 ^ x.sw), psum);
+      add(x.s_pb + 4 * ((0 + x.sw) & 63), psum);
+      add(x.s_pb + 4 * ((32 + x.sw) & 63), psum);
       add(x.s_dr, dsum);
       add(x.s_dr + 4 * 32, dsum);
     }
@@ -284,7 +285,7 @@ attn_bwd_rows_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
   uint64_t* bar_p = bars + 4;
   uint64_t* bar_o = bars + 5;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
-  // overlays: PB (128 x 64 fp32, xor-swizzled) over sQ|sdO ; dR (128 x 65 fp32) over sV|sTV
+  // overlays: PB (128 x 64 fp32, each row rotated by 2*row) over sQ|sdO ; dR (128 x 65 fp32) over sV|sTV
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.x * 128, head = blockIdx.y, b = blockIdx.z;
@@ -374,7 +375,7 @@ attn_bwd_rows_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
     x.s_bias = smem_u32(sBias);
     x.row = row;
     x.row_c = min(row, p.N - 1);
-    x.sw = r_local & 31;
+    x.sw = (2 * r_local) & 63;
 
     if (any_r) {
       mbar_wait(bar_r, 0);
@@ -431,7 +432,7 @@ attn_bwd_rows_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
 #pragma unroll
       for (int k = 0; k < 16; ++k) {
         const int b0 = c * 32 + 2 * k;
-        pk[k] = pack_bf16x2(lds_f32(x.s_pb + 4 * (b0 ^ x.sw)), lds_f32(x.s_pb + 4 * ((b0 + 1) ^ x.sw)));
+        pk[k] = pack_bf16x2(lds_f32(x.s_pb + 4 * ((b0 + x.sw) & 63)), lds_f32(x.s_pb + 4 * (((b0 + 1) + x.sw) & 63)));
         dk[k] = pack_bf16x2(lds_f32(x.s_dr + 4 * b0), lds_f32(x.s_dr + 4 * (b0 + 1)));
       }
       if (p.ctx_k) tmem_st16(x.trow + Npad / 2 + c * 16, dk);

@@ -313,10 +313,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           }
           mbar_wait(&ld_bar[slot], ld_phase[slot]);
           ld_phase[slot] ^= 1;
-        } else {
-          if (issuer) bulk_wait_read<1>();               // at most the other tile still in flight
-          epi_barrier();
         }
+        // (without loads: the barrier of the previous store job already proved this tile drained —
+        //  the issuer waits for the older store before every barrier, see below)
         const uint32_t sbase = slot0 + slot * kEpiSlotBytes;
         const bool hb = is_half_block(it, cb);
         const bool active = !hb || half == 0;             // half-1 threads hold columns of the next tile
@@ -362,6 +361,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         }
         }  // active
         fence_proxy_async_smem();
+        if constexpr (!T::kLoads) {
+          if (issuer) bulk_wait_read<0>();               // previous store job has left its tile
+        }
         epi_barrier();
         if (issuer) {
           const int c0 = n0 + cb * T::kCB;
@@ -376,8 +378,6 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 
         if constexpr (EPI == CREAM_EPI_BF16_GELU) {
           // second store job of the block: GELU of the bf16-rounded pre-activation (what backward sees)
-          if (issuer) bulk_wait_read<1>();
-          epi_barrier();
           const uint32_t sb2 = slot0 + slot * kEpiSlotBytes;
           if (active) {
 #pragma unroll
@@ -391,6 +391,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           }
           }
           fence_proxy_async_smem();
+          if (issuer) bulk_wait_read<0>();
           epi_barrier();
           if (issuer) {
             tma_store_3d(hb ? &tmap_out_h : &tmap_out, epi_slots + slot * kEpiSlotBytes, n0 + cb * T::kCB, m0, it.g);
