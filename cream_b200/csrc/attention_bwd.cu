@@ -152,10 +152,22 @@ __device__ __forceinline__ void bwd_row_af(const BwdRowsParams& p, const RowCtx&
     gv[t] = patch ? lds_f32(x.s_dpb + 4 * (M1 - ri + t)) : g0v;
     gh[t] = patch ? lds_f32(x.s_dpb + 4 * (32 + M1 - ci + t)) : g0h;
   }
-  float prow[G], pcol[G], drow[G], dcol[G], p0 = 0.f, d0 = 0.f, psum = 0.f, dsum = 0.f;
+  float prow[G], pcol[G], drow[G], dcol[G], p0 = 0.f, d0 = 0.f;
 #pragma unroll
   for (int t = 0; t < G; ++t) { prow[t] = 0.f; pcol[t] = 0.f; drow[t] = 0.f; dcol[t] = 0.f; }
   const bool live = x.row < N;
+  // Fold the per-row constants into the gather operands so one element costs
+  //   e = T * (scale log2e) + rv2[rj] + rh2[cj] ; p = 2^e ; dT = p * (dP + gv2[rj] + gh[cj]).
+  // A padding row gets lse = +huge, i.e. p = 0 everywhere, without a per-element select.
+  const float sl = p.scale * kLog2e;
+  const float lsel = live ? x.lsel : 1e30f;
+  const float e0 = fmaf(r0v + r0h, kLog2e, -lsel), g0 = g0v + g0h - x.delta;
+#pragma unroll
+  for (int t = 0; t < G; ++t) {
+    rv[t] = fmaf(rv[t], kLog2e, -lsel);
+    rh[t] *= kLog2e;
+    gv[t] -= x.delta;
+  }
   constexpr int kSplit = (NCH + 1) / 2;   // half 0: chunks [0, kSplit), half 1: [kSplit, NCH)
   // The packed dT of chunk c overwrites T columns [8c, 8c+8).  For the second half those columns
   // belong to chunks its PARTNER may not have read yet, so it keeps its packed dT in registers and
@@ -172,24 +184,19 @@ __device__ __forceinline__ void bwd_row_af(const BwdRowsParams& p, const RowCtx&
 #pragma unroll
     for (int k = 0; k < 16; ++k) {
       const int j = c * 16 + k;
-      float t, dp = __uint_as_float(rp[k]);
-      if (j == 0) { t = fmaf(p.scale, __uint_as_float(rt[k]), r0v + r0h); dp += g0v + g0h; }
-      else if (j < N) {
-        t = fmaf(p.scale, __uint_as_float(rt[k]), rv[(j - 1) / G]) + rh[(j - 1) % G];
-        dp += gv[(j - 1) / G] + gh[(j - 1) % G];
-      } else { t = 0.f; }
-      float pr = fast_exp2(fmaf(t, kLog2e, -x.lsel));
-      if (j >= N || !live) pr = 0.f;
-      const float d = pr * (dp - x.delta);
-      pv[k] = pr;
-      dt[k] = d;
-      psum += pr;
-      dsum += d;
-      if (j == 0) { p0 = pr; d0 = d; }
-      else if (j < N) {
+      float pr = 0.f, d = 0.f;
+      if (j == 0) {
+        pr = fast_exp2(fmaf(sl, __uint_as_float(rt[k]), e0));
+        d = pr * (__uint_as_float(rp[k]) + g0);
+        p0 = pr; d0 = d;
+      } else if (j < N) {
+        pr = fast_exp2(fmaf(sl, __uint_as_float(rt[k]), rv[(j - 1) / G]) + rh[(j - 1) % G]);
+        d = pr * (__uint_as_float(rp[k]) + gv[(j - 1) / G] + gh[(j - 1) % G]);
         prow[(j - 1) / G] += pr; pcol[(j - 1) % G] += pr;
         drow[(j - 1) / G] += d;  dcol[(j - 1) % G] += d;
       }
+      pv[k] = pr;
+      dt[k] = d;
     }
     uint32_t pk[8], dk[8];
 #pragma unroll
@@ -212,6 +219,9 @@ __device__ __forceinline__ void bwd_row_af(const BwdRowsParams& p, const RowCtx&
       wd[1] = make_uint4(dk[4], dk[5], dk[6], dk[7]);
     }
   }
+  float psum = p0, dsum = d0;   // this thread's share of the row totals (every key hits one prow bucket)
+#pragma unroll
+  for (int t = 0; t < G; ++t) { psum += prow[t]; dsum += drow[t]; }
   // scatter the register bucket sums into the shared rows read by the common tail: the thread
   // owning the first column half initialises the row, its partner adds its partial sums.
   if (x.half == 0) {
