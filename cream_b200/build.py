@@ -43,7 +43,7 @@ def _compile_one(src: Path, verbose: bool) -> Path:
     BUILD.mkdir(exist_ok=True)
     obj = BUILD / (src.stem + ".o")
     stamp = BUILD / (src.stem + ".sha")
-    flags = NVCC_FLAGS + GENCODE
+    flags = NVCC_FLAGS + GENCODE + os.environ.get("CREAM_B200_EXTRA_NVCC_FLAGS", "").split()
     dig = _digest(src, " ".join(flags))
     if obj.exists() and stamp.exists() and stamp.read_text() == dig:
         return obj

@@ -18,6 +18,9 @@
 //                 the epilogue are TMA-prefetched into the same staging tile one block ahead, so the
 //                 epilogue issues no strided global accesses and needs no bounds predicates (the
 //                 tensor maps clip ragged M / N tails).
+#include <cstdlib>
+#include <vector>
+
 #include "attention_common.cuh"  // explicit shared-memory accessors
 
 namespace cb {
@@ -47,7 +50,17 @@ struct GemmKernelParams {
   const float* row_scale;
   int rows_per_scale;
   float alpha;
+  long long* trace;   // CREAM_TRACE builds only
 };
+
+#ifdef CREAM_TRACE
+#define CB_TRACE(region, idx, k)                                                         \
+  do {                                                                                   \
+    if (p.trace != nullptr && blockIdx.x == 0 && (idx) < 96) p.trace[(region) * 1024 + (idx) * 8 + (k)] = clock64(); \
+  } while (0)
+#else
+#define CB_TRACE(region, idx, k) do {} while (0)
+#endif
 
 struct WorkItem {
   int mt, nt, g, kb0, kb1;
@@ -188,10 +201,13 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     uint32_t phase = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
+    [[maybe_unused]] int tile_no = 0;
     for (int w = blockIdx.x; w < p.total_work; w += gridDim.x) {
       const WorkItem it = decode_work(p, w);
+      CB_TRACE(2, tile_no, 0);
       mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
       tc_fence_after();
+      CB_TRACE(2, tile_no, 1);
       const uint32_t d_tmem = tmem_base + acc * 256;
       for (int kb = it.kb0; kb < it.kb1; ++kb) {
         mbar_wait(&full_bar[stage], phase);
@@ -212,6 +228,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         if (++stage == p.num_stages) { stage = 0; phase ^= 1; }
       }
       umma_commit(&tmem_full[acc]);
+      CB_TRACE(2, tile_no, 2);
+      ++tile_no;
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
@@ -241,6 +259,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     uint32_t acc_phase = 0;
     int slot = 0;                       // staging tile used by the next store job
     uint32_t ld_phase[2] = {0, 0};
+    [[maybe_unused]] int tile_no = 0, job_no = 0;
 
     // operand prefetch (RESID / DGELU): block stream = (work item, column block) pairs
     auto issue_load = [&](int w, int cb, int s) {
@@ -252,11 +271,36 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     };
     if (T::kLoads && issuer && static_cast<int>(blockIdx.x) < p.total_work) issue_load(blockIdx.x, 0, 0);
 
+    // bias of the column block about to be drained (this thread's kPerThread columns), kept in
+    // registers and requested one block ahead so its latency never sits on the critical path
+    [[maybe_unused]] float bv[T::kPerThread];
+    auto load_bias = [&](int col0, int g) {
+#pragma unroll
+      for (int i = 0; i < T::kPerThread; ++i) bv[i] = 0.f;
+      if (p.bias == nullptr) return;
+      const float* bp = p.bias + col0 + g * p.out_g_col;
+      if (col0 + T::kPerThread <= p.N) {
+#pragma unroll
+        for (int q = 0; q < T::kPerThread / 4; ++q) {
+          const float4 bb = __ldg(reinterpret_cast<const float4*>(bp) + q);
+          bv[4 * q + 0] = bb.x; bv[4 * q + 1] = bb.y; bv[4 * q + 2] = bb.z; bv[4 * q + 3] = bb.w;
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < T::kPerThread; ++i)
+          if (col0 + i < p.N) bv[i] = __ldg(bp + i);
+      }
+    };
+
     for (int w = blockIdx.x; w < p.total_work; w += gridDim.x) {
       const WorkItem it = decode_work(p, w);
       const int m0 = it.mt * kBM, n0 = it.nt * p.BN;
+      if constexpr (T::kBias) load_bias(n0 + half * T::kPerThread, it.g);   // overlaps the wait below
+      if (issuer) CB_TRACE(1, tile_no, 0);
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
+      if (issuer) CB_TRACE(1, tile_no, 1);
+      ++tile_no;
       const int row = m0 + r_local;
       const int tile_cols = min(p.BN, p.N - n0);
       const int nblocks = (tile_cols + T::kCB - 1) / T::kCB;
@@ -265,9 +309,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         if (p.row_scale != nullptr && row < p.M) rscale = __ldg(p.row_scale + row / p.rows_per_scale);
       }
       for (int cb = 0; cb < nblocks; ++cb) {
-        const int col0 = n0 + cb * T::kCB + half * T::kPerThread;     // first column of this thread
-        const int ocol = col0 + it.g * p.out_g_col;
         // ---- accumulator -> registers ----
+        if (issuer) CB_TRACE(0, job_no, 0);
         float v[T::kPerThread];
         {
           const uint32_t taddr = tmem_base + acc * 256 + cb * T::kCB + half * T::kPerThread +
@@ -287,22 +330,13 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           }
         }
         if constexpr (T::kBias) {
-          if (p.bias != nullptr) {
-            if (col0 + T::kPerThread <= p.N) {
-              const float4* b4 = reinterpret_cast<const float4*>(p.bias + ocol);
 #pragma unroll
-              for (int q = 0; q < T::kPerThread / 4; ++q) {
-                const float4 bb = __ldg(b4 + q);
-                v[4 * q + 0] += bb.x; v[4 * q + 1] += bb.y; v[4 * q + 2] += bb.z; v[4 * q + 3] += bb.w;
-              }
-            } else {
-#pragma unroll
-              for (int i = 0; i < T::kPerThread; ++i)
-                if (col0 + i < p.N) v[i] += __ldg(p.bias + ocol + i);
-            }
-          }
+          for (int i = 0; i < T::kPerThread; ++i) v[i] += bv[i];
+          // the next block's bias is requested now and consumed after that block's accumulator read
+          if (cb + 1 < nblocks) load_bias(n0 + (cb + 1) * T::kCB + half * T::kPerThread, it.g);
         }
 
+        if (issuer) CB_TRACE(0, job_no, 1);
         // ---- acquire the staging tile ----
         if constexpr (T::kLoads) {
           if (issuer) {
@@ -316,6 +350,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         }
         // (without loads: the barrier of the previous store job already proved this tile drained —
         //  the issuer waits for the older store before every barrier, see below)
+        if (issuer) CB_TRACE(0, job_no, 2);
         const uint32_t sbase = slot0 + slot * kEpiSlotBytes;
         const bool hb = is_half_block(it, cb);
         const bool active = !hb || half == 0;             // half-1 threads hold columns of the next tile
@@ -324,6 +359,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         for (int q = 0; q < 4; ++q) chunk_off[q] = hb ? chunk_half[q] : chunk_full[q];
 
         // ---- epilogue math + write to the staging tile ----
+        [[maybe_unused]] uint4 pre[4];
         if (active) {
         if constexpr (EPI == CREAM_EPI_F32_RESID) {
 #pragma unroll
@@ -357,14 +393,18 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             u.z = pack_bf16x2(v[8 * q + 4], v[8 * q + 5]);
             u.w = pack_bf16x2(v[8 * q + 6], v[8 * q + 7]);
             sts_u32x4(sbase + chunk_off[q], u);
+            if constexpr (EPI == CREAM_EPI_BF16_GELU) pre[q] = u;
           }
         }
         }  // active
         fence_proxy_async_smem();
+        if (issuer) CB_TRACE(0, job_no, 3);
         if constexpr (!T::kLoads) {
           if (issuer) bulk_wait_read<0>();               // previous store job has left its tile
         }
+        if (issuer) CB_TRACE(0, job_no, 4);
         epi_barrier();
+        if (issuer) CB_TRACE(0, job_no, 5);
         if (issuer) {
           const int c0 = n0 + cb * T::kCB;
           const CUtensorMap* mo = hb ? &tmap_out_h : &tmap_out;
@@ -374,6 +414,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           else tma_store_3d(mo, epi_slots + slot * kEpiSlotBytes, c0, m0, it.g);
           bulk_commit();
         }
+        if (issuer) CB_TRACE(0, job_no, 6);
+        ++job_no;
         slot ^= 1;
 
         if constexpr (EPI == CREAM_EPI_BF16_GELU) {
@@ -382,11 +424,12 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           if (active) {
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
+            // pre[] holds the bf16 pairs just stored: widen them back instead of re-rounding v[]
             uint4 u;
-            u.x = pack_bf16x2(gelu_f(bf16_round(v[8 * q + 0])), gelu_f(bf16_round(v[8 * q + 1])));
-            u.y = pack_bf16x2(gelu_f(bf16_round(v[8 * q + 2])), gelu_f(bf16_round(v[8 * q + 3])));
-            u.z = pack_bf16x2(gelu_f(bf16_round(v[8 * q + 4])), gelu_f(bf16_round(v[8 * q + 5])));
-            u.w = pack_bf16x2(gelu_f(bf16_round(v[8 * q + 6])), gelu_f(bf16_round(v[8 * q + 7])));
+            u.x = pack_bf16x2(gelu_f(__uint_as_float(pre[q].x << 16)), gelu_f(__uint_as_float(pre[q].x & 0xffff0000u)));
+            u.y = pack_bf16x2(gelu_f(__uint_as_float(pre[q].y << 16)), gelu_f(__uint_as_float(pre[q].y & 0xffff0000u)));
+            u.z = pack_bf16x2(gelu_f(__uint_as_float(pre[q].z << 16)), gelu_f(__uint_as_float(pre[q].z & 0xffff0000u)));
+            u.w = pack_bf16x2(gelu_f(__uint_as_float(pre[q].w << 16)), gelu_f(__uint_as_float(pre[q].w & 0xffff0000u)));
             sts_u32x4(sb2 + chunk_off[q], u);
           }
           }
@@ -565,7 +608,47 @@ extern "C" int cream_gemm_bf16(const cream_gemm_desc* d, void* stream_) {
   }
   if (!ta || !tb || !to || !tx || !toh || !txh) return CREAM_ERR_CUDA;
 
+#ifdef CREAM_TRACE
+  static long long* trace_dev = nullptr;
+  const char* trace_env = getenv("CREAM_GEMM_TRACE");
+  if (trace_env != nullptr) {
+    if (trace_dev == nullptr) CB_CUDA_OK(cudaMalloc(&trace_dev, 3 * 1024 * sizeof(long long)));
+    CB_CUDA_OK(cudaMemsetAsync(trace_dev, 0, 3 * 1024 * sizeof(long long), stream));
+    p.trace = trace_dev;
+  }
+#endif
   const int grid = std::min(p.total_work, kNumSMs);
+#ifdef CREAM_TRACE
+  if (trace_env != nullptr) {
+    int rc;
+    switch (d->epi) {
+      case CREAM_EPI_BF16: rc = launch_gemm<CREAM_EPI_BF16>(*ta, *tb, *to, *tx, *toh, *txh, p, smem_bytes, grid, stream); break;
+      case CREAM_EPI_BF16_GELU: rc = launch_gemm<CREAM_EPI_BF16_GELU>(*ta, *tb, *to, *tx, *toh, *txh, p, smem_bytes, grid, stream); break;
+      case CREAM_EPI_F32_RESID: rc = launch_gemm<CREAM_EPI_F32_RESID>(*ta, *tb, *to, *tx, *toh, *txh, p, smem_bytes, grid, stream); break;
+      case CREAM_EPI_BF16_DGELU: rc = launch_gemm<CREAM_EPI_BF16_DGELU>(*ta, *tb, *to, *tx, *toh, *txh, p, smem_bytes, grid, stream); break;
+      default: rc = CREAM_ERR_ARG;
+    }
+    static int dumps = 0;
+    if (rc == CREAM_OK && dumps < 2) {
+      ++dumps;
+      std::vector<long long> h(3 * 1024);
+      CB_CUDA_OK(cudaStreamSynchronize(stream));
+      CB_CUDA_OK(cudaMemcpy(h.data(), trace_dev, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+      const long long t0 = h[2 * 1024];
+      fprintf(stderr, "TRACE epi %d M %d N %d K %d BN %d stages %d\n", d->epi, p.M, p.N, p.K, p.BN, p.num_stages);
+      for (int t = 0; t < 12; ++t)
+        fprintf(stderr, "  mma tile %2d: wait_empty %6lld..%6lld issued %6lld | epi tile: wait_full %6lld..%6lld\n", t,
+                h[2048 + t * 8] - t0, h[2048 + t * 8 + 1] - t0, h[2048 + t * 8 + 2] - t0, h[1024 + t * 8] - t0,
+                h[1024 + t * 8 + 1] - t0);
+      for (int j = 0; j < 40; ++j) {
+        const long long* e = &h[j * 8];
+        fprintf(stderr, "  job %2d: start %6lld tmem+bias %5lld acquire %5lld math+sts %5lld waitrd %5lld barrier %5lld issue %5lld\n",
+                j, e[0] - t0, e[1] - e[0], e[2] - e[1], e[3] - e[2], e[4] - e[3], e[5] - e[4], e[6] - e[5]);
+      }
+    }
+    return rc;
+  }
+#endif
   switch (d->epi) {
     case CREAM_EPI_BF16: return launch_gemm<CREAM_EPI_BF16>(*ta, *tb, *to, *tx, *toh, *txh, p, smem_bytes, grid, stream);
     case CREAM_EPI_BF16_GELU: return launch_gemm<CREAM_EPI_BF16_GELU>(*ta, *tb, *to, *tx, *toh, *txh, p, smem_bytes, grid, stream);

@@ -445,20 +445,21 @@ def test_supernet_fused_matches_module_path():
     assert rel_err(ye.float().cpu(), ya.float().detach().cpu()) < 1e-3, "eval forward == train forward (no dropout)"
 
 
-def test_supernet_s_random_configs_finite():
-    """BASELINE config 3 shapes: supernet-S, the engine's own sample_configs sequence
-    (random.seed(epoch), supernet_engine.py:13-24,36), bs 16: finite loss and grads, unsampled
-    slices exactly zero, identity layers without grad."""
+@pytest.mark.parametrize("size", ["S", "T", "B"])
+def test_supernet_s_random_configs_finite(size):
+    """BASELINE config 3 / 1 / 5 shapes: supernet-S (and T, B), the engine's own sample_configs
+    sequence (random.seed(epoch), supernet_engine.py:13-24,36), bs 16: finite loss and grads,
+    unsampled slices exactly zero, identity layers without grad."""
     import random
     from cream_b200 import ops
     ops.SHADOWS.clear()
-    spec = vo.SUPERNET_S
+    spec = {"S": vo.SUPERNET_S, "T": vo.SUPERNET_T, "B": vo.SUPERNET_B}[size]
     net = _build(spec, True)
     rnd = random.Random(0)
     images = torch.randn(16, 3, 224, 224, device="cuda")
     targets = torch.randint(0, 1000, (16,), device="cuda")
     for step in range(3):
-        cfg = vo.sample_configs(vo.SEARCH_SPACE["S"], rnd)
+        cfg = vo.sample_configs(vo.SEARCH_SPACE[size], rnd)
         net.zero_grad(set_to_none=True)
         net.set_sample_config(cfg)
         loss = F.cross_entropy(net(images).float(), targets)
