@@ -32,7 +32,7 @@ class GemmDesc(C.Structure):
         ("bias", c_void_p),
         ("resid", c_void_p), ("ldr", c_i64),
         ("row_scale", c_void_p), ("rows_per_scale", c_int),
-        ("alpha", c_float), ("split_k", c_int),
+        ("alpha", c_float), ("split_k", c_int), ("cta_pair", c_int),
     ]
 
 

@@ -44,7 +44,8 @@ struct GemmKernelParams {
   int b_group_rows;
   int num_stages;
   uint32_t stage_bytes, a_bytes, tx_bytes;
-  int nb64;
+  int nb64;          // 64-column chunks of this CTA's B stage (MN-major B)
+  int bn_cta;        // B rows (N) staged by one CTA: BN, or BN / 2 for a CTA pair
   int out_g_col;
   const float* bias;
   const float* row_scale;
@@ -120,9 +121,8 @@ __device__ __forceinline__ uint4 lds_u32x4(uint32_t a) {
 __device__ __forceinline__ void sts_u32x4(uint32_t a, uint4 v) {
   asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
-__device__ __forceinline__ float bf16_round(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
 
-template <int EPI>
+template <int EPI, bool kPair>
 __global__ void __launch_bounds__(kNumThreads, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                  const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_aux,
@@ -141,6 +141,13 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  // CTA pair: CTAs (2c, 2c+1) form cluster c and share one 256-row tile; the even CTA leads
+  // (issues the MMAs, owns the full / accumulator-empty barriers).
+  const uint32_t rank = kPair ? cluster_ctarank() : 0u;
+  const bool leader = rank == 0;
+  const int first_work = kPair ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+  const int work_stride = kPair ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
+  constexpr int kTileM = kPair ? 2 * kBM : kBM;
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmap_a);
@@ -154,55 +161,79 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tmem_full[a], 1);
-      mbar_init(&tmem_empty[a], kNumEpiWarps);
+      mbar_init(&tmem_empty[a], kNumEpiWarps * (kPair ? 2 : 1));
       mbar_init(&ld_bar[a], 1);
     }
     fence_mbar_init();
   }
-  if (warp == 2) tmem_alloc<kTmemCols>(tmem_slot);
+  if (warp == 2) {
+    if constexpr (kPair) tmem_alloc_pair<kTmemCols>(tmem_slot);
+    else tmem_alloc<kTmemCols>(tmem_slot);
+  }
   tc_fence_before();
-  __syncthreads();
+  if constexpr (kPair) cluster_sync_all();   // the peer's barriers exist before anything signals them
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0 && lane == 0) {
-    // ===================== TMA producer =====================
+    // ===================== TMA producer (both CTAs of a pair) =====================
     int stage = 0;
     uint32_t phase = 0;
-    for (int w = blockIdx.x; w < p.total_work; w += gridDim.x) {
+    for (int w = first_work; w < p.total_work; w += work_stride) {
       const WorkItem it = decode_work(p, w);
-      const int m0 = it.mt * kBM, n0 = it.nt * p.BN;
+      const int m0 = it.mt * kTileM + static_cast<int>(rank) * kBM;      // this CTA's 128 rows of A
+      const int n0 = it.nt * p.BN + static_cast<int>(rank) * p.bn_cta;    // this CTA's part of B
       for (int kb = it.kb0; kb < it.kb1; ++kb) {
         mbar_wait(&empty_bar[stage], phase ^ 1);
         uint8_t* sa = smem + stage * p.stage_bytes;
         uint8_t* sb = sa + p.a_bytes;
-        mbar_arrive_expect_tx(&full_bar[stage], p.tx_bytes);
-        if (!p.a_mn) {
-          tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * kBK, m0);
+        if constexpr (!kPair) {
+          mbar_arrive_expect_tx(&full_bar[stage], p.tx_bytes);
+          if (!p.a_mn) {
+            tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * kBK, m0);
+          } else {
+            const int c = it.g * p.a_group_off + m0;
+            tma_load_2d(sa, &tmap_a, &full_bar[stage], c, kb * kBK);
+            tma_load_2d(sa + 8192, &tmap_a, &full_bar[stage], c + 64, kb * kBK);
+          }
+          if (!p.b_mn) {
+            tma_load_3d(sb, &tmap_b, &full_bar[stage], kb * kBK, n0, it.g);
+          } else {
+            const int krow = (kb / p.kpg) * p.b_group_rows + (kb % p.kpg) * kBK;
+            for (int c = 0; c < p.nb64; ++c)
+              tma_load_2d(sb + c * 8192, &tmap_b, &full_bar[stage], n0 + c * 64, krow);
+          }
         } else {
-          const int c = it.g * p.a_group_off + m0;
-          tma_load_2d(sa, &tmap_a, &full_bar[stage], c, kb * kBK);
-          tma_load_2d(sa + 8192, &tmap_a, &full_bar[stage], c + 64, kb * kBK);
-        }
-        if (!p.b_mn) {
-          tma_load_3d(sb, &tmap_b, &full_bar[stage], kb * kBK, n0, it.g);
-        } else {
-          const int krow = (kb / p.kpg) * p.b_group_rows + (kb % p.kpg) * kBK;
-          for (int c = 0; c < p.nb64; ++c)
-            tma_load_2d(sb + c * 8192, &tmap_b, &full_bar[stage], n0 + c * 64, krow);
+          // all bytes of the pair are counted on the LEADER's barrier
+          const uint32_t fb = mapa_shared(smem_u32(&full_bar[stage]), 0);
+          if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * p.tx_bytes);
+          if (!p.a_mn) {
+            tma_load_2d_pair(sa, &tmap_a, fb, kb * kBK, m0);
+          } else {
+            const int c = it.g * p.a_group_off + m0;
+            tma_load_2d_pair(sa, &tmap_a, fb, c, kb * kBK);
+            tma_load_2d_pair(sa + 8192, &tmap_a, fb, c + 64, kb * kBK);
+          }
+          if (!p.b_mn) {
+            tma_load_3d_pair(sb, &tmap_b, fb, kb * kBK, n0, it.g);
+          } else {
+            const int krow = (kb / p.kpg) * p.b_group_rows + (kb % p.kpg) * kBK;
+            for (int c = 0; c < p.nb64; ++c) tma_load_2d_pair(sb + c * 8192, &tmap_b, fb, n0 + c * 64, krow);
+          }
         }
         if (++stage == p.num_stages) { stage = 0; phase ^= 1; }
       }
     }
-  } else if (warp == 1 && lane == 0) {
-    // ===================== MMA issuer =====================
-    const uint32_t idesc = umma_idesc_bf16(kBM, p.BN, p.a_mn, p.b_mn);
+  } else if (warp == 1 && lane == 0 && leader) {
+    // ===================== MMA issuer (leader CTA only) =====================
+    const uint32_t idesc = umma_idesc_bf16(kTileM, p.BN, p.a_mn, p.b_mn);
     int stage = 0;
     uint32_t phase = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
     [[maybe_unused]] int tile_no = 0;
-    for (int w = blockIdx.x; w < p.total_work; w += gridDim.x) {
+    for (int w = first_work; w < p.total_work; w += work_stride) {
       const WorkItem it = decode_work(p, w);
       CB_TRACE(2, tile_no, 0);
       mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
@@ -222,12 +253,16 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                                         : umma_smem_desc_sw128(sa + k * 32, 16, 1024);
           const uint64_t bdesc = p.b_mn ? umma_smem_desc_sw128(sb + k * 2048, 8192, 1024)
                                         : umma_smem_desc_sw128(sb + k * 32, 16, 1024);
-          umma_ss(d_tmem, adesc, bdesc, idesc, (kb > it.kb0 || k > 0) ? 1u : 0u);
+          if constexpr (kPair) umma_ss_pair(d_tmem, adesc, bdesc, idesc, (kb > it.kb0 || k > 0) ? 1u : 0u);
+          else umma_ss(d_tmem, adesc, bdesc, idesc, (kb > it.kb0 || k > 0) ? 1u : 0u);
         }
-        umma_commit(&empty_bar[stage]);
+        // frees this stage in both CTAs of a pair
+        if constexpr (kPair) umma_commit_pair(&empty_bar[stage]);
+        else umma_commit(&empty_bar[stage]);
         if (++stage == p.num_stages) { stage = 0; phase ^= 1; }
       }
-      umma_commit(&tmem_full[acc]);
+      if constexpr (kPair) umma_commit_pair(&tmem_full[acc]);
+      else umma_commit(&tmem_full[acc]);
       CB_TRACE(2, tile_no, 2);
       ++tile_no;
       acc ^= 1;
@@ -267,9 +302,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       const bool hb = is_half_block(it, cb);
       mbar_arrive_expect_tx(&ld_bar[s], hb ? kEpiSlotBytes / 2 : kEpiSlotBytes);
       tma_load_3d(epi_slots + s * kEpiSlotBytes, hb ? &tmap_aux_h : &tmap_aux, &ld_bar[s],
-                  it.nt * p.BN + cb * T::kCB, it.mt * kBM, it.g);
+                  it.nt * p.BN + cb * T::kCB, it.mt * kTileM + static_cast<int>(rank) * kBM, it.g);
     };
-    if (T::kLoads && issuer && static_cast<int>(blockIdx.x) < p.total_work) issue_load(blockIdx.x, 0, 0);
+    if (T::kLoads && issuer && first_work < p.total_work) issue_load(first_work, 0, 0);
 
     // bias of the column block about to be drained (this thread's kPerThread columns), kept in
     // registers and requested one block ahead so its latency never sits on the critical path
@@ -292,9 +327,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       }
     };
 
-    for (int w = blockIdx.x; w < p.total_work; w += gridDim.x) {
+    const uint32_t tmem_empty_leader[2] = {mapa_shared(smem_u32(&tmem_empty[0]), 0),
+                                           mapa_shared(smem_u32(&tmem_empty[1]), 0)};
+    for (int w = first_work; w < p.total_work; w += work_stride) {
       const WorkItem it = decode_work(p, w);
-      const int m0 = it.mt * kBM, n0 = it.nt * p.BN;
+      const int m0 = it.mt * kTileM + static_cast<int>(rank) * kBM, n0 = it.nt * p.BN;
       if constexpr (T::kBias) load_bias(n0 + half * T::kPerThread, it.g);   // overlaps the wait below
       if (issuer) CB_TRACE(1, tile_no, 0);
       mbar_wait(&tmem_full[acc], acc_phase);
@@ -342,7 +379,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           if (issuer) {
             bulk_wait_read<0>();                         // the other tile's store has drained
             int nw = w, ncb = cb + 1;
-            if (ncb >= nblocks) { nw = w + gridDim.x; ncb = 0; }
+            if (ncb >= nblocks) { nw = w + work_stride; ncb = 0; }
             if (nw < p.total_work) issue_load(nw, ncb, slot ^ 1);
           }
           mbar_wait(&ld_bar[slot], ld_phase[slot]);
@@ -446,7 +483,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       // all TMEM reads of this accumulator are done
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      if (lane == 0) {
+        if constexpr (kPair) mbar_arrive_cluster(tmem_empty_leader[acc]);   // the leader's MMA warp waits on it
+        else mbar_arrive(&tmem_empty[acc]);
+      }
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
@@ -454,25 +494,51 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   }
 
   tc_fence_before();
-  __syncthreads();
+  if constexpr (kPair) cluster_sync_all();   // no remote arrive / multicast commit may target an exited CTA
+  else __syncthreads();
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc<kTmemCols>(tmem_base);
+    if constexpr (kPair) tmem_dealloc_pair<kTmemCols>(tmem_base);
+    else tmem_dealloc<kTmemCols>(tmem_base);
   }
 }
 
-template <int EPI>
-int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const CUtensorMap& tx,
-                const CUtensorMap& toh, const CUtensorMap& txh, const GemmKernelParams& p, size_t smem_bytes,
-                int grid, cudaStream_t stream) {
+template <int EPI, bool kPair>
+int launch_gemm_impl(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const CUtensorMap& tx,
+                     const CUtensorMap& toh, const CUtensorMap& txh, const GemmKernelParams& p, size_t smem_bytes,
+                     int grid, cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
-    CB_CUDA_OK(cudaFuncSetAttribute(gemm_bf16_kernel<EPI>,
+    CB_CUDA_OK(cudaFuncSetAttribute(gemm_bf16_kernel<EPI, kPair>,
                                     cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
-  gemm_bf16_kernel<EPI><<<grid, kNumThreads, smem_bytes, stream>>>(ta, tb, to, tx, toh, txh, p);
+  if constexpr (!kPair) {
+    gemm_bf16_kernel<EPI, false><<<grid, kNumThreads, smem_bytes, stream>>>(ta, tb, to, tx, toh, txh, p);
+  } else {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(kNumThreads);
+    cfg.dynamicSmemBytes = smem_bytes;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    CB_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_bf16_kernel<EPI, true>, ta, tb, to, tx, toh, txh, p));
+  }
   return check_last("gemm_bf16_kernel launch");
+}
+
+template <int EPI>
+int launch_gemm(bool pair, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const CUtensorMap& tx,
+                const CUtensorMap& toh, const CUtensorMap& txh, const GemmKernelParams& p, size_t smem_bytes,
+                int grid, cudaStream_t stream) {
+  return pair ? launch_gemm_impl<EPI, true>(ta, tb, to, tx, toh, txh, p, smem_bytes, grid, stream)
+              : launch_gemm_impl<EPI, false>(ta, tb, to, tx, toh, txh, p, smem_bytes, grid, stream);
 }
 
 }  // namespace
@@ -510,7 +576,25 @@ extern "C" int cream_gemm_bf16(const cream_gemm_desc* d, void* stream_) {
   // tile width: a multiple of half a store block (32 bf16 / 16 fp32 columns)
   p.BN = std::min(256, round_up(ceil_div(d->N, nt), out_is_bf16 ? 32 : 16));
   p.num_nt = ceil_div(d->N, p.BN);
-  p.num_mt = ceil_div(d->M, kBM);
+  // CTA pair (cta_group::2, 256-row tiles): each CTA stages half of B, which cuts the pair's L2 ->
+  // shared-memory traffic by about a third; the mainloop of the path shapes is bound by exactly that.
+  // Used when a pair tile is full enough and the extra wave quantisation does not eat the gain.
+  bool pair = d->M >= 2 * kBM && p.BN >= 32 && (p.BN % 16) == 0;
+  if (pair) {
+    const int64_t t1 = static_cast<int64_t>(ceil_div(d->M, kBM)) * p.num_nt * d->groups;
+    const int64_t t2 = static_cast<int64_t>(ceil_div(d->M, 2 * kBM)) * p.num_nt * d->groups;
+    const int64_t waves1 = ceil_div64(t1, kNumSMs), waves2 = ceil_div64(t2, kNumSMs / 2);
+    if (d->epi != CREAM_EPI_F32_ATOMIC && waves2 * 4 > waves1 * 5) pair = false;   // > 25 % more waves
+  }
+  if (d->cta_pair == 1) pair = false;
+  if (d->cta_pair == 2) {
+    CB_REQUIRE(p.BN >= 32 && (p.BN % 16) == 0, "CTA pair needs a tile width that is a multiple of 16, >= 32");
+    pair = true;
+  }
+  const int tile_m = pair ? 2 * kBM : kBM;
+  const int sm_units = pair ? kNumSMs / 2 : kNumSMs;
+  p.num_mt = ceil_div(d->M, tile_m);
+  p.bn_cta = pair ? p.BN / 2 : p.BN;
   p.a_mn = d->a_mn ? 1 : 0;
   p.b_mn = d->b_mn ? 1 : 0;
   p.a_group_off = d->a_group_off;
@@ -527,16 +611,16 @@ extern "C" int cream_gemm_bf16(const cream_gemm_desc* d, void* stream_) {
   const int tiles = p.num_mt * p.num_nt * p.groups;
   int split = 1;
   if (d->epi == CREAM_EPI_F32_ATOMIC) {
-    split = d->split_k > 0 ? d->split_k : std::max(1, kNumSMs / tiles);
+    split = d->split_k > 0 ? d->split_k : std::max(1, sm_units / tiles);
     split = std::min(split, p.kb_total);
   }
   p.kb_per_split = ceil_div(p.kb_total, split);
   p.split_k = ceil_div(p.kb_total, p.kb_per_split);
   p.total_work = tiles * p.split_k;
-  p.nb64 = ceil_div(p.BN, 64);
+  p.nb64 = ceil_div(p.bn_cta, 64);
   p.a_bytes = kBM * kBK * 2;
   p.stage_bytes = p.a_bytes + p.nb64 * 8192;
-  p.tx_bytes = p.a_bytes + (p.b_mn ? p.nb64 * 8192 : p.BN * kBK * 2);
+  p.tx_bytes = p.a_bytes + (p.b_mn ? p.nb64 * 8192 : p.bn_cta * kBK * 2);
   const size_t tail_bytes = 1024;  // barriers + tmem slot
   const size_t epi_bytes = 2 * kEpiSlotBytes;
   p.num_stages = std::min<int>(kMaxStages, (227 * 1024 - epi_bytes - tail_bytes) / p.stage_bytes);
@@ -569,7 +653,7 @@ extern "C" int cream_gemm_bf16(const cream_gemm_desc* d, void* stream_) {
     const uint64_t gstride = p.groups > 1 ? static_cast<uint64_t>(d->b_group_rows) * d->ldb
                                           : static_cast<uint64_t>(d->N) * d->ldb;
     const uint64_t strides[3] = {1, static_cast<uint64_t>(d->ldb), gstride};
-    const uint32_t box[3] = {kBK, static_cast<uint32_t>(p.BN), 1};
+    const uint32_t box[3] = {kBK, static_cast<uint32_t>(p.bn_cta), 1};
     tb = get_tensor_map(d->b, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, dims, strides, box,
                         CU_TENSOR_MAP_SWIZZLE_128B);
   } else {
@@ -617,15 +701,15 @@ extern "C" int cream_gemm_bf16(const cream_gemm_desc* d, void* stream_) {
     p.trace = trace_dev;
   }
 #endif
-  const int grid = std::min(p.total_work, kNumSMs);
+  const int grid = pair ? 2 * std::min(p.total_work, kNumSMs / 2) : std::min(p.total_work, kNumSMs);
 #ifdef CREAM_TRACE
   if (trace_env != nullptr) {
     int rc;
     switch (d->epi) {
-      case CREAM_EPI_BF16: rc = launch_gemm<CREAM_EPI_BF16>(*ta, *tb, *to, *tx, *toh, *txh, p, smem_bytes, grid, stream); break;
-      case CREAM_EPI_BF16_GELU: rc = launch_gemm<CREAM_EPI_BF16_GELU>(*ta, *tb, *to, *tx, *toh, *txh, p, smem_bytes, grid, stream); break;
-      case CREAM_EPI_F32_RESID: rc = launch_gemm<CREAM_EPI_F32_RESID>(*ta, *tb, *to, *tx, *toh, *txh, p, smem_bytes, grid, stream); break;
-      case CREAM_EPI_BF16_DGELU: rc = launch_gemm<CREAM_EPI_BF16_DGELU>(*ta, *tb, *to, *tx, *toh, *txh, p, smem_bytes, grid, stream); break;
+      case CREAM_EPI_BF16: rc = launch_gemm<CREAM_EPI_BF16>(pair, *ta, *tb, *to, *tx, *toh, *txh, p, smem_bytes, grid, stream); break;
+      case CREAM_EPI_BF16_GELU: rc = launch_gemm<CREAM_EPI_BF16_GELU>(pair, *ta, *tb, *to, *tx, *toh, *txh, p, smem_bytes, grid, stream); break;
+      case CREAM_EPI_F32_RESID: rc = launch_gemm<CREAM_EPI_F32_RESID>(pair, *ta, *tb, *to, *tx, *toh, *txh, p, smem_bytes, grid, stream); break;
+      case CREAM_EPI_BF16_DGELU: rc = launch_gemm<CREAM_EPI_BF16_DGELU>(pair, *ta, *tb, *to, *tx, *toh, *txh, p, smem_bytes, grid, stream); break;
       default: rc = CREAM_ERR_ARG;
     }
     static int dumps = 0;
@@ -650,11 +734,11 @@ extern "C" int cream_gemm_bf16(const cream_gemm_desc* d, void* stream_) {
   }
 #endif
   switch (d->epi) {
-    case CREAM_EPI_BF16: return launch_gemm<CREAM_EPI_BF16>(*ta, *tb, *to, *tx, *toh, *txh, p, smem_bytes, grid, stream);
-    case CREAM_EPI_BF16_GELU: return launch_gemm<CREAM_EPI_BF16_GELU>(*ta, *tb, *to, *tx, *toh, *txh, p, smem_bytes, grid, stream);
-    case CREAM_EPI_F32_RESID: return launch_gemm<CREAM_EPI_F32_RESID>(*ta, *tb, *to, *tx, *toh, *txh, p, smem_bytes, grid, stream);
-    case CREAM_EPI_BF16_DGELU: return launch_gemm<CREAM_EPI_BF16_DGELU>(*ta, *tb, *to, *tx, *toh, *txh, p, smem_bytes, grid, stream);
-    case CREAM_EPI_F32_ATOMIC: return launch_gemm<CREAM_EPI_F32_ATOMIC>(*ta, *tb, *to, *tx, *toh, *txh, p, smem_bytes, grid, stream);
-    default: return launch_gemm<CREAM_EPI_F32>(*ta, *tb, *to, *tx, *toh, *txh, p, smem_bytes, grid, stream);
+    case CREAM_EPI_BF16: return launch_gemm<CREAM_EPI_BF16>(pair, *ta, *tb, *to, *tx, *toh, *txh, p, smem_bytes, grid, stream);
+    case CREAM_EPI_BF16_GELU: return launch_gemm<CREAM_EPI_BF16_GELU>(pair, *ta, *tb, *to, *tx, *toh, *txh, p, smem_bytes, grid, stream);
+    case CREAM_EPI_F32_RESID: return launch_gemm<CREAM_EPI_F32_RESID>(pair, *ta, *tb, *to, *tx, *toh, *txh, p, smem_bytes, grid, stream);
+    case CREAM_EPI_BF16_DGELU: return launch_gemm<CREAM_EPI_BF16_DGELU>(pair, *ta, *tb, *to, *tx, *toh, *txh, p, smem_bytes, grid, stream);
+    case CREAM_EPI_F32_ATOMIC: return launch_gemm<CREAM_EPI_F32_ATOMIC>(pair, *ta, *tb, *to, *tx, *toh, *txh, p, smem_bytes, grid, stream);
+    default: return launch_gemm<CREAM_EPI_F32>(pair, *ta, *tb, *to, *tx, *toh, *txh, p, smem_bytes, grid, stream);
   }
 }

@@ -128,6 +128,8 @@ typedef struct cream_gemm_desc {
   const float* row_scale; int rows_per_scale; /* DropPath per-sample scale, may be NULL */
   float alpha;
   int split_k;                 /* 0 = choose automatically (only for EPI_F32_ATOMIC)   */
+  int cta_pair;                /* 0 = choose automatically; 1 = one CTA per 128-row tile;
+                                * 2 = CTA pairs (tcgen05 cta_group::2) on 256-row tiles    */
 } cream_gemm_desc;
 
 int cream_gemm_bf16(const cream_gemm_desc* desc, void* stream);

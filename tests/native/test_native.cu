@@ -241,6 +241,7 @@ static int test_gemm(const GemmCase& c) {
   d.bias = (c.epi == CREAM_EPI_F32_ATOMIC || c.epi == CREAM_EPI_BF16_DGELU) ? nullptr : d_bias;
   d.resid = d_res; d.ldr = ldo; d.row_scale = d_rs; d.rows_per_scale = rows_per_scale;
   d.alpha = 1.0f; d.split_k = 0;
+  if (const char* e = getenv("CREAM_TEST_CTA_PAIR")) d.cta_pair = atoi(e);   // 1 = single CTA, 2 = CTA pairs
 
   int rc = cream_gemm_bf16(&d, nullptr);
   cudaError_t se = cudaDeviceSynchronize();
