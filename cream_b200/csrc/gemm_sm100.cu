@@ -579,12 +579,15 @@ extern "C" int cream_gemm_bf16(const cream_gemm_desc* d, void* stream_) {
   // CTA pair (cta_group::2, 256-row tiles): each CTA stages half of B, which cuts the pair's L2 ->
   // shared-memory traffic by about a third; the mainloop of the path shapes is bound by exactly that.
   // Used when a pair tile is full enough and the extra wave quantisation does not eat the gain.
-  bool pair = d->M >= 2 * kBM && p.BN >= 32 && (p.BN % 16) == 0;
-  if (pair) {
+  // Measured on the supernet-S shapes (profiles/): +5..10 % where the mainloop dominates (K >= 768:
+  // fc2 forward, fc1 / qkv dgrad, every wgrad; 8192^3 reaches 1397 TFLOP/s), a loss where the
+  // epilogue dominates (GELU / dGELU, short K) or where 256-row tiles add a wave.
+  bool pair = d->M >= 2 * kBM && p.BN >= 32 && (p.BN % 16) == 0 && d->K >= 768 &&
+              d->epi != CREAM_EPI_BF16_GELU && d->epi != CREAM_EPI_BF16_DGELU;
+  if (pair && d->epi != CREAM_EPI_F32_ATOMIC) {
     const int64_t t1 = static_cast<int64_t>(ceil_div(d->M, kBM)) * p.num_nt * d->groups;
     const int64_t t2 = static_cast<int64_t>(ceil_div(d->M, 2 * kBM)) * p.num_nt * d->groups;
-    const int64_t waves1 = ceil_div64(t1, kNumSMs), waves2 = ceil_div64(t2, kNumSMs / 2);
-    if (d->epi != CREAM_EPI_F32_ATOMIC && waves2 * 4 > waves1 * 5) pair = false;   // > 25 % more waves
+    if (ceil_div64(t2, kNumSMs / 2) > ceil_div64(t1, kNumSMs)) pair = false;   // an extra wave
   }
   if (d->cta_pair == 1) pair = false;
   if (d->cta_pair == 2) {
