@@ -506,7 +506,10 @@ attn_bwd_rows_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
 // -------------------------------------------------------------------------------------------
 constexpr int kColsThreads = 192;
 constexpr int kColStages = 2;
-constexpr int kColStageBytes = 2 * 6 * 8192 + 2 * 8192;  // 6 A boxes per workspace + dO + Q = 112 KB
+constexpr int kColBoxes = 5;       // 64-column boxes staged per workspace: covers Npad + 64 <= 320 columns
+constexpr int kColStageBytes = (2 * kColBoxes + 2) * 8192;  // 5 + 5 A boxes + dO + Q = 96 KB
+constexpr int kRedRowBytes = 272;  // one table-gradient row (64 fp32) + 16 B pad: conflict-free private rows
+constexpr int kRedBytes = 2 * kNB * kRedRowBytes;            // [dTV | dTK] rows staged for the bulk reduce
 
 struct BwdColsParams {
   int B, H, N, Npad, ldw;
@@ -522,7 +525,8 @@ attn_bwd_cols_kernel(const __grid_constant__ CUtensorMap map_wp, const __grid_co
                      const BwdColsParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   require_smem_alignment(smem);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kColStages * kColStageBytes);
+  uint8_t* red_rows = smem + kColStages * kColStageBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(red_rows + kRedBytes);
   uint64_t* full = bars;
   uint64_t* empty = bars + kColStages;
   uint64_t* done = bars + 2 * kColStages;
@@ -531,7 +535,7 @@ attn_bwd_cols_kernel(const __grid_constant__ CUtensorMap map_wp, const __grid_co
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nkb = ceil_div(p.N, 64);
   const int mtiles = ceil_div(p.Npad + kNB, 128);  // <= 3
-  const int nboxes = 2 * mtiles;                    // 64-column boxes actually consumed per workspace
+  const int nboxes = min(2 * mtiles, kColBoxes);    // 64-column boxes actually consumed per workspace
   const int items = p.B * p.H;                      // persistent: item = (batch, head)
   uint64_t* acc_free = done + 1;                    // epilogue -> MMA: TMEM accumulators drained
 
@@ -561,10 +565,10 @@ attn_bwd_cols_kernel(const __grid_constant__ CUtensorMap map_wp, const __grid_co
         mbar_arrive_expect_tx(&full[s], (2 * nboxes + 2) * 8192);
         for (int c = 0; c < nboxes; ++c) {
           tma_load_3d(st + c * 8192, &map_wp, &full[s], c * 64, kb * 64, w);
-          tma_load_3d(st + (6 + c) * 8192, &map_wd, &full[s], c * 64, kb * 64, w);
+          tma_load_3d(st + (kColBoxes + c) * 8192, &map_wd, &full[s], c * 64, kb * 64, w);
         }
-        tma_load_3d(st + 12 * 8192, &map_do, &full[s], head * kD, kb * 64, b);
-        tma_load_3d(st + 13 * 8192, &map_q, &full[s], head * kD, kb * 64, b);
+        tma_load_3d(st + (2 * kColBoxes) * 8192, &map_do, &full[s], head * kD, kb * 64, b);
+        tma_load_3d(st + (2 * kColBoxes + 1) * 8192, &map_q, &full[s], head * kD, kb * 64, b);
       }
     }
   } else if (warp == 1 && lane == 0) {
@@ -582,11 +586,13 @@ attn_bwd_cols_kernel(const __grid_constant__ CUtensorMap map_wp, const __grid_co
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
             const uint32_t acc = (kb > 0 || k > 0) ? 1u : 0u;
-            // A: two 64-wide MN chunks (LBO = 8192) of 64 K-rows; B: one chunk.
+            // A: two 64-wide MN chunks (LBO = 8192) of 64 K-rows; B: one chunk.  The last M tile
+            // covers only 16 valid columns; its second chunk is whatever follows in the stage
+            // (finite bf16 data) and lands in accumulator lanes nobody reads.
             umma_ss(tmem + mt * 64, umma_smem_desc_sw128(st + (2 * mt) * 8192 + k * 2048, 8192, 1024),
-                    umma_smem_desc_sw128(st + 12 * 8192 + k * 2048, 8192, 1024), idesc, acc);
-            umma_ss(tmem + 192 + mt * 64, umma_smem_desc_sw128(st + (6 + 2 * mt) * 8192 + k * 2048, 8192, 1024),
-                    umma_smem_desc_sw128(st + 13 * 8192 + k * 2048, 8192, 1024), idesc, acc);
+                    umma_smem_desc_sw128(st + (2 * kColBoxes) * 8192 + k * 2048, 8192, 1024), idesc, acc);
+            umma_ss(tmem + 192 + mt * 64, umma_smem_desc_sw128(st + (kColBoxes + 2 * mt) * 8192 + k * 2048, 8192, 1024),
+                    umma_smem_desc_sw128(st + (2 * kColBoxes + 1) * 8192 + k * 2048, 8192, 1024), idesc, acc);
           }
         }
         umma_commit(&empty[s]);
@@ -625,9 +631,21 @@ attn_bwd_cols_kernel(const __grid_constant__ CUtensorMap map_wp, const __grid_co
                 o4[q] = u;
               }
             } else if (m >= p.Npad && m < p.Npad + kNB && dtab != nullptr) {
-              float* dst = dtab + (static_cast<int64_t>(tab) * kNB + (m - p.Npad)) * kD + c * 32;
+              // table-gradient row (one bucket): staged in this thread's private shared row and
+              // added to global memory by ONE 256-byte bulk reduce (the L2 does the fp32 adds on
+              // whole lines) instead of 64 scattered per-element atomics
+              const uint32_t srow = smem_u32(red_rows) + (which * kNB + (m - p.Npad)) * kRedRowBytes;
+              if (c == 0) bulk_wait_read<0>();           // the previous item's reduce has left the row
 #pragma unroll
-              for (int i = 0; i < 32; ++i) atomicAdd(dst + i, mul * __uint_as_float(raw[i]));
+              for (int q = 0; q < 8; ++q)
+                sts_f32x4(srow + c * 128 + q * 16,
+                          make_float4(mul * __uint_as_float(raw[4 * q + 0]), mul * __uint_as_float(raw[4 * q + 1]),
+                                      mul * __uint_as_float(raw[4 * q + 2]), mul * __uint_as_float(raw[4 * q + 3])));
+              if (c == 1) {
+                fence_proxy_async_smem();
+                bulk_reduce_add_f32(dtab + (static_cast<int64_t>(tab) * kNB + (m - p.Npad)) * kD, srow, kD * 4);
+                bulk_commit();
+              }
             }
           }
         }
@@ -636,6 +654,7 @@ attn_bwd_cols_kernel(const __grid_constant__ CUtensorMap map_wp, const __grid_co
       __syncwarp();
       if (lane == 0) mbar_arrive(acc_free);
     }
+    bulk_wait_all();   // this thread's table-gradient reduces have completed
   }
   tc_fence_before();
   __syncthreads();
@@ -735,7 +754,7 @@ extern "C" int cream_attn_bwd(const cream_attn_desc* d, void* stream_) {
   c.dqkv = static_cast<__nv_bfloat16*>(d->dqkv); c.lddqkv = d->ld_dqkv;
   c.dtk = ctx_k ? d->dtk_pack : nullptr;
   c.dtv = ctx_v ? d->dtv_pack : nullptr;
-  const size_t smem_cols = kColStages * kColStageBytes + 256;
+  const size_t smem_cols = kColStages * kColStageBytes + kRedBytes + 256;
   const int grid2 = std::min(d->B * d->H, kNumSMs);
   attn_bwd_cols_kernel<<<grid2, kColsThreads, smem_cols, stream>>>(*mwp, *mwd, *mdo64, *mq64, c);
   return check_last("attn_bwd_cols_kernel");

@@ -95,12 +95,6 @@ __device__ __forceinline__ void tma_reduce_add_3d(const CUtensorMap* m, const vo
                "r"(smem_u32(smem)), "r"(c0), "r"(c1), "r"(c2)
                : "memory");
 }
-__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void bulk_wait_read() {
-  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
-}
-__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void epi_barrier() {
   asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
 }

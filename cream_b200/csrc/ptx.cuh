@@ -119,6 +119,20 @@ __device__ __forceinline__ void tma_load_4d(void* smem, const CUtensorMap* m, ui
       : "memory");
 }
 
+// bulk async-group completion (TMA stores / reduces issued by one thread)
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+// global[dst .. dst+bytes) += shared[src ..): contiguous fp32, 16-byte aligned, bytes % 16 == 0
+__device__ __forceinline__ void bulk_reduce_add_f32(float* dst, uint32_t smem_src, uint32_t bytes) {
+  asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;" ::"l"(dst),
+               "r"(smem_src), "r"(bytes)
+               : "memory");
+}
+
 // ----------------------------------------------------------------------------
 // tcgen05 / TMEM
 // ----------------------------------------------------------------------------
