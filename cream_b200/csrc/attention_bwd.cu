@@ -505,9 +505,9 @@ attn_bwd_rows_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
 // warp 0: TMA, warp 1: MMA, warps 2..5: epilogue.
 // -------------------------------------------------------------------------------------------
 constexpr int kColsThreads = 192;
-constexpr int kColStages = 2;
+constexpr int kColStages = 4;
 constexpr int kColBoxes = 5;       // 64-column boxes staged per workspace: covers Npad + 64 <= 320 columns
-constexpr int kColStageBytes = (2 * kColBoxes + 2) * 8192;  // 5 + 5 A boxes + dO + Q = 96 KB
+constexpr int kColStageBytes = (kColBoxes + 1) * 8192;      // one product, 64 query rows: 5 A boxes + dO (or Q) = 48 KB
 constexpr int kRedRowBytes = 272;  // one table-gradient row (64 fp32) + 16 B pad: conflict-free private rows
 constexpr int kRedBytes = 2 * kNB * kRedRowBytes;            // [dTV | dTK] rows staged for the bulk reduce
 
@@ -529,22 +529,24 @@ attn_bwd_cols_kernel(const __grid_constant__ CUtensorMap map_wp, const __grid_co
   uint64_t* bars = reinterpret_cast<uint64_t*>(red_rows + kRedBytes);
   uint64_t* full = bars;
   uint64_t* empty = bars + kColStages;
-  uint64_t* done = bars + 2 * kColStages;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+  uint64_t* done = bars + 2 * kColStages;           // [2] MMA -> epilogue, one per product
+  uint64_t* acc_free = done + 2;                    // [2] epilogue -> MMA: that product's accumulators drained
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_free + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nkb = ceil_div(p.N, 64);
   const int mtiles = ceil_div(p.Npad + kNB, 128);  // <= 3
   const int nboxes = min(2 * mtiles, kColBoxes);    // 64-column boxes actually consumed per workspace
   const int items = p.B * p.H;                      // persistent: item = (batch, head)
-  uint64_t* acc_free = done + 1;                    // epilogue -> MMA: TMEM accumulators drained
 
+  // The two products of an item run back to back through ONE stage ring (product 0: [P|PB]^T dO,
+  // product 1: [dT|dR]^T Q), each into its own 192 accumulator columns, so the epilogue of one
+  // product drains while the tensor core works on the other.
   if (threadIdx.x == 0) {
     prefetch_tmap(&map_wp);
     prefetch_tmap(&map_wd);
     for (int s = 0; s < kColStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    mbar_init(done, 1);
-    mbar_init(acc_free, 4);
+    for (int q = 0; q < 2; ++q) { mbar_init(&done[q], 1); mbar_init(&acc_free[q], 4); }
     fence_mbar_init();
   }
   if (warp == 2) tmem_alloc<512>(tmem_slot);
@@ -554,50 +556,50 @@ attn_bwd_cols_kernel(const __grid_constant__ CUtensorMap map_wp, const __grid_co
   const uint32_t tmem = *tmem_slot;
 
   if (warp == 0 && lane == 0) {
-    // loads run ahead across items: the next item streams in while this one is drained
+    // loads run ahead across products and items
     int it = 0;
     for (int w = blockIdx.x; w < items; w += gridDim.x) {
       const int b = w / p.H, head = w - b * p.H;
-      for (int kb = 0; kb < nkb; ++kb, ++it) {
-        const int s = it % kColStages;
-        mbar_wait(&empty[s], ((it / kColStages) & 1) ^ 1);
-        uint8_t* st = smem + s * kColStageBytes;
-        mbar_arrive_expect_tx(&full[s], (2 * nboxes + 2) * 8192);
-        for (int c = 0; c < nboxes; ++c) {
-          tma_load_3d(st + c * 8192, &map_wp, &full[s], c * 64, kb * 64, w);
-          tma_load_3d(st + (kColBoxes + c) * 8192, &map_wd, &full[s], c * 64, kb * 64, w);
+      for (int prod = 0; prod < 2; ++prod) {
+        const CUtensorMap* ma = prod ? &map_wd : &map_wp;
+        const CUtensorMap* mb = prod ? &map_q : &map_do;
+        for (int kb = 0; kb < nkb; ++kb, ++it) {
+          const int s = it % kColStages;
+          mbar_wait(&empty[s], ((it / kColStages) & 1) ^ 1);
+          uint8_t* st = smem + s * kColStageBytes;
+          mbar_arrive_expect_tx(&full[s], (nboxes + 1) * 8192);
+          for (int c = 0; c < nboxes; ++c) tma_load_3d(st + c * 8192, ma, &full[s], c * 64, kb * 64, w);
+          tma_load_3d(st + kColBoxes * 8192, mb, &full[s], head * kD, kb * 64, b);
         }
-        tma_load_3d(st + (2 * kColBoxes) * 8192, &map_do, &full[s], head * kD, kb * 64, b);
-        tma_load_3d(st + (2 * kColBoxes + 1) * 8192, &map_q, &full[s], head * kD, kb * 64, b);
       }
     }
   } else if (warp == 1 && lane == 0) {
     const uint32_t idesc = umma_idesc_bf16(128, kD, 1, 1);
     int it = 0, n = 0;
     for (int w = blockIdx.x; w < items; w += gridDim.x, ++n) {
-      mbar_wait(acc_free, (n & 1) ^ 1);             // previous item's accumulators have been read
-      tc_fence_after();
-      for (int kb = 0; kb < nkb; ++kb, ++it) {
-        const int s = it % kColStages;
-        mbar_wait(&full[s], (it / kColStages) & 1);
+      for (int prod = 0; prod < 2; ++prod) {
+        mbar_wait(&acc_free[prod], (n & 1) ^ 1);     // the previous item's accumulators of this product were read
         tc_fence_after();
-        const uint32_t st = smem_u32(smem + s * kColStageBytes);
-        for (int mt = 0; mt < mtiles; ++mt) {
+        for (int kb = 0; kb < nkb; ++kb, ++it) {
+          const int s = it % kColStages;
+          mbar_wait(&full[s], (it / kColStages) & 1);
+          tc_fence_after();
+          const uint32_t st = smem_u32(smem + s * kColStageBytes);
+          for (int mt = 0; mt < mtiles; ++mt) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const uint32_t acc = (kb > 0 || k > 0) ? 1u : 0u;
-            // A: two 64-wide MN chunks (LBO = 8192) of 64 K-rows; B: one chunk.  The last M tile
-            // covers only 16 valid columns; its second chunk is whatever follows in the stage
-            // (finite bf16 data) and lands in accumulator lanes nobody reads.
-            umma_ss(tmem + mt * 64, umma_smem_desc_sw128(st + (2 * mt) * 8192 + k * 2048, 8192, 1024),
-                    umma_smem_desc_sw128(st + (2 * kColBoxes) * 8192 + k * 2048, 8192, 1024), idesc, acc);
-            umma_ss(tmem + 192 + mt * 64, umma_smem_desc_sw128(st + (kColBoxes + 2 * mt) * 8192 + k * 2048, 8192, 1024),
-                    umma_smem_desc_sw128(st + (2 * kColBoxes + 1) * 8192 + k * 2048, 8192, 1024), idesc, acc);
+            for (int k = 0; k < 4; ++k) {
+              // A: two 64-wide MN chunks (LBO = 8192) of 64 K-rows; B: one chunk.  The last M tile
+              // covers only 16 valid columns; its second chunk is whatever follows in the stage
+              // (finite bf16 data) and lands in accumulator lanes nobody reads.
+              umma_ss(tmem + prod * 192 + mt * 64, umma_smem_desc_sw128(st + (2 * mt) * 8192 + k * 2048, 8192, 1024),
+                      umma_smem_desc_sw128(st + kColBoxes * 8192 + k * 2048, 8192, 1024), idesc,
+                      (kb > 0 || k > 0) ? 1u : 0u);
+            }
           }
+          umma_commit(&empty[s]);
         }
-        umma_commit(&empty[s]);
+        umma_commit(&done[prod]);
       }
-      umma_commit(done);
     }
   } else if (warp >= 2) {
     const int quarter = warp & 3;
@@ -605,10 +607,10 @@ attn_bwd_cols_kernel(const __grid_constant__ CUtensorMap map_wp, const __grid_co
     int n = 0;
     for (int w = blockIdx.x; w < items; w += gridDim.x, ++n) {
       const int b = w / p.H, head = w - b * p.H;
-      mbar_wait(done, n & 1);
-      tc_fence_after();
       const int tab = p.shared_tables ? 0 : head;
       for (int which = 0; which < 2; ++which) {          // 0: dV / dTV   1: dK / dTK
+        mbar_wait(&done[which], n & 1);
+        tc_fence_after();
         const float mul = which ? p.scale : 1.0f;
         float* dtab = which ? p.dtk : p.dtv;
         const int col0 = ((which ? 1 : 2) * p.H + head) * kD;
@@ -649,10 +651,10 @@ attn_bwd_cols_kernel(const __grid_constant__ CUtensorMap map_wp, const __grid_co
             }
           }
         }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&acc_free[which]);
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(acc_free);
     }
     bulk_wait_all();   // this thread's table-gradient reduces have completed
   }
