@@ -1,3 +1,4 @@
+#include <cstdlib>
 // Fused attention backward with relative-position terms, sm_100a (tcgen05 + TMEM + TMA).
 //
 // Adjoint of attention_fwd.cu (autograd of AutoFormer/model/module/multihead_super.py:135-154
@@ -42,7 +43,14 @@ struct BwdRowsParams {
   __nv_bfloat16* dqkv; int64_t lddqkv;
   __nv_bfloat16* ws_p; __nv_bfloat16* ws_dt;  // (B*H*N, ldw)
   float* dbias;
+  long long* trace;   // CREAM_TRACE builds only
 };
+
+#ifdef CREAM_TRACE
+#define ROWS_TRACE(slot) do { if (p.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) p.trace[slot] = clock64(); } while (0)
+#else
+#define ROWS_TRACE(slot) do {} while (0)
+#endif
 
 __device__ __forceinline__ void rows_barrier() { asm volatile("bar.sync 2, %0;" ::"n"(kRowThreads) : "memory"); }
 
@@ -130,70 +138,97 @@ __device__ __forceinline__ void bwd_row_generic(const BwdRowsParams& p, const Ro
   rows_barrier();
 }
 
-// AutoFormer-structured twin (see softmax_af in attention_fwd.cu): the four gather operand
-// vectors and the four bucket-sum vectors of a row are registers; afterwards the bucket sums
-// are scattered ONCE into the shared rows the common tail reads.
+// AutoFormer-structured twin (see softmax_af in attention_fwd.cu): the gather operand vectors and
+// the bucket-sum vectors of a row are registers; afterwards the bucket sums are scattered ONCE
+// into the shared rows the common tail reads.
+//
+// The two threads of a row split the keys 112 / 96: 112 = 8 grid rows, so key j0 + 112 has the
+// same grid column as key j0 and a grid row 8 higher.  Both halves therefore run the SAME fully
+// unrolled code on "local" grid rows 0..7 with their own operand registers (the kernel is
+// instruction-fetch bound: one shared stream halves its footprint).  The only asymmetric element
+// is local key 0: the cls key for half 0, grid position (7, 13) for half 1.
+constexpr int kAfSplitCols = 112;                 // keys owned by the first thread of a row
+constexpr int kAfSplitRows = 8;                   // = kAfSplitCols / 14 grid rows
+constexpr int kDtHiCol = 464;                     // TMEM columns [464, 512): packed dT of the second half
+
 template <int G>
 __device__ __forceinline__ void bwd_row_af(const BwdRowsParams& p, const RowCtx& x) {
+  static_assert(G == 14 && kAfSplitCols == kAfSplitRows * G, "split is tied to the 14 x 14 grid");
   constexpr int N = G * G + 1;
-  constexpr int NPAD = (N + 15) / 16 * 16;
-  constexpr int NCH = NPAD / 16;
+  constexpr int LR = kAfSplitRows;                // local grid rows per half
+  constexpr int NCC = kAfSplitCols / 16;          // 7 chunks for half 0, 6 for half 1
   const int M1 = p.af_max_rel + 1;
   const bool patch = x.row >= 1 && x.row < N;
+  const bool live = x.row < N;
+  const int hi = x.half;                           // 0 / 1
   const int qi = patch ? x.row - 1 : 0;
   const int ri = qi / G, ci = qi - ri * G;
-  const float r0v = lds_f32(x.s_r), r0h = lds_f32(x.s_r + 4 * 32);
-  const float g0v = lds_f32(x.s_dpb), g0h = lds_f32(x.s_dpb + 4 * 32);
-  float rv[G], rh[G], gv[G], gh[G];
-#pragma unroll
-  for (int t = 0; t < G; ++t) {
-    rv[t] = patch ? lds_f32(x.s_r + 4 * (M1 - ri + t)) : r0v;
-    rh[t] = patch ? lds_f32(x.s_r + 4 * (32 + M1 - ci + t)) : r0h;
-    gv[t] = patch ? lds_f32(x.s_dpb + 4 * (M1 - ri + t)) : g0v;
-    gh[t] = patch ? lds_f32(x.s_dpb + 4 * (32 + M1 - ci + t)) : g0h;
-  }
-  float prow[G], pcol[G], drow[G], dcol[G], p0 = 0.f, d0 = 0.f;
-#pragma unroll
-  for (int t = 0; t < G; ++t) { prow[t] = 0.f; pcol[t] = 0.f; drow[t] = 0.f; dcol[t] = 0.f; }
-  const bool live = x.row < N;
+  const int vb = M1 - ri + LR * hi;               // bucket of local grid row 0
   // Fold the per-row constants into the gather operands so one element costs
-  //   e = T * (scale log2e) + rv2[rj] + rh2[cj] ; p = 2^e ; dT = p * (dP + gv2[rj] + gh[cj]).
-  // A padding row gets lse = +huge, i.e. p = 0 everywhere, without a per-element select.
+  //   e = T * (scale log2e) + rv[rj] + rh[cj] ; p = 2^e ; dT = p * (dP + gv[rj] + gh[cj]).
+  // A padding row gets lse = +huge, i.e. p = 0 everywhere, without a per-element select; the local
+  // grid rows of half 1 that do not exist (>= 6) get the same treatment.
   const float sl = p.scale * kLog2e;
   const float lsel = live ? x.lsel : 1e30f;
-  const float e0 = fmaf(r0v + r0h, kLog2e, -lsel), g0 = g0v + g0h - x.delta;
+  const float r0v = lds_f32(x.s_r), r0h = lds_f32(x.s_r + 4 * 32);
+  const float g0v = lds_f32(x.s_dpb), g0h = lds_f32(x.s_dpb + 4 * 32);
+  float rv[LR], gv[LR], rh[G], gh[G];
+#pragma unroll
+  for (int t = 0; t < LR; ++t) {
+    const bool exists = hi == 0 || t < G - LR;
+    const float r = patch ? lds_f32(x.s_r + 4 * (exists ? vb + t : 0)) : r0v;
+    const float g = patch ? lds_f32(x.s_dpb + 4 * (exists ? vb + t : 0)) : g0v;
+    rv[t] = exists ? fmaf(r, kLog2e, -lsel) : -1e30f;
+    gv[t] = exists ? g - x.delta : 0.f;
+  }
 #pragma unroll
   for (int t = 0; t < G; ++t) {
-    rv[t] = fmaf(rv[t], kLog2e, -lsel);
-    rh[t] *= kLog2e;
-    gv[t] -= x.delta;
+    rh[t] = (patch ? lds_f32(x.s_r + 4 * (32 + M1 - ci + t)) : r0h) * kLog2e;
+    gh[t] = patch ? lds_f32(x.s_dpb + 4 * (32 + M1 - ci + t)) : g0h;
   }
-  constexpr int kSplit = (NCH + 1) / 2;   // half 0: chunks [0, kSplit), half 1: [kSplit, NCH)
-  // The packed dT of chunk c overwrites T columns [8c, 8c+8).  For the second half those columns
-  // belong to chunks its PARTNER may not have read yet, so it keeps its packed dT in registers and
-  // stores them after the pair barrier below.
-  uint32_t keep[NCH - kSplit][8];
+  // local key 0: the cls key (bucket 0 of both tables) or grid position (7, 13)
+  float e_first, g_first;
+  if (hi == 0) {
+    e_first = fmaf(r0v + r0h, kLog2e, -lsel);
+    g_first = g0v + g0h - x.delta;
+  } else {
+    const float r7 = patch ? lds_f32(x.s_r + 4 * (M1 - ri + LR - 1)) : r0v;
+    const float g7 = patch ? lds_f32(x.s_dpb + 4 * (M1 - ri + LR - 1)) : g0v;
+    e_first = fmaf(r7, kLog2e, -lsel) + rh[G - 1];
+    g_first = g7 - x.delta + gh[G - 1];
+  }
+  float prow[LR], drow[LR], pcol[G], dcol[G], pf = 0.f, df = 0.f;
 #pragma unroll
-  for (int c = 0; c < NCH; ++c) {
-    if ((c < kSplit) != (x.half == 0)) continue;
+  for (int t = 0; t < LR; ++t) { prow[t] = 0.f; drow[t] = 0.f; }
+#pragma unroll
+  for (int t = 0; t < G; ++t) { pcol[t] = 0.f; dcol[t] = 0.f; }
+
+  const uint32_t t_in = x.trow + kAfSplitCols * hi;               // this half's T columns
+  const uint32_t t_out = hi ? x.trow + kDtHiCol : x.trow;        // packed dT: in place, or the spare columns
+  const int64_t w0 = x.wrow + kAfSplitCols * hi;
+#pragma unroll
+  for (int cc = 0; cc < NCC; ++cc) {
+    if (cc == NCC - 1 && hi) break;                                // half 1 owns 6 chunks (keys 112..207)
     uint32_t rt[16], rp[16];
-    tmem_ld16(x.trow + c * 16, rt);
-    tmem_ld16(x.trow + 256 + c * 16, rp);
+    tmem_ld16(t_in + cc * 16, rt);
+    tmem_ld16(t_in + 256 + cc * 16, rp);
     tmem_ld_wait();
     float pv[16], dt[16];
 #pragma unroll
     for (int k = 0; k < 16; ++k) {
-      const int j = c * 16 + k;
-      float pr = 0.f, d = 0.f;
-      if (j == 0) {
-        pr = fast_exp2(fmaf(sl, __uint_as_float(rt[k]), e0));
-        d = pr * (__uint_as_float(rp[k]) + g0);
-        p0 = pr; d0 = d;
-      } else if (j < N) {
-        pr = fast_exp2(fmaf(sl, __uint_as_float(rt[k]), rv[(j - 1) / G]) + rh[(j - 1) % G]);
-        d = pr * (__uint_as_float(rp[k]) + gv[(j - 1) / G] + gh[(j - 1) % G]);
-        prow[(j - 1) / G] += pr; pcol[(j - 1) % G] += pr;
-        drow[(j - 1) / G] += d;  dcol[(j - 1) % G] += d;
+      const int j0 = cc * 16 + k;                                  // local key
+      float pr, d;
+      if (j0 == 0) {
+        pr = fast_exp2(fmaf(sl, __uint_as_float(rt[k]), e_first));
+        d = pr * (__uint_as_float(rp[k]) + g_first);
+        pf = pr; df = d;
+      } else {
+        constexpr int kDummy = 0; (void)kDummy;
+        const int rj = (j0 - 1) / G, cj = (j0 - 1) % G;
+        pr = fast_exp2(fmaf(sl, __uint_as_float(rt[k]), rv[rj]) + rh[cj]);
+        d = pr * (__uint_as_float(rp[k]) + gv[rj] + gh[cj]);
+        prow[rj] += pr; pcol[cj] += pr;
+        drow[rj] += d;  dcol[cj] += d;
       }
       pv[k] = pr;
       dt[k] = d;
@@ -204,68 +239,58 @@ __device__ __forceinline__ void bwd_row_af(const BwdRowsParams& p, const RowCtx&
       pk[k] = pack_bf16x2(pv[2 * k], pv[2 * k + 1]);
       dk[k] = pack_bf16x2(dt[2 * k], dt[2 * k + 1]);
     }
-    if (c < kSplit) {
-      tmem_st8(x.trow + c * 8, dk);
-    } else {
-#pragma unroll
-      for (int k = 0; k < 8; ++k) keep[c >= kSplit ? c - kSplit : 0][k] = dk[k];
-    }
+    tmem_st8(t_out + cc * 8, dk);     // half 0: over T columns it has already read; half 1: spare columns
     if (live) {
-      uint4* wp = reinterpret_cast<uint4*>(p.ws_p + x.wrow + c * 16);
-      uint4* wd = reinterpret_cast<uint4*>(p.ws_dt + x.wrow + c * 16);
+      uint4* wp = reinterpret_cast<uint4*>(p.ws_p + w0 + cc * 16);
+      uint4* wd = reinterpret_cast<uint4*>(p.ws_dt + w0 + cc * 16);
       wp[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
       wp[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
       wd[0] = make_uint4(dk[0], dk[1], dk[2], dk[3]);
       wd[1] = make_uint4(dk[4], dk[5], dk[6], dk[7]);
     }
   }
-  float psum = p0, dsum = d0;   // this thread's share of the row totals (every key hits one prow bucket)
+  // this thread's share of the row totals (every key hits exactly one vertical bucket)
+  float psum = pf, dsum = df;
 #pragma unroll
-  for (int t = 0; t < G; ++t) { psum += prow[t]; dsum += drow[t]; }
+  for (int t = 0; t < LR; ++t) { psum += prow[t]; dsum += drow[t]; }
+
   // scatter the register bucket sums into the shared rows read by the common tail: the thread
-  // owning the first column half initialises the row, its partner adds its partial sums.
-  if (x.half == 0) {
+  // owning the first half initialises the row, its partner adds its partial sums after the barrier.
+  auto put = [&](uint32_t a, float v) { if (hi) v += lds_f32(a); sts_f32(a, v); };
+  if (hi == 0)
     for (int k = 0; k < kNB; ++k) { sts_f32(x.s_pb + 4 * ((k + x.sw) & 63), 0.f); sts_f32(x.s_dr + 4 * k, 0.f); }
-    if (patch) {
+  else
+    rows_barrier();
+  if (patch) {
 #pragma unroll
-      for (int t = 0; t < G; ++t) {
-        sts_f32(x.s_pb + 4 * (((M1 - ri + t) + x.sw) & 63), prow[t]);
-        sts_f32(x.s_pb + 4 * (((32 + M1 - ci + t) + x.sw) & 63), pcol[t]);
-        sts_f32(x.s_dr + 4 * (M1 - ri + t), drow[t]);
-        sts_f32(x.s_dr + 4 * (32 + M1 - ci + t), dcol[t]);
-      }
-      sts_f32(x.s_pb + 4 * ((0 + x.sw) & 63), p0);
-      sts_f32(x.s_pb + 4 * ((32 + x.sw) & 63), p0);
-      sts_f32(x.s_dr, d0);
-      sts_f32(x.s_dr + 4 * 32, d0);
-    } else {
-      sts_f32(x.s_pb + 4 * ((0 + x.sw) & 63), psum);
-      sts_f32(x.s_pb + 4 * ((32 + x.sw) & 63), psum);
-      sts_f32(x.s_dr, dsum);
-      sts_f32(x.s_dr + 4 * 32, dsum);
+    for (int t = 0; t < LR; ++t) {
+      if (hi && t >= G - LR) continue;
+      put(x.s_pb + 4 * (((vb + t) + x.sw) & 63), prow[t]);
+      put(x.s_dr + 4 * (vb + t), drow[t]);
     }
-  }
-  rows_barrier();
-  if (x.half == 1) {
 #pragma unroll
-    for (int c = kSplit; c < NCH; ++c) tmem_st8(x.trow + c * 8, keep[c - kSplit]);
-    auto add = [](uint32_t a, float v) { sts_f32(a, lds_f32(a) + v); };
-    if (patch) {
-#pragma unroll
-      for (int t = 0; t < G; ++t) {
-        add(x.s_pb + 4 * (((M1 - ri + t) + x.sw) & 63), prow[t]);
-        add(x.s_pb + 4 * (((32 + M1 - ci + t) + x.sw) & 63), pcol[t]);
-        add(x.s_dr + 4 * (M1 - ri + t), drow[t]);
-        add(x.s_dr + 4 * (32 + M1 - ci + t), dcol[t]);
-      }
-      // j == 0 (cls key) lives in the first half: p0 / d0 are zero here
-    } else {
-      add(x.s_pb + 4 * ((0 + x.sw) & 63), psum);
-      add(x.s_pb + 4 * ((32 + x.sw) & 63), psum);
-      add(x.s_dr, dsum);
-      add(x.s_dr + 4 * 32, dsum);
+    for (int t = 0; t < G; ++t) {
+      put(x.s_pb + 4 * (((32 + M1 - ci + t) + x.sw) & 63), pcol[t]);
+      put(x.s_dr + 4 * (32 + M1 - ci + t), dcol[t]);
     }
+    if (hi == 0) {           // cls key: bucket 0 of the vertical and of the horizontal table
+      sts_f32(x.s_pb + 4 * ((0 + x.sw) & 63), pf);
+      sts_f32(x.s_pb + 4 * ((32 + x.sw) & 63), pf);
+      sts_f32(x.s_dr, df);
+      sts_f32(x.s_dr + 4 * 32, df);
+    } else {                 // grid position (7, 13)
+      put(x.s_pb + 4 * (((M1 - ri + LR - 1) + x.sw) & 63), pf);
+      put(x.s_pb + 4 * (((32 + M1 - ci + G - 1) + x.sw) & 63), pf);
+      put(x.s_dr + 4 * (M1 - ri + LR - 1), df);
+      put(x.s_dr + 4 * (32 + M1 - ci + G - 1), df);
+    }
+  } else {
+    put(x.s_pb + 4 * ((0 + x.sw) & 63), psum);
+    put(x.s_pb + 4 * ((32 + x.sw) & 63), psum);
+    put(x.s_dr, dsum);
+    put(x.s_dr + 4 * 32, dsum);
   }
+  if (hi == 0) rows_barrier();
   rows_barrier();
 }
 
@@ -335,8 +360,10 @@ attn_bwd_rows_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
       tma_load_3d(sV, &map_kv, bar_ld, vcol, 0, b);
       if (p.ctx_k) tma_load_3d(sTK, &map_tk, bar_ld, 0, 0, tab);
       if (p.ctx_v) tma_load_3d(sTV, &map_tv, bar_ld, 0, 0, tab);
+      ROWS_TRACE(0);
       mbar_wait(bar_ld, 0);
       tc_fence_after();
+      ROWS_TRACE(1);
       const uint32_t aQ = smem_u32(sQ), adO = smem_u32(sdO), aK = smem_u32(sK), aV = smem_u32(sV);
       const uint32_t aTK = smem_u32(sTK), aTV = smem_u32(sTV);
       const uint32_t id64 = umma_idesc_bf16(128, kNB, 0, 0);
@@ -361,13 +388,19 @@ attn_bwd_rows_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
         umma_ss(tmem + 0, umma_smem_desc_sw128(aQ + k * 32, 16, 1024),
                 umma_smem_desc_sw128(aK + k * 32, 16, 1024), idN, k > 0);
       umma_commit(bar_s);
+      ROWS_TRACE(2);
 
       mbar_wait(bar_p, 0);
       tc_fence_after();
+      ROWS_TRACE(3);
       const uint32_t id_o = umma_idesc_bf16(128, kD, 0, 1);
       const int ksteps = (Npad + (p.ctx_k ? kNB : 0)) / 16;
-      for (int k = 0; k < ksteps; ++k)   // dQ = [dT | dR] [K ; TK]
-        umma_ts(tmem + 192, tmem + 8 * k, umma_smem_desc_sw128(aK + k * 2048, 8192, 1024), id_o, k > 0);
+      for (int k = 0; k < ksteps; ++k) {  // dQ = [dT | dR] [K ; TK]
+        // structured path: the packed dT of keys >= 112 sits in the spare columns (see bwd_row_af)
+        const bool hi_part = p.af_grid != 0 && k >= kAfSplitCols / 16 && k < Npad / 16;
+        const uint32_t a_col = hi_part ? kDtHiCol + 8 * (k - kAfSplitCols / 16) : 8 * k;
+        umma_ts(tmem + 192, tmem + a_col, umma_smem_desc_sw128(aK + k * 2048, 8192, 1024), id_o, k > 0);
+      }
       umma_commit(bar_o);
     }
   } else {
@@ -387,9 +420,29 @@ attn_bwd_rows_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
     x.row_c = min(row, p.N - 1);
     x.sw = (2 * r_local) & 63;
 
+    const int tslot = threadIdx.x == 32 ? 8 : (threadIdx.x == 160 ? 24 : -1);
+#define RT(k) do { if (tslot >= 0) ROWS_TRACE(tslot + (k)); } while (0)
+    // delta_i = dO_i . O_i and lse_i straight from global (256 B per row), requested FIRST: the
+    // row-strided loads take ~5k cycles and complete under the operand loads / first MMAs
+    float delta = 0.f, lse = 0.f;
+    if (row < p.N) {
+      const uint4* o4 = reinterpret_cast<const uint4*>(p.out + (static_cast<int64_t>(b) * p.N + row) * p.ldo + head * kD);
+      const uint4* g4 = reinterpret_cast<const uint4*>(p.dout + (static_cast<int64_t>(b) * p.N + row) * p.lddo + head * kD);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const uint4 a = __ldg(o4 + q), g = __ldg(g4 + q);
+        const float2 a0 = unpack_bf16x2(a.x), a1 = unpack_bf16x2(a.y), a2 = unpack_bf16x2(a.z), a3 = unpack_bf16x2(a.w);
+        const float2 g0 = unpack_bf16x2(g.x), g1 = unpack_bf16x2(g.y), g2 = unpack_bf16x2(g.z), g3 = unpack_bf16x2(g.w);
+        delta += a0.x * g0.x + a0.y * g0.y + a1.x * g1.x + a1.y * g1.y + a2.x * g2.x + a2.y * g2.y +
+                 a3.x * g3.x + a3.y * g3.y;
+      }
+      lse = p.lse[(static_cast<int64_t>(b) * p.H + head) * p.N + row];
+    }
+    RT(0);
     if (any_r) {
       mbar_wait(bar_r, 0);
       tc_fence_after();
+      RT(1);
       {
         const int c = half;                      // each thread of the pair stages 32 of the 64 buckets
         uint32_t raw[32];
@@ -410,30 +463,19 @@ attn_bwd_rows_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
       mbar_arrive(bar_rfree);
       rows_barrier();                            // both halves of R / dPB staged before anyone gathers
     }
+    RT(2);
 
-    // delta_i = dO_i . O_i and lse_i straight from global (256 B per row)
-    float delta = 0.f, lse = 0.f;
-    if (row < p.N) {
-      const uint4* o4 = reinterpret_cast<const uint4*>(p.out + (static_cast<int64_t>(b) * p.N + row) * p.ldo + head * kD);
-      const uint4* g4 = reinterpret_cast<const uint4*>(p.dout + (static_cast<int64_t>(b) * p.N + row) * p.lddo + head * kD);
-#pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        const uint4 a = __ldg(o4 + q), g = __ldg(g4 + q);
-        const float2 a0 = unpack_bf16x2(a.x), a1 = unpack_bf16x2(a.y), a2 = unpack_bf16x2(a.z), a3 = unpack_bf16x2(a.w);
-        const float2 g0 = unpack_bf16x2(g.x), g1 = unpack_bf16x2(g.y), g2 = unpack_bf16x2(g.z), g3 = unpack_bf16x2(g.w);
-        delta += a0.x * g0.x + a0.y * g0.y + a1.x * g1.x + a1.y * g1.y + a2.x * g2.x + a2.y * g2.y +
-                 a3.x * g3.x + a3.y * g3.y;
-      }
-      lse = p.lse[(static_cast<int64_t>(b) * p.H + head) * p.N + row];
-    }
     x.delta = delta;
     x.lsel = lse * kLog2e;
     x.wrow = ((static_cast<int64_t>(b) * p.H + head) * p.N + row) * p.ldw;
+    RT(3);
     mbar_wait(bar_s, 0);
     tc_fence_after();
+    RT(4);
 
     if (p.af_grid == 14) bwd_row_af<14>(p, x);
     else bwd_row_generic(p, x);
+    RT(5);
 
     // bucket sums: PB -> workspace ; dR -> workspace + TMEM (A operand of the dQ MMA)
     {
@@ -462,10 +504,12 @@ attn_bwd_rows_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
     tmem_st_wait();
     tc_fence_before();
     mbar_arrive(bar_p);
+    RT(6);
 
     const uint32_t trow = x.trow;
     mbar_wait(bar_o, 0);
     tc_fence_after();
+    RT(7);
     __nv_bfloat16* qrow = p.dqkv + (static_cast<int64_t>(b) * p.N + row) * p.lddqkv + head * kD;
     {
       const int c = half;
@@ -745,9 +789,35 @@ extern "C" int cream_attn_bwd(const cream_attn_desc* d, void* stream_) {
                            std::max<size_t>(Npad * 128, 26 * 1024) + 8192 + 2 * 128 * kStride * 4 + 2 * 64 * 4 + 128;
   CB_REQUIRE(smem_rows <= 227 * 1024, "shared memory budget");
   dim3 grid(ceil_div(d->N, 128), d->H, d->B);
+#ifdef CREAM_TRACE
+  static long long* trace_dev = nullptr;
+  if (getenv("CREAM_ATTN_TRACE") != nullptr) {
+    if (trace_dev == nullptr) CB_CUDA_OK(cudaMalloc(&trace_dev, 64 * sizeof(long long)));
+    CB_CUDA_OK(cudaMemsetAsync(trace_dev, 0, 64 * sizeof(long long), stream));
+    p.trace = trace_dev;
+  }
+#endif
   attn_bwd_rows_kernel<<<grid, kRowsThreads, smem_rows, stream>>>(*mq, *mkv, *mdo, *mtk, *mtv, p);
   int rc = check_last("attn_bwd_rows_kernel");
   if (rc) return rc;
+#ifdef CREAM_TRACE
+  if (p.trace != nullptr) {
+    static int dumps = 0;
+    if (p.af_grid != 0 && dumps++ < 4) {
+      long long h[64];
+      CB_CUDA_OK(cudaStreamSynchronize(stream));
+      CB_CUDA_OK(cudaMemcpy(h, trace_dev, sizeof(h), cudaMemcpyDeviceToHost));
+      const long long t0 = h[0];
+      fprintf(stderr, "ROWS TRACE (cycles from first TMA issue) B %d H %d N %d af %d\n", p.B, p.H, p.N, p.af_grid);
+      fprintf(stderr, "  mma thread: loads landed %lld | T,dP issued %lld | bar_p %lld\n", h[1] - t0, h[2] - t0, h[3] - t0);
+      for (int q = 0; q < 2; ++q) {
+        const long long* e = h + 8 + 16 * q;
+        fprintf(stderr, "  row thread half %d: start %lld | R ready %lld | staged %lld | delta loaded %lld | T ready %lld | columns done %lld | tail done %lld | dQ ready %lld\n",
+                q, e[0] - t0, e[1] - t0, e[2] - t0, e[3] - t0, e[4] - t0, e[5] - t0, e[6] - t0, e[7] - t0);
+      }
+    }
+  }
+#endif
 
   BwdColsParams c{};
   c.B = d->B; c.H = d->H; c.N = d->N; c.Npad = Npad; c.ldw = ldw;
