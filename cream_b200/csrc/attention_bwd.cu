@@ -206,13 +206,21 @@ __device__ __forceinline__ void bwd_row_af(const BwdRowsParams& p, const RowCtx&
   const uint32_t t_in = x.trow + kAfSplitCols * hi;               // this half's T columns
   const uint32_t t_out = hi ? x.trow + kDtHiCol : x.trow;        // packed dT: in place, or the spare columns
   const int64_t w0 = x.wrow + kAfSplitCols * hi;
+  // accumulator reads run one chunk ahead of the arithmetic (tcgen05.wait::ld covers every load
+  // issued before it, so the next chunk is requested right after the wait)
+  uint32_t rtb[2][16], rpb[2][16];
+  tmem_ld16(t_in, rtb[0]);
+  tmem_ld16(t_in + 256, rpb[0]);
 #pragma unroll
   for (int cc = 0; cc < NCC; ++cc) {
     if (cc == NCC - 1 && hi) break;                                // half 1 owns 6 chunks (keys 112..207)
-    uint32_t rt[16], rp[16];
-    tmem_ld16(t_in + cc * 16, rt);
-    tmem_ld16(t_in + 256 + cc * 16, rp);
+    uint32_t (&rt)[16] = rtb[cc & 1];
+    uint32_t (&rp)[16] = rpb[cc & 1];
     tmem_ld_wait();
+    if (cc + 1 < NCC && !(cc + 1 == NCC - 1 && hi)) {
+      tmem_ld16(t_in + (cc + 1) * 16, rtb[(cc + 1) & 1]);
+      tmem_ld16(t_in + 256 + (cc + 1) * 16, rpb[(cc + 1) & 1]);
+    }
     float pv[16], dt[16];
 #pragma unroll
     for (int k = 0; k < 16; ++k) {

@@ -161,11 +161,15 @@ __device__ __forceinline__ void softmax_af(const AttnFwdParams& p, uint32_t trow
     rh[t] = patch ? lds_f16(sr_row + 2 * (32 + M1 - ci + t)) : r0h;
   }
   float mx = -INFINITY;
+  // accumulator reads run one chunk ahead of the arithmetic in both passes (tcgen05.wait::ld covers
+  // every load issued before it, so the next chunk is requested right after the wait)
+  uint32_t rb[2][16];
+  tmem_ld16(trow, rb[0]);
 #pragma unroll
   for (int c = 0; c < NCH; ++c) {
-    uint32_t raw[16];
-    tmem_ld16(trow + c * 16, raw);
+    uint32_t (&raw)[16] = rb[c & 1];
     tmem_ld_wait();
+    if (c + 1 < NCH) tmem_ld16(trow + (c + 1) * 16, rb[(c + 1) & 1]);
 #pragma unroll
     for (int k = 0; k < 16; ++k) {
       const int j = c * 16 + k;
@@ -184,11 +188,12 @@ __device__ __forceinline__ void softmax_af(const AttnFwdParams& p, uint32_t trow
 #pragma unroll
   for (int t = 0; t < G; ++t) { prow[t] = 0.f; pcol[t] = 0.f; }
   const float mxl = mx * kLog2e;
+  tmem_ld16(trow, rb[0]);
 #pragma unroll
   for (int c = 0; c < NCH; ++c) {
-    uint32_t raw[16];
-    tmem_ld16(trow + c * 16, raw);
+    uint32_t (&raw)[16] = rb[c & 1];
     tmem_ld_wait();
+    if (c + 1 < NCH) tmem_ld16(trow + (c + 1) * 16, rb[(c + 1) & 1]);
     float pv[16];
 #pragma unroll
     for (int k = 0; k < 16; ++k) {
