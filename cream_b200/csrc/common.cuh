@@ -89,6 +89,30 @@ __device__ __forceinline__ float2 unpack_bf16x2(uint32_t u) {
   return __bfloat1622float2(v);
 }
 
+// Adds n contiguous fp32 partial sums held in SHARED memory to global memory.  Called by every
+// thread of the block after the sums are complete (it synchronises).  When the geometry allows
+// it is ONE bulk reduce (the L2 adds whole 128-byte lines), not n same-address atomics: with a few
+// hundred blocks folding into the same few hundred addresses, per-element atomics serialise in the
+// L2 and cost more than the streaming pass that produced the sums.
+__device__ __forceinline__ void block_add_to_global(float* dst, const float* s_src, int n) {
+  __syncthreads();
+  const bool bulk = (n & 3) == 0 && n > 0 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0 &&
+                    (static_cast<uint32_t>(__cvta_generic_to_shared(s_src)) & 15) == 0;
+  if (bulk) {
+    if (threadIdx.x == 0 && threadIdx.y == 0) {
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;" ::"l"(dst),
+                   "r"(static_cast<uint32_t>(__cvta_generic_to_shared(s_src))), "r"(n * 4)
+                   : "memory");
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // shared memory must outlive the read
+    }
+  } else {
+    const int t = threadIdx.y * blockDim.x + threadIdx.x, nt = blockDim.x * blockDim.y;
+    for (int i = t; i < n; i += nt) atomicAdd(dst + i, s_src[i]);
+  }
+}
+
 // Host-side TMA tensor-map factory (cached). dims/strides in elements; strides[0]
 // is implicit (1). Returns nullptr on failure.
 const CUtensorMap* get_tensor_map(const void* base, CUtensorMapDataType dtype, int rank,

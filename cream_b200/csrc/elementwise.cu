@@ -152,18 +152,21 @@ cast_scale_kernel(const float* __restrict__ in, int64_t ldi, __nv_bfloat16* __re
     }
   }
   if (dbias == nullptr) return;
+  __shared__ __align__(16) float outv[128];
   red[threadIdx.y][threadIdx.x][0] = a0; red[threadIdx.y][threadIdx.x][1] = a1;
   red[threadIdx.y][threadIdx.x][2] = a2; red[threadIdx.y][threadIdx.x][3] = a3;
   __syncthreads();
-  if (threadIdx.y == 0 && live) {
+  if (threadIdx.y == 0) {
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       float t = 0.f;
 #pragma unroll
       for (int y = 0; y < 8; ++y) t += red[y][threadIdx.x][k];
-      if (c + k < cols) atomicAdd(dbias + c + k, t);
+      outv[threadIdx.x * 4 + k] = t;
     }
   }
+  const int c0 = blockIdx.x * 128;
+  block_add_to_global(dbias + c0, outv, min(128, cols - c0));
 }
 
 // dbias[c] += sum_r dy[r,c]  (bf16 input).  Block = 32 column threads (x8 columns) x 8 row lanes.
@@ -200,18 +203,21 @@ colsum_kernel(const __nv_bfloat16* __restrict__ dy, int64_t ld, float* __restric
       }
     }
   }
+  __shared__ __align__(16) float outv[256];
 #pragma unroll
   for (int k = 0; k < 8; ++k) red[threadIdx.y][threadIdx.x][k] = acc[k];
   __syncthreads();
-  if (threadIdx.y == 0 && live) {
+  if (threadIdx.y == 0) {
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
       float t = 0.f;
 #pragma unroll
       for (int y = 0; y < 8; ++y) t += red[y][threadIdx.x][k];
-      if (c + k < cols) atomicAdd(dbias + c + k, t);
+      outv[threadIdx.x * 8 + k] = t;
     }
   }
+  const int c0 = blockIdx.x * 256;
+  block_add_to_global(dbias + c0, outv, min(256, cols - c0));
 }
 
 struct PackSrc {

@@ -123,11 +123,8 @@ ln_bwd_kernel(const void* __restrict__ dy, int64_t lddy, const float* __restrict
       atomicAdd(&sacc[E + c], pb[i]);
     }
   }
-  __syncthreads();
-  for (int c = threadIdx.x; c < E; c += blockDim.x) {
-    atomicAdd(dgamma + c, sacc[c]);
-    atomicAdd(dbeta + c, sacc[E + c]);
-  }
+  block_add_to_global(dgamma, sacc, E);
+  block_add_to_global(dbeta, sacc + E, E);
 }
 
 // Vectorised backward (E % 4 == 0): each lane owns float4 groups c = 4*(lane + 32*i).  All loads
@@ -217,11 +214,8 @@ ln_bwd_vec_kernel(const void* __restrict__ dy, int64_t lddy, const float* __rest
       atomicAdd(&sacc[E + c + 2], pb[i].z); atomicAdd(&sacc[E + c + 3], pb[i].w);
     }
   }
-  __syncthreads();
-  for (int c = threadIdx.x; c < E; c += blockDim.x) {
-    atomicAdd(dgamma + c, sacc[c]);
-    atomicAdd(dbeta + c, sacc[E + c]);
-  }
+  block_add_to_global(dgamma, sacc, E);
+  block_add_to_global(dbeta, sacc + E, E);
 }
 
 }  // namespace
