@@ -69,6 +69,14 @@ class GradBuckets:
         return "block%d" % i
 
 
+class StagedBatch:
+    """A batch whose host->device copy is in flight on the trainer's copy stream."""
+    __slots__ = ("images", "targets", "ready")
+
+    def __init__(self, images, targets, ready):
+        self.images, self.targets, self.ready = images, targets, ready
+
+
 class SupernetTrainer:
     def __init__(self, model: Vision_TransformerSuper, choices: dict, lr: float = 5e-4, weight_decay: float = 0.05,
                  process_group=None, grad_dtype: torch.dtype = torch.float32):
@@ -88,6 +96,7 @@ class SupernetTrainer:
         self.optimizer = torch.optim.AdamW([{"params": decay, "weight_decay": weight_decay},
                                             {"params": no_decay, "weight_decay": 0.0}], lr=lr, fused=model.pos_embed.is_cuda)
         self.comm_stream = torch.cuda.Stream() if (self.world > 1 and model.pos_embed.is_cuda) else None
+        self.copy_stream = torch.cuda.Stream() if model.pos_embed.is_cuda else None
         self.last_config: Optional[dict] = None
 
     # ------------------------------------------------------------------------------------
@@ -119,13 +128,38 @@ class SupernetTrainer:
         for n, p in self.params.items():
             p.grad = self.buckets.views[n] if n in sampled else None
 
-    def step(self, images: torch.Tensor, targets: torch.Tensor, config: Optional[dict] = None,
+    def stage(self, images: torch.Tensor, targets: torch.Tensor) -> StagedBatch:
+        """Start the host->device copy of the NEXT batch on a side stream and return a handle for
+        `step`.  With pinned host tensors (the reference's DataLoader(pin_memory=True) +
+        `.to(device, non_blocking=True)`, supernet_engine.py:57-58) the copy is a DMA that runs under
+        the kernels of the step in flight instead of in front of its own step."""
+        dev = self.model.pos_embed.device
+        if self.copy_stream is None or images.is_cuda:
+            return StagedBatch(images.to(dev), targets.to(dev), None)
+        with torch.cuda.stream(self.copy_stream):
+            di = images.to(dev, non_blocking=True)
+            dt = targets.to(dev, non_blocking=True)
+            ready = torch.cuda.Event()
+            ready.record(self.copy_stream)
+        return StagedBatch(di, dt, ready)
+
+    def step(self, images, targets: Optional[torch.Tensor] = None, config: Optional[dict] = None,
              rnd=random) -> torch.Tensor:
-        """One training step; returns the (device) loss tensor without synchronising."""
+        """One training step; returns the (device) loss tensor without synchronising.
+        `images` is a tensor (host or device) or a StagedBatch from `stage`."""
         model = self.model
         dev = model.pos_embed.device
-        images = images.to(dev, non_blocking=True)
-        targets = targets.to(dev, non_blocking=True)
+        if isinstance(images, StagedBatch):
+            staged = images
+            if staged.ready is not None:
+                cur = torch.cuda.current_stream()
+                cur.wait_event(staged.ready)
+                staged.images.record_stream(cur)
+                staged.targets.record_stream(cur)
+            images, targets = staged.images, staged.targets
+        else:
+            images = images.to(dev, non_blocking=True)
+            targets = targets.to(dev, non_blocking=True)
         cfg = config if config is not None else sample_configs(self.choices, rnd)
         self.last_config = cfg
         model.set_sample_config(cfg)
