@@ -180,18 +180,30 @@ class IrpeAttentionFn(torch.autograd.Function):
     """Attention core of RPEAttention.forward (rpe_vision_transformer.py:73-92) with iRPE on
     keys and/or values.  qkv (B, N, 3*64h); rpe_k: contextual lookup_table_weight
     (H|1, 64, nb) or bias lookup_table_bias (H|1, nb); rpe_v: (H|1, nb, 64); ids: int (N, N)
-    bucket ids (numpy, from ops.irpe_bucket_ids)."""
+    bucket ids (numpy, from ops.irpe_bucket_ids).
+    Cross method (iRPE_Cross, irpe.py:696-751): ids = (row ids, column ids) and rpe_k2 / rpe_v2 are
+    the column tables; the two tables share one 64-row pack (rows at [0,32), columns at [32,64))
+    and the kernel gathers from both, exactly like AutoFormer's vertical / horizontal pair."""
 
     @staticmethod
-    def forward(ctx, qkv, heads, scale, ids, mode, rpe_k, rpe_v):
+    def forward(ctx, qkv, heads, scale, ids, mode, rpe_k, rpe_v, rpe_k2=None, rpe_v2=None):
         B, N, W3 = qkv.shape
         assert W3 == 3 * ops.HEAD_DIM * heads
         dev = qkv.device
         qkv2 = ops.as_bf16_2d(qkv)
-        idx_t = ops.irpe_index_table_u8(ids, dev)
+        cross = isinstance(ids, (tuple, list))
+        half = ops.NB_PACK // 2
+        if cross:
+            assert mode != "bias", "cross + bias mode is not supported by the fused kernel"
+            idx_t = ops.irpe_index_table_u8(ids[0], dev)
+            idx_t2 = ops.irpe_index_table_u8(ids[1], dev, offset=half)
+            nb = int(max(ids[0].max(), ids[1].max())) + 1
+            assert nb <= half, "cross tables must fit 32 packed rows each"
+        else:
+            idx_t, idx_t2 = ops.irpe_index_table_u8(ids, dev), None
+            nb = int(ids.max()) + 1
         tk = tv = bias = None
         per_head = False
-        nb = int(ids.max()) + 1
         if rpe_k is not None:
             per_head = rpe_k.shape[0] > 1
             T = rpe_k.shape[0]
@@ -202,7 +214,12 @@ class IrpeAttentionFn(torch.autograd.Function):
                 assert rpe_k.shape[1] == ops.HEAD_DIM and rpe_k.shape[2] >= nb
                 tk = ops.new_pack(T, dev)
                 w = rpe_k.detach()   # (T, D, nb): bucket stride = stride(2), channel stride = stride(1)
-                ops.pack_tables(tk, T, w, w.shape[2], 0, (w.stride(0), w.stride(2), w.stride(1)))
+                if cross:
+                    w2 = rpe_k2.detach()
+                    ops.pack_tables(tk, T, w, w.shape[2], 0, (w.stride(0), w.stride(2), w.stride(1)),
+                                    w2, w2.shape[2], half, (w2.stride(0), w2.stride(2), w2.stride(1)))
+                else:
+                    ops.pack_tables(tk, T, w, w.shape[2], 0, (w.stride(0), w.stride(2), w.stride(1)))
         if rpe_v is not None:
             assert mode != "bias", "bias mode has no value-side table (irpe.py:489-491)"
             per_head = per_head or rpe_v.shape[0] > 1
@@ -210,30 +227,48 @@ class IrpeAttentionFn(torch.autograd.Function):
             assert rpe_k is None or rpe_k.shape[0] == T, "k and v tables must agree on head sharing"
             tv = ops.new_pack(T, dev)
             w = rpe_v.detach()       # (T, nb, D)
-            ops.pack_tables(tv, T, w, w.shape[1], 0, (w.stride(0), w.stride(1), w.stride(2)))
-        idx = (idx_t if (tk is not None or bias is not None) else None, None, idx_t if tv is not None else None, None)
+            if cross:
+                w2 = rpe_v2.detach()
+                ops.pack_tables(tv, T, w, w.shape[1], 0, (w.stride(0), w.stride(1), w.stride(2)),
+                                w2, w2.shape[1], half, (w2.stride(0), w2.stride(1), w2.stride(2)))
+            else:
+                ops.pack_tables(tv, T, w, w.shape[1], 0, (w.stride(0), w.stride(1), w.stride(2)))
+        on_k = tk is not None or bias is not None
+        idx = (idx_t if on_k else None, idx_t2 if on_k else None,
+               idx_t if tv is not None else None, idx_t2 if tv is not None else None)
         out, lse = ops.attention_fwd(qkv2, B, heads, N, scale, tk=tk, tv=tv, per_head=per_head, idx=idx, bias=bias)
-        ctx.save_for_backward(qkv2, out, lse, tk, tv, bias, rpe_k, rpe_v)
-        ctx.meta = (B, heads, N, scale, idx, per_head, mode, qkv.dtype)
+        ctx.save_for_backward(qkv2, out, lse, tk, tv, bias, rpe_k, rpe_v, rpe_k2, rpe_v2)
+        ctx.meta = (B, heads, N, scale, idx, per_head, mode, qkv.dtype, cross)
         return out.reshape(B, N, ops.HEAD_DIM * heads)
 
     @staticmethod
     def backward(ctx, dout):
-        qkv2, out, lse, tk, tv, bias, rpe_k, rpe_v = ctx.saved_tensors
-        B, heads, N, scale, idx, per_head, mode, dtype = ctx.meta
+        qkv2, out, lse, tk, tv, bias, rpe_k, rpe_v, rpe_k2, rpe_v2 = ctx.saved_tensors
+        B, heads, N, scale, idx, per_head, mode, dtype, cross = ctx.meta
+        half = ops.NB_PACK // 2
         d2 = ops.as_bf16_2d(dout)
         dqkv, dtk, dtv, dbias = ops.attention_bwd(qkv2, out, lse, d2, B, heads, N, scale, tk=tk, tv=tv,
                                                   per_head=per_head, idx=idx, bias=bias)
-        gk = gv = None
+        gk = gv = gk2 = gv2 = None
         if rpe_k is not None:
             gk = torch.zeros_like(rpe_k)
             if mode == "bias":
                 gk += dbias[:, :rpe_k.shape[1]]
             else:
                 T = rpe_k.shape[0]
-                ops.unpack_table_grads(dtk, T, gk, gk.shape[2], 0, (gk.stride(0), gk.stride(2), gk.stride(1)))
+                if cross:
+                    gk2 = torch.zeros_like(rpe_k2)
+                    ops.unpack_table_grads(dtk, T, gk, gk.shape[2], 0, (gk.stride(0), gk.stride(2), gk.stride(1)),
+                                           gk2, gk2.shape[2], half, (gk2.stride(0), gk2.stride(2), gk2.stride(1)))
+                else:
+                    ops.unpack_table_grads(dtk, T, gk, gk.shape[2], 0, (gk.stride(0), gk.stride(2), gk.stride(1)))
         if rpe_v is not None:
             gv = torch.zeros_like(rpe_v)
             T = rpe_v.shape[0]
-            ops.unpack_table_grads(dtv, T, gv, gv.shape[1], 0, (gv.stride(0), gv.stride(1), gv.stride(2)))
-        return dqkv.reshape(B, N, -1).to(dtype), None, None, None, None, gk, gv
+            if cross:
+                gv2 = torch.zeros_like(rpe_v2)
+                ops.unpack_table_grads(dtv, T, gv, gv.shape[1], 0, (gv.stride(0), gv.stride(1), gv.stride(2)),
+                                       gv2, gv2.shape[1], half, (gv2.stride(0), gv2.stride(1), gv2.stride(2)))
+            else:
+                ops.unpack_table_grads(dtv, T, gv, gv.shape[1], 0, (gv.stride(0), gv.stride(1), gv.stride(2)))
+        return dqkv.reshape(B, N, -1).to(dtype), None, None, None, None, gk, gv, gk2, gv2

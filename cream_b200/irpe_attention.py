@@ -3,9 +3,9 @@
 `RPEAttention` mirrors iRPE/DeiT-with-iRPE/rpe_vision_transformer.py:45-97 (constructor,
 parameter names `qkv`, `proj`, `rpe_q/rpe_k/rpe_v.lookup_table_{weight,bias}`), with the
 reference's q@k^T + rpe_k(q) gather, softmax, attn@v + rpe_v(attn) executed by ONE kernel.
-Supported in this round: rpe on k and/or v (contextual), bias mode on k, shared or per-head
-tables, methods euclidean / quant / product (<= 64 buckets); rpe on q and the cross method
-are the next rows of SURVEY.md §8f.
+Supported: rpe on k and/or v (contextual), bias mode on k, shared or per-head tables, methods
+euclidean / quant / product (<= 64 buckets) and cross (rows + columns tables, contextual);
+rpe on q is the next row of SURVEY.md §8f.
 """
 from __future__ import annotations
 
@@ -17,7 +17,8 @@ import torch.nn as nn
 from . import ops
 from .autoformer.functional import IrpeAttentionFn, SlicedLinearFn
 
-METHODS = {"euc": 0, "quant": 1, "product": 3}
+METHODS = {"euc": 0, "quant": 1, "product": 3, "cross": 4}
+CROSS_ROWS, CROSS_COLS = 41, 42
 
 
 class IrpeTable(nn.Module):
@@ -42,6 +43,15 @@ class IrpeTable(nn.Module):
         return self.lookup_table_bias if self.mode == 'bias' else self.lookup_table_weight
 
 
+class IrpeCrossTable(nn.Module):
+    """iRPE_Cross (irpe.py:696-751): `rp_rows` + `rp_cols`, each an iRPE table of its own."""
+
+    def __init__(self, head_dim, num_heads, mode, transposed, num_buckets):
+        super().__init__()
+        self.rp_rows = IrpeTable(head_dim, num_heads, mode, transposed, num_buckets)
+        self.rp_cols = IrpeTable(head_dim, num_heads, mode, transposed, num_buckets)
+
+
 class RPEAttention(nn.Module):
     def __init__(self, dim, num_heads=8, qkv_bias=False, qk_scale=None, attn_drop=0., proj_drop=0.,
                  rpe_on='k', method='product', mode='contextual', shared_head=True, ratio=1.9, skip=1):
@@ -61,16 +71,27 @@ class RPEAttention(nn.Module):
             self.mode = 'contextual'
         beta_int = int(2 * ratio)
         nb = ((2 * beta_int + 1) ** 2 if method == 'product' else 2 * beta_int + 1) + (1 if skip > 0 else 0)
-        assert nb <= ops.NB_PACK, "more than 64 buckets is not supported by the fused kernel"
+        self.cross = method == 'cross'
+        assert nb <= (ops.NB_PACK // 2 if self.cross else ops.NB_PACK), "too many buckets for the fused kernel"
+        if self.cross and self.mode == 'bias':
+            raise NotImplementedError("cross + bias mode is not supported by the fused kernel")
         self.num_buckets = nb
         t_heads = 1 if shared_head else num_heads
+        make = IrpeCrossTable if self.cross else IrpeTable
         self.rpe_q = None
-        self.rpe_k = IrpeTable(head_dim, t_heads, self.mode, True, nb) if 'k' in rpe_on else None
-        self.rpe_v = IrpeTable(head_dim, t_heads, self.mode, False, nb) if 'v' in rpe_on else None
+        self.rpe_k = make(head_dim, t_heads, self.mode, True, nb) if 'k' in rpe_on else None
+        self.rpe_v = make(head_dim, t_heads, self.mode, False, nb) if 'v' in rpe_on else None
 
     def bucket_ids(self, L):
         side = int(math.sqrt(L))
         skip = L - side * side
+        if self.cross:
+            out = []
+            for m in (CROSS_ROWS, CROSS_COLS):
+                ids, nb = ops.irpe_bucket_ids(m, side, side, skip, 1 * self.ratio, 2 * self.ratio, 8 * self.ratio)
+                assert nb == self.num_buckets
+                out.append(ids)
+            return tuple(out)
         ids, nb = ops.irpe_bucket_ids(self.method, side, side, skip, 1 * self.ratio, 2 * self.ratio, 8 * self.ratio)
         assert nb == self.num_buckets
         return ids
@@ -78,8 +99,12 @@ class RPEAttention(nn.Module):
     def forward(self, x):
         B, N, C = x.shape
         qkv = SlicedLinearFn.apply(x, self.qkv.weight, self.qkv.bias, C, 3 * C, False)   # (B, N, 3C) bf16
-        out = IrpeAttentionFn.apply(qkv, self.num_heads, float(self.scale), self.bucket_ids(N), self.mode,
-                                    self.rpe_k.table if self.rpe_k is not None else None,
-                                    self.rpe_v.table if self.rpe_v is not None else None)
+        if self.cross:
+            tabs = [t.rp_rows.table if t is not None else None for t in (self.rpe_k, self.rpe_v)] + \
+                   [t.rp_cols.table if t is not None else None for t in (self.rpe_k, self.rpe_v)]
+        else:
+            tabs = [self.rpe_k.table if self.rpe_k is not None else None,
+                    self.rpe_v.table if self.rpe_v is not None else None, None, None]
+        out = IrpeAttentionFn.apply(qkv, self.num_heads, float(self.scale), self.bucket_ids(N), self.mode, *tabs)
         out = SlicedLinearFn.apply(out, self.proj.weight, self.proj.bias, C, C, False)
         return self.proj_drop(out)

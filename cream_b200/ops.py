@@ -293,11 +293,13 @@ def irpe_bucket_ids(method: int, height: int, width: int, skip: int, alpha: floa
     return _INDEX_CACHE[key]
 
 
-def irpe_index_table_u8(ids: np.ndarray, device) -> torch.Tensor:
-    key = ("irpe_u8", ids.tobytes(), str(device))
+def irpe_index_table_u8(ids: np.ndarray, device, offset: int = 0) -> torch.Tensor:
+    """uint8 gather table of iRPE bucket ids, shifted by `offset` rows into the 64-row table pack
+    (the cross method keeps its column table at rows [32, 64))."""
+    key = ("irpe_u8", ids.tobytes(), offset, str(device))
     if key not in _INDEX_CACHE:
-        assert ids.max() < NB_PACK, "more than 64 buckets is not supported by the fused kernel"
-        _INDEX_CACHE[key] = _u8_table(ids, 0, device)
+        assert ids.max() + offset < NB_PACK, "more than 64 buckets is not supported by the fused kernel"
+        _INDEX_CACHE[key] = _u8_table(ids, offset, device)
     return _INDEX_CACHE[key]
 
 

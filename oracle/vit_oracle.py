@@ -279,14 +279,20 @@ def rpe_attention(x, qkv_w, qkv_b, proj_w, proj_b, num_heads: int, bucket_ids,
     scale = (C // num_heads) ** -0.5
     q = q * scale
     attn = q @ k.transpose(-2, -1)
+    # cross method (iRPE_Cross.forward, irpe.py:726-751): every table is a (rows, cols) pair with
+    # its own bucket ids and the two encodings are summed
+    def both(fn, x_, tab):
+        if isinstance(tab, (tuple, list)):
+            return fn(x_, tab[0], bucket_ids[0]) + fn(x_, tab[1], bucket_ids[1])
+        return fn(x_, tab, bucket_ids)
     if rpe_k is not None:
-        attn = attn + irpe_rpe_transposed(q, rpe_k, bucket_ids, mode)
+        attn = attn + both(lambda x_, t, i: irpe_rpe_transposed(x_, t, i, mode), q, rpe_k)
     if rpe_q is not None:
-        attn = attn + irpe_rpe_transposed(k * scale, rpe_q, bucket_ids, mode).transpose(2, 3)
+        attn = attn + both(lambda x_, t, i: irpe_rpe_transposed(x_, t, i, mode), k * scale, rpe_q).transpose(2, 3)
     attn = attn.softmax(dim=-1)
     out = attn @ v
     if rpe_v is not None:
-        out = out + irpe_rpe_value(attn, rpe_v, bucket_ids)
+        out = out + both(irpe_rpe_value, attn, rpe_v)
     if return_core:
         return out
     x = out.transpose(1, 2).reshape(B, N, C)

@@ -204,6 +204,7 @@ IRPE_CASES = {
     "qkv_ctx_perhead": ("qkv", "ctx", False, "product", 128, 2, 7),
     "qk_bias": ("qk", "bias", False, "euc", 64, 2, 7),
     "k_ctx_quant": ("k", "ctx", True, "quant", 64, 1, 5),
+    "kv_ctx_cross": ("kv", "ctx", True, "cross", 128, 2, 7),       # iRPE_Cross: rows + cols tables
 }
 
 

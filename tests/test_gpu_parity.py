@@ -321,6 +321,8 @@ IRPE_GPU_CASES = {
     "kv_ctx_perhead": ("kv", "contextual", False, "product", 2, 7),
     "k_bias": ("k", "bias", False, "euc", 2, 7),
     "k_ctx_quant": ("k", "contextual", True, "quant", 1, 5),
+    "kv_ctx_cross": ("kv", "contextual", True, "cross", 2, 7),
+    "k_ctx_cross_perhead": ("k", "contextual", False, "cross", 2, 14),
 }
 
 
@@ -343,10 +345,19 @@ def test_irpe_attention_module(name):
     # oracle (fp32, CPU) with the same parameters
     P = {k: v.detach().cpu().clone().requires_grad_(True) for k, v in m.named_parameters()}
     xr = x.detach().cpu().clone().requires_grad_(True)
-    mid = {"product": rel_index.PRODUCT, "euc": rel_index.EUCLIDEAN, "quant": rel_index.QUANT}[method]
-    ids, nb = rel_index.irpe_bucket_ids(mid, grid, grid, 1, 1.9, 3.8, 15.2)
-    np.testing.assert_array_equal(ids, m.bucket_ids(N))            # library ids == oracle ids (bit exact)
-    tab = lambda w: next((v for k, v in P.items() if k.startswith(f"rpe_{w}.")), None)
+    if method == "cross":
+        ids = tuple(rel_index.irpe_bucket_ids(mm, grid, grid, 1, 1.9, 3.8, 15.2)[0]
+                    for mm in (rel_index.CROSS_ROWS, rel_index.CROSS_COLS))
+        for a, b in zip(ids, m.bucket_ids(N)):
+            np.testing.assert_array_equal(a, b)                        # library ids == oracle ids (bit exact)
+    else:
+        mid = {"product": rel_index.PRODUCT, "euc": rel_index.EUCLIDEAN, "quant": rel_index.QUANT}[method]
+        ids, nb = rel_index.irpe_bucket_ids(mid, grid, grid, 1, 1.9, 3.8, 15.2)
+        np.testing.assert_array_equal(ids, m.bucket_ids(N))            # library ids == oracle ids (bit exact)
+
+    def tab(w):
+        hits = [v for k, v in P.items() if k.startswith(f"rpe_{w}.")]     # cross: rp_rows, rp_cols
+        return None if not hits else (hits[0] if len(hits) == 1 else tuple(hits))
     ref = vo.rpe_attention(xr, P["qkv.weight"], P["qkv.bias"], P["proj.weight"], P["proj.bias"], heads, ids,
                            rpe_k=tab("k"), rpe_v=tab("v"), mode=mode)
     ref.backward(gy.cpu())
@@ -356,13 +367,13 @@ def test_irpe_attention_module(name):
         assert rel_err(p.grad.float().cpu(), P[pn].grad) < 2e-2, pn
 
 
-def test_irpe_attention_golden_k_ctx_shared(golden_dir):
-    """BASELINE config-2 kind (contextual product on keys, shared head) against the fixture
-    written by the reference's own RPEAttention."""
+@pytest.mark.parametrize("name", ["k_ctx_shared", "kv_ctx_cross"])
+def test_irpe_attention_golden_k_ctx_shared(golden_dir, name):
+    """BASELINE config-2 kind (contextual product on keys, shared head), and the cross method on
+    keys and values, against the fixtures written by the reference's own RPEAttention."""
     from cream_b200.irpe_attention import RPEAttention
     from make_golden import IRPE_CASES
     g = np.load(golden_dir / "irpe_attention.npz")
-    name = "k_ctx_shared"
     rpe_on, mode, shared, method, C, heads, grid = IRPE_CASES[name]
     m = RPEAttention(C, num_heads=heads, qkv_bias=True, rpe_on=rpe_on, method=method, mode="contextual",
                      shared_head=shared).cuda()

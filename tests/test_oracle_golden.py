@@ -128,8 +128,12 @@ def _irpe_params(name):
 def test_irpe_attention_oracle_matches_reference(golden_dir, name):
     g = np.load(golden_dir / "irpe_attention.npz")
     rpe_on, mode, shared, method, C, heads, grid = IRPE_CASES[name]
-    mid = {"product": rel_index.PRODUCT, "euc": rel_index.EUCLIDEAN, "quant": rel_index.QUANT}[method]
-    ids, nb = rel_index.irpe_bucket_ids(mid, grid, grid, 1, 1.9, 3.8, 15.2)
+    if method == "cross":
+        ids = tuple(rel_index.irpe_bucket_ids(m, grid, grid, 1, 1.9, 3.8, 15.2)[0]
+                    for m in (rel_index.CROSS_ROWS, rel_index.CROSS_COLS))
+    else:
+        mid = {"product": rel_index.PRODUCT, "euc": rel_index.EUCLIDEAN, "quant": rel_index.QUANT}[method]
+        ids, nb = rel_index.irpe_bucket_ids(mid, grid, grid, 1, 1.9, 3.8, 15.2)
     N, B = grid * grid + 1, 2
     # parameter order of RPEAttention.named_parameters(): qkv.weight, qkv.bias, proj.weight,
     # proj.bias, then rpe_q / rpe_k / rpe_v lookup tables in attribute order
@@ -138,7 +142,9 @@ def test_irpe_attention_oracle_matches_reference(golden_dir, name):
     for pn, shape in shapes.items():
         seed += 1
         params[pn] = rand(shape, seed, 0.3 if "lookup" in pn else 0.08).requires_grad_(True)
-    tab = lambda w: next((v for k, v in params.items() if k.startswith(f"rpe_{w}.")), None)
+    def tab(w):
+        hits = [v for k, v in params.items() if k.startswith(f"rpe_{w}.")]   # cross: rp_rows, rp_cols
+        return None if not hits else (hits[0] if len(hits) == 1 else tuple(hits))
     x = rand((B, N, C), 99).requires_grad_(True)
     gy = rand((B, N, C), 98)
     y = vo.rpe_attention(x, params["qkv.weight"], params["qkv.bias"], params["proj.weight"], params["proj.bias"],
