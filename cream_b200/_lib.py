@@ -53,6 +53,8 @@ class AttnDesc(C.Structure):
         ("dtk_pack", c_void_p), ("dtv_pack", c_void_p),
         ("dbias_pack", c_void_p),
         ("workspace", c_void_p), ("workspace_bytes", c_i64),
+        ("dense_bias", c_void_p), ("dense_stride_b", c_i64), ("dense_stride_h", c_i64), ("dense_stride_i", c_i64),
+        ("ddense", c_void_p),
     ]
 
 

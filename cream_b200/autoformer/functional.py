@@ -5,6 +5,7 @@ as full-size tensors that are zero outside the sampled slice, exactly like autog
 the reference's slicing views."""
 from __future__ import annotations
 
+import numpy as np
 import torch
 
 from .. import _lib, ops
@@ -186,7 +187,31 @@ class IrpeAttentionFn(torch.autograd.Function):
     and the kernel gathers from both, exactly like AutoFormer's vertical / horizontal pair."""
 
     @staticmethod
-    def forward(ctx, qkv, heads, scale, ids, mode, rpe_k, rpe_v, rpe_k2=None, rpe_v2=None):
+    def _q_term(qkv2, B, N, heads, scale, ids_list, tables, mode):
+        """rpe_q(k * scale)^T of RPEAttention.forward (rpe_vision_transformer.py:82-83) as a dense
+        (B|1, H, N, N) logit term: lookup = (k*scale) @ table (irpe.py:617-633), gathered per KEY row
+        with the library's own rpe_index kernel, transposed to (query, key).  Returns (dense, saved)."""
+        dev = qkv2.device
+        if mode == "bias":
+            dense = None
+            for ids, tab in zip(ids_list, tables):
+                idl = torch.from_numpy(ids.astype(np.int64)).to(dev)
+                t = tab[:, idl.flatten()].view(1, tab.shape[0], N, N).transpose(2, 3)       # (1, T, i, j)
+                dense = t if dense is None else dense + t
+            return dense.expand(1, heads, N, N).contiguous().float(), None
+        k = qkv2.view(B, N, 3, heads, ops.HEAD_DIM)[:, :, 1].permute(0, 2, 1, 3).float() * scale   # (B, H, N, D)
+        dense, saved = None, []
+        for ids, tab in zip(ids_list, tables):
+            w = tab.detach().float()                                                      # (T, D, nb)
+            lookup = torch.matmul(k, w.unsqueeze(0)).contiguous()                         # (B, H, N, nb)
+            idx32 = torch.from_numpy(ids.astype(np.int32)).to(dev)
+            y = ops.rpe_index_forward(lookup, idx32)                                      # [b,h,j,i] = lookup[b,h,j,ids[j,i]]
+            dense = y if dense is None else dense + y
+            saved.append((idx32, lookup.shape))
+        return dense.transpose(2, 3).contiguous(), (k, saved)
+
+    @staticmethod
+    def forward(ctx, qkv, heads, scale, ids, mode, rpe_k, rpe_v, rpe_k2=None, rpe_v2=None, rpe_q=None, rpe_q2=None):
         B, N, W3 = qkv.shape
         assert W3 == 3 * ops.HEAD_DIM * heads
         dev = qkv.device
@@ -236,20 +261,53 @@ class IrpeAttentionFn(torch.autograd.Function):
         on_k = tk is not None or bias is not None
         idx = (idx_t if on_k else None, idx_t2 if on_k else None,
                idx_t if tv is not None else None, idx_t2 if tv is not None else None)
-        out, lse = ops.attention_fwd(qkv2, B, heads, N, scale, tk=tk, tv=tv, per_head=per_head, idx=idx, bias=bias)
-        ctx.save_for_backward(qkv2, out, lse, tk, tv, bias, rpe_k, rpe_v, rpe_k2, rpe_v2)
-        ctx.meta = (B, heads, N, scale, idx, per_head, mode, qkv.dtype, cross)
+        dense = qsave = None
+        if rpe_q is not None:
+            ids_list = list(ids) if cross else [ids]
+            dense, qsave = IrpeAttentionFn._q_term(qkv2, B, N, heads, scale, ids_list,
+                                                   [rpe_q, rpe_q2] if cross else [rpe_q], mode)
+        out, lse = ops.attention_fwd(qkv2, B, heads, N, scale, tk=tk, tv=tv, per_head=per_head, idx=idx, bias=bias,
+                                     dense=dense)
+        ctx.save_for_backward(qkv2, out, lse, tk, tv, bias, rpe_k, rpe_v, rpe_k2, rpe_v2, rpe_q, rpe_q2, dense)
+        ctx.meta = (B, heads, N, scale, idx, per_head, mode, qkv.dtype, cross, ids, qsave)
         return out.reshape(B, N, ops.HEAD_DIM * heads)
 
     @staticmethod
     def backward(ctx, dout):
-        qkv2, out, lse, tk, tv, bias, rpe_k, rpe_v, rpe_k2, rpe_v2 = ctx.saved_tensors
-        B, heads, N, scale, idx, per_head, mode, dtype, cross = ctx.meta
+        qkv2, out, lse, tk, tv, bias, rpe_k, rpe_v, rpe_k2, rpe_v2, rpe_q, rpe_q2, dense = ctx.saved_tensors
+        B, heads, N, scale, idx, per_head, mode, dtype, cross, ids, qsave = ctx.meta
         half = ops.NB_PACK // 2
         d2 = ops.as_bf16_2d(dout)
+        ddense = torch.empty((B, heads, N, N), dtype=torch.float32, device=qkv2.device) if dense is not None else None
         dqkv, dtk, dtv, dbias = ops.attention_bwd(qkv2, out, lse, d2, B, heads, N, scale, tk=tk, tv=tv,
-                                                  per_head=per_head, idx=idx, bias=bias)
-        gk = gv = gk2 = gv2 = None
+                                                  per_head=per_head, idx=idx, bias=bias, dense=dense, ddense=ddense)
+        gk = gv = gk2 = gv2 = gq = gq2 = None
+        if rpe_q is not None:
+            tabs = [rpe_q, rpe_q2] if cross else [rpe_q]
+            ids_list = list(ids) if cross else [ids]
+            grads = []
+            dy = ddense.transpose(2, 3).contiguous()                     # [b,h,j,i]: gradient of the gathered lookup
+            if mode == "bias":
+                for idn, tab in zip(ids_list, tabs):
+                    g = torch.zeros_like(tab)                            # (T, nb)
+                    src = dy.sum(0) if tab.shape[0] > 1 else dy.sum((0, 1))[None]
+                    g.view(tab.shape[0], -1).index_add_(1, torch.from_numpy(idn.astype(np.int64)).flatten().to(dy.device),
+                                                        src.reshape(tab.shape[0], -1))
+                    grads.append(g)
+            else:
+                kq, saved = qsave
+                dk = torch.zeros_like(kq)
+                for (idx32, lshape), tab in zip(saved, tabs):
+                    dl = torch.zeros(lshape, dtype=torch.float32, device=dy.device)
+                    ops.rpe_index_backward(dl, dy, idx32)                # scatter-add per key row
+                    w = tab.detach().float()                             # (T, D, nb)
+                    gw = torch.einsum("bhnd,bhnc->hdc", kq, dl)
+                    grads.append((gw if tab.shape[0] > 1 else gw.sum(0, keepdim=True)).to(tab.dtype))
+                    dk += torch.matmul(dl, w.transpose(1, 2).unsqueeze(0))
+                dq5 = dqkv.view(B, N, 3, heads, ops.HEAD_DIM)
+                dq5[:, :, 1] += (dk * scale).permute(0, 2, 1, 3).to(dqkv.dtype)
+            gq = grads[0]
+            gq2 = grads[1] if cross else None
         if rpe_k is not None:
             gk = torch.zeros_like(rpe_k)
             if mode == "bias":
@@ -271,4 +329,4 @@ class IrpeAttentionFn(torch.autograd.Function):
                                        gv2, gv2.shape[1], half, (gv2.stride(0), gv2.stride(1), gv2.stride(2)))
             else:
                 ops.unpack_table_grads(dtv, T, gv, gv.shape[1], 0, (gv.stride(0), gv.stride(1), gv.stride(2)))
-        return dqkv.reshape(B, N, -1).to(dtype), None, None, None, None, gk, gv, gk2, gv2
+        return dqkv.reshape(B, N, -1).to(dtype), None, None, None, None, gk, gv, gk2, gv2, gq, gq2

@@ -43,6 +43,8 @@ struct BwdRowsParams {
   __nv_bfloat16* dqkv; int64_t lddqkv;
   __nv_bfloat16* ws_p; __nv_bfloat16* ws_dt;  // (B*H*N, ldw)
   float* dbias;
+  const float* dense; int64_t dense_sb, dense_sh, dense_si;   // dense additive logit term (generic path)
+  float* ddense;                                              // (B,H,N,N) fp32: dS, or NULL
   long long* trace;   // CREAM_TRACE builds only
 };
 
@@ -55,6 +57,8 @@ struct BwdRowsParams {
 __device__ __forceinline__ void rows_barrier() { asm volatile("bar.sync 2, %0;" ::"n"(kRowThreads) : "memory"); }
 
 struct RowCtx {
+  const float* drow;    // this row of the dense additive logit term, or NULL
+  float* ddrow;         // this row of its gradient, or NULL
   uint32_t trow;        // TMEM address of this thread's lane
   uint32_t s_r, s_dpb;  // shared addresses of this row's staged R (scaled) and dPB, fp32[kStride]
   uint32_t s_pb, s_dr;  // shared addresses of this row's PB (64 floats, rotated by sw) and dR (kStride)
@@ -99,6 +103,7 @@ __device__ __forceinline__ void bwd_row_generic(const BwdRowsParams& p, const Ro
         if (ib) t += lds_f32(x.s_r + 4 * b_id);
       }
       if (use_bias) t += lds_f32(x.s_bias + 4 * a_id);
+      if (x.drow != nullptr && c * 16 + k < p.N) t += __ldg(x.drow + c * 16 + k);
       float pr = fast_exp2(fmaf(t, kLog2e, -x.lsel));
       if (c * 16 + k >= p.N || x.row >= p.N) pr = 0.f;
       float dp = __uint_as_float(rp[k]);
@@ -109,6 +114,7 @@ __device__ __forceinline__ void bwd_row_generic(const BwdRowsParams& p, const Ro
       const float d = pr * (dp - x.delta);
       pv[k] = pr;
       dt[k] = d;
+      if (x.ddrow != nullptr && c * 16 + k < p.N && x.row < p.N) x.ddrow[c * 16 + k] = d;
       if (p.ctx_v) {
         if (iva) { const uint32_t a = x.s_pb + 4 * ((va_id + x.sw) & 63); sts_f32(a, lds_f32(a) + pr); }
         if (ivb) { const uint32_t a = x.s_pb + 4 * ((vb_id + x.sw) & 63); sts_f32(a, lds_f32(a) + pr); }
@@ -426,6 +432,8 @@ attn_bwd_rows_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
     x.s_bias = smem_u32(sBias);
     x.row = row;
     x.row_c = min(row, p.N - 1);
+    x.drow = p.dense ? p.dense + b * p.dense_sb + head * p.dense_sh + x.row_c * p.dense_si : nullptr;
+    x.ddrow = p.ddense ? p.ddense + ((static_cast<int64_t>(b) * p.H + head) * p.N + x.row_c) * p.N : nullptr;
     x.sw = (2 * r_local) & 63;
 
     const int tslot = threadIdx.x == 32 ? 8 : (threadIdx.x == 160 ? 24 : -1);
@@ -763,6 +771,9 @@ extern "C" int cream_attn_bwd(const cream_attn_desc* d, void* stream_) {
   p.dqkv = static_cast<__nv_bfloat16*>(d->dqkv); p.lddqkv = d->ld_dqkv;
   p.ws_p = ws_p; p.ws_dt = ws_dt;
   p.dbias = d->dbias_pack;
+  p.dense = d->dense_bias; p.dense_sb = d->dense_stride_b; p.dense_sh = d->dense_stride_h; p.dense_si = d->dense_stride_i;
+  p.ddense = d->ddense;
+  if (p.dense != nullptr || p.ddense != nullptr) p.af_grid = 0;   // generic gather path only
 
   const uint64_t dims[3] = {static_cast<uint64_t>(3 * d->H * kD), static_cast<uint64_t>(d->N), static_cast<uint64_t>(d->B)};
   const uint64_t strides[3] = {1, static_cast<uint64_t>(d->ld_qkv), static_cast<uint64_t>(d->N) * d->ld_qkv};

@@ -41,6 +41,7 @@ struct AttnFwdParams {
   const uint8_t* idx_va; const uint8_t* idx_vb; // V-side
   int ldi;
   const float* bias;                   // (H or 1, 64) pre-packed bias table, gathered by idx_a
+  const float* dense; int64_t dense_sb, dense_sh, dense_si;   // dense additive logit term (generic path)
   __nv_bfloat16* out; int64_t ldo;     // (B*N, H*64)
   float* lse;                          // (B, H, N)
 };
@@ -51,8 +52,8 @@ struct AttnFwdParams {
 //   pass 2: p = exp(t - max); row sum; P -> bf16x2 in place; bucket sums PB[idx_v*] += p
 // ---------------------------------------------------------------------------------------
 __device__ __forceinline__ void softmax_generic(const AttnFwdParams& p, uint32_t trow, uint32_t sr_row,
-                                                uint32_t spb_row, uint32_t sbias, int row_c, float& mx_out,
-                                                float& sum_out) {
+                                                uint32_t spb_row, uint32_t sbias, int row_c, const float* drow,
+                                                float& mx_out, float& sum_out) {
   const int Npad = p.Npad;
   const int nchunks = Npad / 16;
   const uint8_t* ia = p.idx_a ? p.idx_a + static_cast<int64_t>(row_c) * p.ldi : nullptr;
@@ -77,6 +78,7 @@ __device__ __forceinline__ void softmax_generic(const AttnFwdParams& p, uint32_t
         if (ib) t += lds_f16(sr_row + 2 * byte_of(wb, k));
       }
       if (use_bias) t += lds_f32(sbias + 4 * a_id);
+      if (drow != nullptr && c * 16 + k < p.N) t += __ldg(drow + c * 16 + k);
       if (c * 16 + k >= p.N) t = -INFINITY;
       mx = fmaxf(mx, t);
       raw[k] = __float_as_uint(t);
@@ -381,7 +383,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
     if (p.af_grid == 14) {
       softmax_af<14>(p, trow, sr_row, smem_u32(smem) + r_local * kPBStrideAF * 4, row, mx, sum);
     } else {
-      softmax_generic(p, trow, sr_row, smem_u32(smem) + r_local * kPBStride * 4, smem_u32(sBias), row_c, mx, sum);
+      const float* drow = p.dense ? p.dense + b * p.dense_sb + head * p.dense_sh + row_c * p.dense_si : nullptr;
+      softmax_generic(p, trow, sr_row, smem_u32(smem) + r_local * kPBStride * 4, smem_u32(sBias), row_c, drow, mx, sum);
     }
     tmem_st_wait();
     tc_fence_before();
@@ -451,8 +454,9 @@ extern "C" int cream_attn_fwd(const cream_attn_desc* d, void* stream_) {
   p.bias = d->bias_pack;
   p.out = static_cast<__nv_bfloat16*>(d->out); p.ldo = d->ld_out;
   p.lse = d->lse;
+  p.dense = d->dense_bias; p.dense_sb = d->dense_stride_b; p.dense_sh = d->dense_stride_h; p.dense_si = d->dense_stride_i;
   // structured AutoFormer gather: square grid + cls, both tables, clamp never binding
-  if (d->af_grid > 0) {
+  if (d->af_grid > 0 && d->dense_bias == nullptr) {
     CB_REQUIRE(d->af_grid * d->af_grid + 1 == d->N && ctx_k && ctx_v && !d->bias_pack, "af mode needs N = g*g+1 and both table packs");
     CB_REQUIRE(2 * d->af_max_rel + 2 <= 32, "af tables must fit 32 packed rows");
     if (d->af_grid == 14 && d->af_max_rel >= d->af_grid - 1) {

@@ -4,8 +4,9 @@
 parameter names `qkv`, `proj`, `rpe_q/rpe_k/rpe_v.lookup_table_{weight,bias}`), with the
 reference's q@k^T + rpe_k(q) gather, softmax, attn@v + rpe_v(attn) executed by ONE kernel.
 Supported: rpe on k and/or v (contextual), bias mode on k, shared or per-head tables, methods
-euclidean / quant / product (<= 64 buckets) and cross (rows + columns tables, contextual);
-rpe on q is the next row of SURVEY.md §8f.
+euclidean / quant / product (<= 64 buckets) and cross (rows + columns tables, contextual).
+iRPE on queries (rpe_q) rides on the kernel's dense additive logit term: its lookup GEMM is a
+library matmul, its gather / scatter-add the library's own rpe_index kernels.
 """
 from __future__ import annotations
 
@@ -57,8 +58,6 @@ class RPEAttention(nn.Module):
                  rpe_on='k', method='product', mode='contextual', shared_head=True, ratio=1.9, skip=1):
         super().__init__()
         assert attn_drop == 0.0, "attention dropout is not supported by the fused kernel"
-        if 'q' in rpe_on:
-            raise NotImplementedError("iRPE on queries is not implemented yet (SURVEY.md §8f row 1)")
         self.num_heads = num_heads
         head_dim = dim // num_heads
         assert head_dim == ops.HEAD_DIM, "fused attention kernel is built for head_dim 64"
@@ -78,7 +77,7 @@ class RPEAttention(nn.Module):
         self.num_buckets = nb
         t_heads = 1 if shared_head else num_heads
         make = IrpeCrossTable if self.cross else IrpeTable
-        self.rpe_q = None
+        self.rpe_q = make(head_dim, t_heads, self.mode, True, nb) if 'q' in rpe_on else None
         self.rpe_k = make(head_dim, t_heads, self.mode, True, nb) if 'k' in rpe_on else None
         self.rpe_v = make(head_dim, t_heads, self.mode, False, nb) if 'v' in rpe_on else None
 
@@ -99,12 +98,13 @@ class RPEAttention(nn.Module):
     def forward(self, x):
         B, N, C = x.shape
         qkv = SlicedLinearFn.apply(x, self.qkv.weight, self.qkv.bias, C, 3 * C, False)   # (B, N, 3C) bf16
-        if self.cross:
-            tabs = [t.rp_rows.table if t is not None else None for t in (self.rpe_k, self.rpe_v)] + \
-                   [t.rp_cols.table if t is not None else None for t in (self.rpe_k, self.rpe_v)]
-        else:
-            tabs = [self.rpe_k.table if self.rpe_k is not None else None,
-                    self.rpe_v.table if self.rpe_v is not None else None, None, None]
-        out = IrpeAttentionFn.apply(qkv, self.num_heads, float(self.scale), self.bucket_ids(N), self.mode, *tabs)
+        pick = (lambda t: t.rp_rows.table) if self.cross else (lambda t: t.table)
+        pick2 = (lambda t: t.rp_cols.table) if self.cross else (lambda t: None)
+        first = [pick(t) if t is not None else None for t in (self.rpe_k, self.rpe_v)]
+        second = [pick2(t) if t is not None else None for t in (self.rpe_k, self.rpe_v)]
+        q1 = pick(self.rpe_q) if self.rpe_q is not None else None
+        q2 = pick2(self.rpe_q) if self.rpe_q is not None else None
+        out = IrpeAttentionFn.apply(qkv, self.num_heads, float(self.scale), self.bucket_ids(N), self.mode,
+                                    *first, *second, q1, q2)
         out = SlicedLinearFn.apply(out, self.proj.weight, self.proj.bias, C, C, False)
         return self.proj_drop(out)

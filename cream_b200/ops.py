@@ -347,6 +347,19 @@ def new_pack(num_tables: int, device) -> torch.Tensor:
 # --------------------------------------------------------------------------------------------
 # attention
 # --------------------------------------------------------------------------------------------
+def _set_dense(d, dense, B, H, N):
+    """dense: fp32 (B|1, H|1, N, N) additive logit term, last dim contiguous; size-1 dims broadcast."""
+    if dense is None:
+        return
+    if dense.dtype != torch.float32 or not dense.is_cuda or dense.dim() != 4 or dense.stride(3) != 1:
+        raise RuntimeError("cream_b200: dense attention bias must be a CUDA fp32 (B|1, H|1, N, N) tensor, last dim contiguous")
+    assert dense.shape[2] == N and dense.shape[3] == N and dense.shape[0] in (1, B) and dense.shape[1] in (1, H)
+    d.dense_bias = _p(dense)
+    d.dense_stride_b = dense.stride(0) if dense.shape[0] > 1 else 0
+    d.dense_stride_h = dense.stride(1) if dense.shape[1] > 1 else 0
+    d.dense_stride_i = dense.stride(2)
+
+
 def _attn_desc(B, H, N, scale, qkv, tk, tv, per_head, idx, bias, af=None):
     d = AttnDesc()
     if af is not None:
@@ -364,12 +377,14 @@ def _attn_desc(B, H, N, scale, qkv, tk, tv, per_head, idx, bias, af=None):
 
 
 def attention_fwd(qkv, B, H, N, scale, *, tk=None, tv=None, per_head=False, idx=(None, None, None, None),
-                  bias=None, need_lse=True, af=None):
-    """Fused attention forward.  qkv: (B*N, 3*H*64) bf16.  Returns (out (B*N, H*64) bf16, lse)."""
+                  bias=None, need_lse=True, af=None, dense=None):
+    """Fused attention forward.  qkv: (B*N, 3*H*64) bf16.  Returns (out (B*N, H*64) bf16, lse).
+    dense: optional fp32 (B|1, H|1, N, N) term added to the logits (see cream_attn_desc.dense_bias)."""
     _check_2d(qkv, torch.bfloat16, "qkv", 8)
     out = empty_bf16(B * N, H * HEAD_DIM, qkv.device)
     lse = torch.empty((B, H, N), dtype=torch.float32, device=qkv.device) if need_lse else None
     d = _attn_desc(B, H, N, scale, qkv, tk, tv, per_head, idx, bias, af)
+    _set_dense(d, dense, B, H, N)
     d.out, d.ld_out, d.lse = _p(out), out.stride(0), _p(lse)
     if PROFILE is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -385,9 +400,10 @@ def attention_fwd(qkv, B, H, N, scale, *, tk=None, tv=None, per_head=False, idx=
 
 
 def attention_bwd(qkv, out, lse, dout, B, H, N, scale, *, tk=None, tv=None, per_head=False,
-                  idx=(None, None, None, None), bias=None, af=None, dtk=None, dtv=None):
+                  idx=(None, None, None, None), bias=None, af=None, dtk=None, dtv=None, dense=None, ddense=None):
     """Returns (dqkv bf16, dtk_pack fp32|None, dtv_pack fp32|None, dbias fp32|None).  dtk / dtv may
-    be caller-provided zeroed (T, 64, 64) fp32 accumulators."""
+    be caller-provided zeroed (T, 64, 64) fp32 accumulators.  With `dense`, pass `ddense` = an fp32
+    (B, H, N, N) tensor to receive the logit gradient dS."""
     _check_2d(dout, torch.bfloat16, "dout", 8)
     dev = qkv.device
     dqkv = empty_bf16(B * N, 3 * H * HEAD_DIM, dev)
@@ -405,6 +421,10 @@ def attention_bwd(qkv, out, lse, dout, B, H, N, scale, *, tk=None, tv=None, per_
     d.dqkv, d.ld_dqkv = _p(dqkv), dqkv.stride(0)
     d.dtk_pack, d.dtv_pack, d.dbias_pack = _p(dtk), _p(dtv), _p(dbias)
     d.workspace, d.workspace_bytes = _p(ws), nbytes
+    _set_dense(d, dense, B, H, N)
+    if ddense is not None:
+        assert ddense.dtype == torch.float32 and ddense.is_contiguous() and tuple(ddense.shape) == (B, H, N, N)
+        d.ddense = _p(ddense)
     check(_lib.load().cream_attn_bwd(C.byref(d), _stream()), "cream_attn_bwd", kernels=2)
     return dqkv, dtk, dtv, dbias
 

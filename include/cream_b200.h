@@ -175,6 +175,15 @@ typedef struct cream_attn_desc {
   float* dtk_pack; float* dtv_pack;    /* fp32 (T, 64, 64) accumulated (+=), caller-zeroed  */
   float* dbias_pack;                   /* fp32 (T, 64) accumulated, or NULL                 */
   void* workspace; int64_t workspace_bytes; /* see cream_attn_bwd_workspace_bytes          */
+  /* ---- optional dense additive logit term (generic gather path only) ----
+   * S[b,h,i,j] += dense_bias[b*stride_b + h*stride_h + i*stride_i + j]  (fp32, j contiguous; a
+   * stride of 0 broadcasts).  Carries what the reference adds to the logits outside the bucket
+   * tables: iRPE on queries, rpe_q(k*scale)^T (rpe_vision_transformer.py:82-83), TinyViT's per-head
+   * attention_biases[:, idxs] (tiny_vit.py:281-283), an additive -inf mask (TinyCLIP text tower,
+   * open_clip/model.py:756-762).  Backward: ddense (fp32, (B,H,N,N) contiguous, may be NULL)
+   * receives dS = P * (dP - delta). */
+  const float* dense_bias; int64_t dense_stride_b, dense_stride_h, dense_stride_i;
+  float* ddense;
 } cream_attn_desc;
 
 int cream_attn_fwd(const cream_attn_desc* desc, void* stream);

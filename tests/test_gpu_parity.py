@@ -323,6 +323,10 @@ IRPE_GPU_CASES = {
     "k_ctx_quant": ("k", "contextual", True, "quant", 1, 5),
     "kv_ctx_cross": ("kv", "contextual", True, "cross", 2, 7),
     "k_ctx_cross_perhead": ("k", "contextual", False, "cross", 2, 14),
+    "qkv_ctx_perhead": ("qkv", "contextual", False, "product", 2, 7),     # deit_*_shared_qkv kind
+    "qk_ctx_shared": ("qk", "contextual", True, "product", 2, 14),
+    "qk_bias": ("qk", "bias", False, "euc", 2, 7),
+    "q_ctx_cross": ("q", "contextual", True, "cross", 1, 5),
 }
 
 
@@ -359,7 +363,7 @@ def test_irpe_attention_module(name):
         hits = [v for k, v in P.items() if k.startswith(f"rpe_{w}.")]     # cross: rp_rows, rp_cols
         return None if not hits else (hits[0] if len(hits) == 1 else tuple(hits))
     ref = vo.rpe_attention(xr, P["qkv.weight"], P["qkv.bias"], P["proj.weight"], P["proj.bias"], heads, ids,
-                           rpe_k=tab("k"), rpe_v=tab("v"), mode=mode)
+                           rpe_q=tab("q"), rpe_k=tab("k"), rpe_v=tab("v"), mode=mode)
     ref.backward(gy.cpu())
     assert rel_err(y.float().cpu(), ref.detach()) < 1e-2
     assert rel_err(x.grad.float().cpu(), xr.grad) < 2e-2
@@ -367,7 +371,7 @@ def test_irpe_attention_module(name):
         assert rel_err(p.grad.float().cpu(), P[pn].grad) < 2e-2, pn
 
 
-@pytest.mark.parametrize("name", ["k_ctx_shared", "kv_ctx_cross"])
+@pytest.mark.parametrize("name", ["k_ctx_shared", "kv_ctx_cross", "qkv_ctx_perhead"])   # qk_bias fixture: head_dim 32
 def test_irpe_attention_golden_k_ctx_shared(golden_dir, name):
     """BASELINE config-2 kind (contextual product on keys, shared head), and the cross method on
     keys and values, against the fixtures written by the reference's own RPEAttention."""
@@ -375,8 +379,8 @@ def test_irpe_attention_golden_k_ctx_shared(golden_dir, name):
     from make_golden import IRPE_CASES
     g = np.load(golden_dir / "irpe_attention.npz")
     rpe_on, mode, shared, method, C, heads, grid = IRPE_CASES[name]
-    m = RPEAttention(C, num_heads=heads, qkv_bias=True, rpe_on=rpe_on, method=method, mode="contextual",
-                     shared_head=shared).cuda()
+    m = RPEAttention(C, num_heads=heads, qkv_bias=True, rpe_on=rpe_on, method=method,
+                     mode="bias" if mode == "bias" else "contextual", shared_head=shared).cuda()
     shapes = {k[len(name) + 7:]: tuple(int(v) for v in g[k]) for k in g.files if k.startswith(name + "_shape_")}
     seed = 100
     with torch.no_grad():
