@@ -527,3 +527,44 @@ def test_attention_structured_matches_generic_full_size():
         res[name] = (out.float(), lse, dqkv.float(), dtk, dtv)
     for a, b, tol in zip(res["generic"], res["structured"], (2e-3, 1e-4, 1e-2, 1e-2, 1e-2)):
         assert rel_err(a.cpu(), b.cpu()) < tol
+
+
+@pytest.mark.parametrize("B,N,h,kind", [(2, 77, 2, "causal"), (3, 50, 2, "per_head"), (2, 197, 3, "full")])
+def test_attention_dense_logit_term(B, N, h, kind):
+    """The dense additive logit term of cream_attn_desc: a causal -inf mask broadcast over batch and
+    heads (TinyCLIP text tower, open_clip/model.py:756-762), a per-head (H, N, N) bias (TinyViT
+    attention_biases[:, idxs], tiny_vit.py:281-283) and a full (B, H, N, N) term, against a plain
+    fp32 PyTorch attention on the same bf16-rounded inputs; dS against autograd."""
+    from cream_b200 import ops
+    torch.manual_seed(21)
+    qkv = bf16r(torch.randn(B, N, 3, h, 64) * 0.7)
+    dout = bf16r(torch.randn(B, N, h, 64))
+    if kind == "causal":
+        dense = torch.full((1, 1, N, N), float("-inf")).triu_(1)
+    elif kind == "per_head":
+        dense = torch.randn(1, h, N, N)
+    else:
+        dense = torch.randn(B, h, N, N)
+    q, k, v = [qkv[:, :, i].permute(0, 2, 1, 3).clone().requires_grad_(True) for i in range(3)]
+    dref = dense.clone().requires_grad_(kind != "causal")
+    att = (torch.matmul(q, k.transpose(-1, -2)) * 0.125 + dref).softmax(-1)
+    ref = torch.matmul(att, v).permute(0, 2, 1, 3)                       # (B, N, h, 64)
+    ref.backward(dout)
+    g = ops.empty_bf16(B * N, 3 * 64 * h)
+    g.copy_(qkv.reshape(B * N, -1).cuda())
+    do = ops.empty_bf16(B * N, 64 * h)
+    do.copy_(dout.reshape(B * N, -1).cuda())
+    dd = dense.cuda().contiguous()
+    out, lse = ops.attention_fwd(g, B, h, N, 0.125, dense=dd)
+    ddense = torch.empty((B, h, N, N), dtype=torch.float32, device="cuda")
+    dqkv, _, _, _ = ops.attention_bwd(g, out, lse, do, B, h, N, 0.125, dense=dd, ddense=ddense)
+    assert rel_err(out.float().cpu().view(B, N, h, 64), ref.detach()) < 4e-3
+    got = dqkv.float().cpu().view(B, N, 3, h, 64)
+    for i, t in enumerate((q, k, v)):
+        assert rel_err(got[:, :, i].permute(0, 2, 1, 3), t.grad) < 1e-2
+    if kind == "causal":
+        assert float(ddense.triu(1).abs().max()) == 0.0              # masked logits receive no gradient
+    else:
+        want = dref.grad if kind == "full" else dref.grad            # autograd already reduced broadcast dims
+        have = ddense.cpu() if kind == "full" else ddense.cpu().sum(0, keepdim=True)
+        assert rel_err(have, want) < 1e-2
