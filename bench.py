@@ -263,7 +263,7 @@ def main():
     ms, flops, attn_flops, launches, _ = timed(K, False, rnd)
     host_enqueue_ms = host_ms[0]
     clocks = sampler.stop() if sampler else None
-    timed(2, True, rnd)
+    timed(3, True, rnd)
     ms_e2e, _, _, _, last_loss = timed(K, True, rnd)
 
     # ---- per-kernel roofline pass (instrumented; separate from the timed region) ----

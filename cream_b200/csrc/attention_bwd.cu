@@ -1,4 +1,3 @@
-#include <cstdlib>
 // Fused attention backward with relative-position terms, sm_100a (tcgen05 + TMEM + TMA).
 //
 // Adjoint of attention_fwd.cu (autograd of AutoFormer/model/module/multihead_super.py:135-154
@@ -10,13 +9,16 @@
 //      thread-local bucket sums  PB[i,b] = sum_j P[i,j][idx_v=b],  dR[i,b] = sum_j dT[i,j][idx_k=b];
 //      dQ = scale * [dT | dR] . [K ; TK]   (tcgen05, A operand from TMEM);
 //      [P | PB] and [dT | dR] (bf16) go to a workspace for the column-form products.
-//  bwd_cols (CTA = head x batch):
+//  bwd_cols (persistent over head x batch):
 //      [dV ; dTV] = [P | PB]^T dO        [dK ; dTK] = scale * [dT | dR]^T Q
-//      (MN-major A operands streamed from the workspace by TMA; table gradients are
-//      accumulated across (batch, head) with fp32 atomics on 64x64 tiles).
+//      (MN-major A operands streamed from the workspace by TMA; the two products run back to
+//      back through one stage ring so each epilogue overlaps the other product's MMAs; table
+//      gradients leave through 256-byte bulk reduce-adds, not per-element atomics).
 //
-// Round-1 note: the workspace round trip (2 x B*H*N*(Npad+64) bf16) costs about 3x the
-// algorithmic bytes of the fused ideal; fusing bwd_cols into bwd_rows is the next step.
+// The workspace round trip (2 x B*H*N*(Npad+64) bf16) costs about 3x the algorithmic bytes of the
+// fused ideal; a single fused kernel needs the dK/dV accumulators of all keys resident (CTA pairs).
+#include <cstdlib>
+
 #include "attention_common.cuh"
 
 namespace cb {
@@ -237,7 +239,6 @@ __device__ __forceinline__ void bwd_row_af(const BwdRowsParams& p, const RowCtx&
         d = pr * (__uint_as_float(rp[k]) + g_first);
         pf = pr; df = d;
       } else {
-        constexpr int kDummy = 0; (void)kDummy;
         const int rj = (j0 - 1) / G, cj = (j0 - 1) % G;
         pr = fast_exp2(fmaf(sl, __uint_as_float(rt[k]), rv[rj]) + rh[cj]);
         d = pr * (__uint_as_float(rp[k]) + gv[rj] + gh[cj]);

@@ -71,10 +71,10 @@ class GradBuckets:
 
 class StagedBatch:
     """A batch whose host->device copy is in flight on the trainer's copy stream."""
-    __slots__ = ("images", "targets", "ready")
+    __slots__ = ("images", "targets", "ready", "slot")
 
-    def __init__(self, images, targets, ready):
-        self.images, self.targets, self.ready = images, targets, ready
+    def __init__(self, images, targets, ready, slot=-1):
+        self.images, self.targets, self.ready, self.slot = images, targets, ready, slot
 
 
 class SupernetTrainer:
@@ -97,6 +97,10 @@ class SupernetTrainer:
                                             {"params": no_decay, "weight_decay": 0.0}], lr=lr, fused=model.pos_embed.is_cuda)
         self.comm_stream = torch.cuda.Stream() if (self.world > 1 and model.pos_embed.is_cuda) else None
         self.copy_stream = torch.cuda.Stream() if model.pos_embed.is_cuda else None
+        # two persistent device staging slots (no allocator traffic, hence no cudaMalloc, in steady state)
+        self._slots = [None, None]
+        self._slot_free = [None, None]      # event: the step that consumed the slot has read it
+        self._next_slot = 0
         self.last_config: Optional[dict] = None
 
     # ------------------------------------------------------------------------------------
@@ -136,12 +140,24 @@ class SupernetTrainer:
         dev = self.model.pos_embed.device
         if self.copy_stream is None or images.is_cuda:
             return StagedBatch(images.to(dev), targets.to(dev), None)
+        i = self._next_slot
+        self._next_slot ^= 1
+        slot = self._slots[i]
+        if slot is None or slot[0].shape != images.shape or slot[0].dtype != images.dtype or \
+                slot[1].shape != targets.shape or slot[1].dtype != targets.dtype:
+            slot = (torch.empty(images.shape, dtype=images.dtype, device=dev),
+                    torch.empty(targets.shape, dtype=targets.dtype, device=dev))
+            self._slots[i] = slot
+            self._slot_free[i] = None
+            self.copy_stream.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(self.copy_stream):
-            di = images.to(dev, non_blocking=True)
-            dt = targets.to(dev, non_blocking=True)
+            if self._slot_free[i] is not None:
+                self.copy_stream.wait_event(self._slot_free[i])     # the previous user of the slot has read it
+            slot[0].copy_(images, non_blocking=True)
+            slot[1].copy_(targets, non_blocking=True)
             ready = torch.cuda.Event()
             ready.record(self.copy_stream)
-        return StagedBatch(di, dt, ready)
+        return StagedBatch(slot[0], slot[1], ready, i)
 
     def step(self, images, targets: Optional[torch.Tensor] = None, config: Optional[dict] = None,
              rnd=random) -> torch.Tensor:
@@ -149,13 +165,10 @@ class SupernetTrainer:
         `images` is a tensor (host or device) or a StagedBatch from `stage`."""
         model = self.model
         dev = model.pos_embed.device
-        if isinstance(images, StagedBatch):
-            staged = images
+        staged = images if isinstance(images, StagedBatch) else None
+        if staged is not None:
             if staged.ready is not None:
-                cur = torch.cuda.current_stream()
-                cur.wait_event(staged.ready)
-                staged.images.record_stream(cur)
-                staged.targets.record_stream(cur)
+                torch.cuda.current_stream().wait_event(staged.ready)
             images, targets = staged.images, staged.targets
         else:
             images = images.to(dev, non_blocking=True)
@@ -168,6 +181,10 @@ class SupernetTrainer:
         lg = logits.detach().requires_grad_(True)
         loss = F.cross_entropy(lg, targets)
         (dlogits,) = torch.autograd.grad(loss, lg)
+        if staged is not None and staged.slot >= 0:      # images (im2col) and targets (loss) have been consumed
+            ev = torch.cuda.Event()
+            ev.record()
+            self._slot_free[staged.slot] = ev
         self._backward(saved, dlogits)
         self.optimizer.step()
         return loss.detach()
