@@ -248,12 +248,16 @@ def main():
     # subnet once each, so the caching allocator owns its pools before any timed or warm-up step
     # (the search space changes every activation shape from step to step).
     ss = SEARCH_SPACE["S"]
-    for pick in (max, min):
-        d = pick(ss["depth"])
-        trainer.step(dev_imgs[0], dev_tgts[0], config={"layer_num": d, "embed_dim": [pick(ss["embed_dim"])] * d,
-                                                       "num_heads": [pick(ss["num_heads"])] * d,
-                                                       "mlp_ratio": [pick(ss["mlp_ratio"])] * d})
+    prime = random.Random(12345)
+    for e in sorted(ss["embed_dim"], reverse=True):
+        for pick in (max, min):
+            d = pick(ss["depth"])
+            trainer.step(dev_imgs[0], dev_tgts[0], config={"layer_num": d, "embed_dim": [e] * d,
+                                                           "num_heads": [pick(ss["num_heads"])] * d,
+                                                           "mlp_ratio": [pick(ss["mlp_ratio"])] * d})
+        trainer.step(dev_imgs[0], dev_tgts[0], rnd=prime)      # one mixed (per-layer h, r) subnet
     torch.cuda.synchronize()
+    segments0 = torch.cuda.memory_stats().get("segment.all.allocated", 0)
     # identical config stream on every rank (supernet_engine.py:36 seeds `random` with the epoch)
     rnd = random.Random(0)
     timed(W, False, rnd)                                   # warm-up (untimed)
@@ -322,6 +326,7 @@ def main():
         "e2e": {"value": imgs / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": B * 3 * 224 * 224 * 4 + B * 8,
                 "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / K, "last_loss": last_loss},
         "gpu_launches": launches,
+        "allocator_segments_grown_after_priming": torch.cuda.memory_stats().get("segment.all.allocated", 0) - segments0,
         "host_enqueue_ms_per_step": host_enqueue_ms,
         "clocks": clocks,
         "roofline": roofline,
