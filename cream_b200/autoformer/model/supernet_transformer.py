@@ -278,15 +278,17 @@ class Vision_TransformerSuper(nn.Module):
     def _drop_path_scales(self, batch, device):
         if not self.training or all(b.drop_path_prob == 0.0 for b in self.blocks):
             return None
-        scales = []
-        for blk in self.blocks[:self.sample_layer_num]:
-            if blk.drop_path_prob == 0.0:
-                scales.append(None)
-                continue
-            a = drop_path_scale(batch, blk.drop_path_prob, True, device)
-            f = drop_path_scale(batch, blk.drop_path_prob, True, device)
-            scales.append(torch.stack([a, f]).contiguous())
-        return scales
+        # floor(keep + U[0,1)) / keep per layer, branch and sample (model/utils.py:71-87), drawn for all
+        # sampled layers in one shot: 4 small launches per step instead of 9 per layer
+        blocks = self.blocks[:self.sample_layer_num]
+        key = (tuple(b.drop_path_prob for b in blocks), str(device))
+        cache = self.__dict__.setdefault("_keep_cache", {})
+        keep = cache.get(key)
+        if keep is None:
+            keep = torch.tensor([1.0 - q for q in key[0]], dtype=torch.float32).view(-1, 1, 1).to(device)
+            cache[key] = keep
+        all_scales = torch.floor(keep + torch.rand(len(blocks), 2, batch, dtype=torch.float32, device=device)) / keep
+        return [None if b.drop_path_prob == 0.0 else all_scales[i] for i, b in enumerate(blocks)]
 
     def forward(self, x):
         assert self.sample_config is not None, "call set_sample_config(config) first"

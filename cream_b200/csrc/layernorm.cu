@@ -132,21 +132,21 @@ ln_bwd_kernel(const void* __restrict__ dy, int64_t lddy, const float* __restrict
 // resident warps per SM the kernel lives on memory-level parallelism inside a warp, and a
 // load/accumulate interleaving serialises one DRAM round trip per element (measured: 12 % of HBM).
 template <bool kDyF32, int kV>
-__global__ void __launch_bounds__(kBwdWarps * 32)
+__global__ void __launch_bounds__(kBwdWarps * 32, kV <= 3 ? 4 : 3)   // E <= 384: 16 warps / SM without spills
 ln_bwd_vec_kernel(const void* __restrict__ dy, int64_t lddy, const float* __restrict__ x, int64_t ldx,
                   const float* __restrict__ gamma, const float* __restrict__ mean,
                   const float* __restrict__ rstd, const float* __restrict__ resid_grad, int64_t ldrg,
                   float* __restrict__ dx, int64_t lddx, float* __restrict__ dgamma,
                   float* __restrict__ dbeta, int64_t rows, int E) {
-  extern __shared__ float sacc[];  // [2][E]
+  extern __shared__ float sacc[];  // [2][E] partial sums, then gamma [E] (kept out of the register file)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* sgam = sacc + 2 * E;
   for (int i = threadIdx.x; i < 2 * E; i += blockDim.x) sacc[i] = 0.f;
+  for (int i = threadIdx.x; i < E; i += blockDim.x) sgam[i] = __ldg(gamma + i);
   __syncthreads();
-  float4 gm[kV], pg[kV], pb[kV];
+  float4 pg[kV], pb[kV];
 #pragma unroll
   for (int i = 0; i < kV; ++i) {
-    const int c = 4 * (lane + 32 * i);
-    gm[i] = c < E ? __ldg(reinterpret_cast<const float4*>(gamma + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
     pg[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     pb[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
@@ -184,7 +184,8 @@ ln_bwd_vec_kernel(const void* __restrict__ dy, int64_t lddy, const float* __rest
         xh.x = (xh.x - mu) * rs; xh.y = (xh.y - mu) * rs; xh.z = (xh.z - mu) * rs; xh.w = (xh.w - mu) * rs;
         pg[i].x += dv[i].x * xh.x; pg[i].y += dv[i].y * xh.y; pg[i].z += dv[i].z * xh.z; pg[i].w += dv[i].w * xh.w;
         pb[i].x += dv[i].x; pb[i].y += dv[i].y; pb[i].z += dv[i].z; pb[i].w += dv[i].w;
-        dv[i].x *= gm[i].x; dv[i].y *= gm[i].y; dv[i].z *= gm[i].z; dv[i].w *= gm[i].w;
+        const float4 gm = *reinterpret_cast<const float4*>(sgam + c);
+        dv[i].x *= gm.x; dv[i].y *= gm.y; dv[i].z *= gm.z; dv[i].w *= gm.w;
         s1 += dv[i].x + dv[i].y + dv[i].z + dv[i].w;
         s2 += dv[i].x * xh.x + dv[i].y * xh.y + dv[i].z * xh.z + dv[i].w * xh.w;
       }
@@ -248,9 +249,9 @@ extern "C" int cream_layernorm_bwd(const void* dy, int64_t lddy, int dy_f32, con
   CB_REQUIRE(E >= 1 && E <= 32 * kMaxPerLane, "embed dim must be <= 768");
   // few, fat blocks: every block ends with 2*E global atomics, so the block count bounds the
   // per-address contention on dgamma / dbeta (1184 blocks made this kernel 4x slower than HBM)
-  const int grid = static_cast<int>(std::min<int64_t>(ceil_div64(rows, kBwdWarps), kNumSMs * 3));
+  const int grid = static_cast<int>(std::min<int64_t>(ceil_div64(rows, kBwdWarps), kNumSMs * 4));
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  const size_t smem = 2 * E * sizeof(float);
+  const size_t smem = 3 * E * sizeof(float);
   const bool vec_ok = (E % 4 == 0) && (ldx % 4 == 0) && (lddx % 4 == 0) && (lddy % 4 == 0) &&
                       (resid_grad == nullptr || ldrg % 4 == 0) &&
                       ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dx) | reinterpret_cast<uintptr_t>(dy) |

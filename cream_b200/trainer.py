@@ -55,9 +55,16 @@ class GradBuckets:
                 self.groups["embed"].append(name)
         self.flat: Dict[str, torch.Tensor] = {}
         self.views: Dict[str, torch.Tensor] = {}
+        # one master buffer (a single memset per step), one contiguous 256-byte aligned span per group
+        # (the unit of all-reduce), parameters at 16-byte aligned offsets inside it
+        sizes = {g: (sum((named[n].numel() + 3) // 4 * 4 for n in names) + 63) // 64 * 64
+                 for g, names in self.groups.items()}
+        dev = next(iter(named.values())).device
+        self.master = torch.zeros(sum(sizes.values()), dtype=torch.float32, device=dev)
+        base = 0
         for gname, names in self.groups.items():
-            total = sum((named[n].numel() + 3) // 4 * 4 for n in names)
-            buf = torch.zeros(total, dtype=torch.float32, device=named[names[0]].device)
+            buf = self.master[base:base + sizes[gname]]
+            base += sizes[gname]
             off = 0
             for n in names:
                 p = named[n]
@@ -120,9 +127,7 @@ class SupernetTrainer:
         """engine.backward with per-layer bucket all-reduce interleaved."""
         cfg = saved.config
         names = engine.sampled_param_names(self.geo, cfg)
-        used = {"embed", "head"} | {self.buckets.group_of_layer(i) for i in range(cfg["layer_num"])}
-        for g in used:
-            self.buckets.flat[g].zero_()
+        self.buckets.master.zero_()          # one memset (140 MB for supernet-S, ~25 us) instead of one per group
         G = {n: self.buckets.views[n] for n in names}
         engine.backward(self.params, self.geo, saved, dlogits, grads=G,
                         on_group_done=self._allreduce if self.world > 1 else None)
