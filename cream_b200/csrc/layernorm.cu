@@ -61,6 +61,64 @@ ln_fwd_kernel(const float* __restrict__ x, int64_t ldx, const float* __restrict_
   }
 }
 
+// Vector twin of ln_fwd_kernel for E % 4 == 0 and 16-byte aligned rows: one 16-byte load and one
+// 8-byte (bf16) / 16-byte (fp32) store per lane and 128 columns, all loads of a row in flight before
+// the first reduction.  (The scalar kernel moves 4 / 2 bytes per lane per instruction.)
+template <bool kOutF32, int kV>
+__global__ void __launch_bounds__(kWarps * 32)
+ln_fwd_vec_kernel(const float* __restrict__ x, int64_t ldx, const float* __restrict__ gamma,
+                  const float* __restrict__ beta, float eps, void* __restrict__ out, int64_t ldo,
+                  float* __restrict__ mean, float* __restrict__ rstd, int64_t rows, int E) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const float invE = 1.0f / E;
+  for (int64_t r = static_cast<int64_t>(blockIdx.x) * kWarps + warp; r < rows;
+       r += static_cast<int64_t>(gridDim.x) * kWarps) {
+    const float* xr = x + r * ldx;
+    float4 v[kV];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < kV; ++i) {
+      const int c = 4 * (lane + 32 * i);
+      v[i] = c < E ? __ldg(reinterpret_cast<const float4*>(xr + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int i = 0; i < kV; ++i) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    const float mu = warp_sum(s) * invE;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < kV; ++i) {
+      const int c = 4 * (lane + 32 * i);
+      if (c < E) {
+        v[i].x -= mu; v[i].y -= mu; v[i].z -= mu; v[i].w -= mu;
+        q += v[i].x * v[i].x + v[i].y * v[i].y + v[i].z * v[i].z + v[i].w * v[i].w;
+      }
+    }
+    const float rs = rsqrtf(warp_sum(q) * invE + eps);
+    if (lane == 0) {
+      if (mean) mean[r] = mu;
+      if (rstd) rstd[r] = rs;
+    }
+#pragma unroll
+    for (int i = 0; i < kV; ++i) {
+      const int c = 4 * (lane + 32 * i);
+      if (c < E) {
+        const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + c));
+        const float4 b = __ldg(reinterpret_cast<const float4*>(beta + c));
+        const float y0 = fmaf(v[i].x * rs, g.x, b.x), y1 = fmaf(v[i].y * rs, g.y, b.y);
+        const float y2 = fmaf(v[i].z * rs, g.z, b.z), y3 = fmaf(v[i].w * rs, g.w, b.w);
+        if (kOutF32) {
+          *reinterpret_cast<float4*>(static_cast<float*>(out) + r * ldo + c) = make_float4(y0, y1, y2, y3);
+        } else {
+          uint2 o;
+          o.x = pack_bf16x2(y0, y1);
+          o.y = pack_bf16x2(y2, y3);
+          *reinterpret_cast<uint2*>(static_cast<__nv_bfloat16*>(out) + r * ldo + c) = o;
+        }
+      }
+    }
+  }
+}
+
 // dX = resid_grad + rstd * (dy*g - mean(dy*g) - xhat * mean(dy*g*xhat)); dgamma/dbeta via
 // per-lane register partials -> shared -> global atomics.
 constexpr int kBwdWarps = 4;
@@ -231,6 +289,23 @@ extern "C" int cream_layernorm_fwd(const float* x, int64_t ldx, const float* gam
   CB_REQUIRE(E >= 1 && E <= 32 * kMaxPerLane, "embed dim must be <= 768");
   const int grid = static_cast<int>(std::min<int64_t>(ceil_div64(rows, kWarps), kNumSMs * 16));
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  const bool vec = (E & 3) == 0 && (ldx & 3) == 0 && (ldo & 3) == 0 && E <= 768 &&
+                   ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(out) |
+                     reinterpret_cast<uintptr_t>(gamma) | reinterpret_cast<uintptr_t>(beta)) & 15) == 0;
+  if (vec) {
+#define CB_LN_FWD_VEC(F32, V) \
+  ln_fwd_vec_kernel<F32, V><<<grid, kWarps * 32, 0, stream>>>(x, ldx, gamma, beta, eps, out, ldo, mean, rstd, rows, E)
+    const int v = ceil_div(E, 128);
+    if (out_f32) {
+      if (v <= 2) CB_LN_FWD_VEC(true, 2); else if (v == 3) CB_LN_FWD_VEC(true, 3);
+      else if (v == 4) CB_LN_FWD_VEC(true, 4); else CB_LN_FWD_VEC(true, 6);
+    } else {
+      if (v <= 2) CB_LN_FWD_VEC(false, 2); else if (v == 3) CB_LN_FWD_VEC(false, 3);
+      else if (v == 4) CB_LN_FWD_VEC(false, 4); else CB_LN_FWD_VEC(false, 6);
+    }
+#undef CB_LN_FWD_VEC
+    return check_last("ln_fwd_vec_kernel");
+  }
 #define CB_LN_FWD(F32, PER) \
   ln_fwd_kernel<F32, PER><<<grid, kWarps * 32, 0, stream>>>(x, ldx, gamma, beta, eps, out, ldo, mean, rstd, rows, E)
   if (out_f32) { if (E <= 256) CB_LN_FWD(true, 8); else if (E <= 512) CB_LN_FWD(true, 16); else CB_LN_FWD(true, 24); }
