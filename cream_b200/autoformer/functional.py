@@ -330,3 +330,35 @@ class IrpeAttentionFn(torch.autograd.Function):
             else:
                 ops.unpack_table_grads(dtv, T, gv, gv.shape[1], 0, (gv.stride(0), gv.stride(1), gv.stride(2)))
         return dqkv.reshape(B, N, -1).to(dtype), None, None, None, None, gk, gv, gk2, gv2, gq, gq2
+
+
+class DenseAttentionFn(torch.autograd.Function):
+    """softmax(scale * q k^T + dense) v with the fused kernel; qkv (B, N, 3*64h) in the reference's
+    [q | k | v] column order, dense an optional fp32 (B|1, H|1, N, N) additive logit term (mask or
+    bias).  Returns (B, N, 64h).  The gradient of `dense` is produced only when it requires grad."""
+
+    @staticmethod
+    def forward(ctx, qkv, heads, scale, dense):
+        B, N, W3 = qkv.shape
+        assert W3 == 3 * ops.HEAD_DIM * heads
+        qkv2 = ops.as_bf16_2d(qkv)
+        out, lse = ops.attention_fwd(qkv2, B, heads, N, scale, dense=dense)
+        ctx.save_for_backward(qkv2, out, lse, dense)
+        ctx.meta = (B, heads, N, scale, qkv.dtype, dense is not None and dense.requires_grad)
+        return out.reshape(B, N, ops.HEAD_DIM * heads)
+
+    @staticmethod
+    def backward(ctx, dout):
+        qkv2, out, lse, dense = ctx.saved_tensors
+        B, heads, N, scale, dtype, want = ctx.meta
+        ddense = torch.empty((B, heads, N, N), dtype=torch.float32, device=qkv2.device) if want else None
+        dqkv, _, _, _ = ops.attention_bwd(qkv2, out, lse, ops.as_bf16_2d(dout), B, heads, N, scale,
+                                          dense=dense, ddense=ddense)
+        gd = None
+        if want:
+            gd = ddense
+            if dense.shape[0] == 1:
+                gd = gd.sum(0, keepdim=True)
+            if dense.shape[1] == 1:
+                gd = gd.sum(1, keepdim=True)
+        return dqkv.reshape(B, N, -1).to(dtype), None, None, gd

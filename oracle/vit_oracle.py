@@ -297,3 +297,26 @@ def rpe_attention(x, qkv_w, qkv_b, proj_w, proj_b, num_heads: int, bucket_ids,
         return out
     x = out.transpose(1, 2).reshape(B, N, C)
     return F.linear(x, proj_w, proj_b)
+
+
+def clip_attention(x, in_proj_weight, in_proj_bias, out_w, out_b, n_head: int, attn_mask=None,
+                   head_z=None, hidden_z=None):
+    """TinyCLIP ResidualAttentionBlock.attention, TinyCLIP/src/open_clip/model.py:238-283 (the naive
+    branch, which also documents what the nn.MultiheadAttention branch computes).  x is
+    (length, batch, embed) — the reference's LND layout; attn_mask an additive (length, length)
+    float mask (text tower: -inf above the diagonal, model.py:756-762)."""
+    length, batch, d_model = x.shape
+    ws, bs = in_proj_weight.chunk(3), in_proj_bias.chunk(3)
+    dph = ws[0].shape[0] // n_head
+    q, k, v = [F.linear(x, w, b) for w, b in zip(ws, bs)]
+    q, k, v = [t.reshape(length, batch * n_head, -1).transpose(0, 1) for t in (q, k, v)]
+    sim = (q * dph ** -0.5) @ k.transpose(1, 2)
+    if attn_mask is not None:
+        sim = sim + attn_mask
+    out = torch.softmax(sim, -1) @ v
+    if head_z is not None:
+        out = (out.view(batch, n_head, length, dph) * head_z.view(1, -1, 1, 1)).view(batch * n_head, length, dph)
+    out = F.linear(out.transpose(0, 1).reshape(length, batch, -1), out_w, out_b)
+    if hidden_z is not None:
+        out = out * hidden_z
+    return out

@@ -568,3 +568,33 @@ def test_attention_dense_logit_term(B, N, h, kind):
         want = dref.grad if kind == "full" else dref.grad            # autograd already reduced broadcast dims
         have = ddense.cpu() if kind == "full" else ddense.cpu().sum(0, keepdim=True)
         assert rel_err(have, want) < 1e-2
+
+
+@pytest.mark.parametrize("L,B,heads,causal,prune", [(50, 4, 2, False, False), (77, 3, 2, True, False), (77, 2, 2, True, True)])
+def test_clip_attention_module(L, B, heads, causal, prune):
+    """TinyCLIP ResidualAttentionBlock.attention mirror (LND layout, in_proj chunking, causal additive
+    mask, head_z / hidden_z multipliers) against the oracle restatement of model.py:238-283."""
+    from cream_b200.clip_attention import ClipAttention
+    E = 64 * heads
+    torch.manual_seed(31)
+    m = ClipAttention(E, heads).cuda()
+    with torch.no_grad():
+        for p in m.parameters():
+            p.copy_(bf16r(torch.randn(p.shape) * 0.08))
+    x = bf16r(torch.randn(L, B, E)).cuda().requires_grad_(True)
+    gy = bf16r(torch.randn(L, B, E)).cuda()
+    mask = torch.full((L, L), float("-inf")).triu_(1) if causal else None
+    head_z = bf16r(torch.rand(1, heads, 1, 1)) if prune else None
+    hidden_z = bf16r(torch.rand(E)) if prune else None
+    y = m(x, mask.cuda() if causal else None, head_z=head_z.cuda() if prune else None,
+          hidden_z=hidden_z.cuda() if prune else None)
+    y.backward(gy.to(y.dtype))
+    P = {k: v.detach().cpu().clone().requires_grad_(True) for k, v in m.named_parameters()}
+    xr = x.detach().cpu().clone().requires_grad_(True)
+    ref = vo.clip_attention(xr, P["in_proj_weight"], P["in_proj_bias"], P["out_proj.weight"], P["out_proj.bias"],
+                            heads, mask, head_z, hidden_z)
+    ref.backward(gy.cpu())
+    assert rel_err(y.float().cpu(), ref.detach()) < 1e-2
+    assert rel_err(x.grad.float().cpu(), xr.grad) < 2e-2
+    for pn, p in m.named_parameters():
+        assert rel_err(p.grad.float().cpu(), P[pn].grad) < 2e-2, pn

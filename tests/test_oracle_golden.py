@@ -155,3 +155,23 @@ def test_irpe_attention_oracle_matches_reference(golden_dir, name):
     check_summary(g, f"{name}_gx", x.grad, 1e-4)
     for pn, p in params.items():
         check_summary(g, f"{name}_grad_{pn}", p.grad, 1e-4, what=f"{name} grad {pn}")
+
+
+@pytest.mark.parametrize("L,B,heads,causal", [(50, 3, 2, False), (77, 2, 2, True)])
+def test_clip_attention_oracle_matches_torch_mha(L, B, heads, causal):
+    """The TinyCLIP attention restatement against nn.MultiheadAttention — the call the reference's
+    default branch makes (open_clip/model.py:246-248) — forward and input gradient."""
+    E = 64 * heads
+    torch.manual_seed(5)
+    mha = torch.nn.MultiheadAttention(E, heads)
+    x = torch.randn(L, B, E, requires_grad=True)
+    mask = torch.full((L, L), float("-inf")).triu_(1) if causal else None
+    ref = mha(x, x, x, need_weights=False, attn_mask=mask)[0]
+    gy = torch.randn_like(ref)
+    ref.backward(gy)
+    x2 = x.detach().clone().requires_grad_(True)
+    y = vo.clip_attention(x2, mha.in_proj_weight, mha.in_proj_bias, mha.out_proj.weight, mha.out_proj.bias,
+                          heads, mask)
+    y.backward(gy)
+    assert torch.allclose(y, ref, atol=2e-5, rtol=1e-4)
+    assert torch.allclose(x2.grad, x.grad, atol=2e-5, rtol=1e-4)
