@@ -1,0 +1,63 @@
+"""TinyViT window attention on the fused B200 kernel.
+
+`Attention` mirrors TinyViT/models/tiny_vit.py:215-286 (constructor signature, parameter names
+`norm`, `qkv`, `proj`, `attention_biases`, buffer `attention_bias_idxs`, the `(B, N, C)` interface
+where B already counts windows).  LayerNorm, the qkv / proj linears and the attention core are the
+library's kernels; the per-head scalar bias `attention_biases[:, idxs]` enters the core through the
+kernel's dense additive logit term and receives its gradient from it.
+
+TinyViT uses head_dim 32 (key_dim 32, attn_ratio 1); the fused kernel is built for 64, so q, k, v
+are zero-padded to 64 channels per head (q·k and P·v are unchanged by zero channels).  A native
+32-wide variant with several 7x7 windows per CTA is the next step.
+"""
+from __future__ import annotations
+
+import itertools
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import ops
+from .autoformer.functional import DenseAttentionFn, SlicedLayerNormFn, SlicedLinearFn
+
+
+class Attention(nn.Module):
+    def __init__(self, dim, key_dim, num_heads=8, attn_ratio=4, resolution=(14, 14)):
+        super().__init__()
+        assert isinstance(resolution, tuple) and len(resolution) == 2
+        self.num_heads, self.key_dim = num_heads, key_dim
+        self.scale = key_dim ** -0.5
+        self.nh_kd = key_dim * num_heads
+        self.d = int(attn_ratio * key_dim)
+        self.dh = self.d * num_heads
+        self.attn_ratio = attn_ratio
+        assert key_dim <= ops.HEAD_DIM and self.d <= ops.HEAD_DIM, "per-head widths above 64 are not supported"
+        assert resolution[0] * resolution[1] <= 208, "at most 208 tokens per window"
+        self.norm = nn.LayerNorm(dim)
+        self.qkv = nn.Linear(dim, self.dh + 2 * self.nh_kd)
+        self.proj = nn.Linear(self.dh, dim)
+        points = list(itertools.product(range(resolution[0]), range(resolution[1])))
+        offsets, idxs = {}, []
+        for p1 in points:                                   # tiny_vit.py:237-247, same numbering order
+            for p2 in points:
+                off = (abs(p1[0] - p2[0]), abs(p1[1] - p2[1]))
+                if off not in offsets:
+                    offsets[off] = len(offsets)
+                idxs.append(offsets[off])
+        n = len(points)
+        self.attention_biases = nn.Parameter(torch.zeros(num_heads, len(offsets)))
+        self.register_buffer("attention_bias_idxs", torch.LongTensor(idxs).view(n, n), persistent=False)
+
+    def forward(self, x):  # x (B, N, C)
+        B, N, C = x.shape
+        H, kd, d, D = self.num_heads, self.key_dim, self.d, ops.HEAD_DIM
+        x = SlicedLayerNormFn.apply(x.float(), self.norm.weight, self.norm.bias, C, self.norm.eps)
+        qkv = SlicedLinearFn.apply(x, self.qkv.weight, self.qkv.bias, C, self.qkv.out_features, False)
+        q, k, v = qkv.view(B, N, H, -1).split([kd, kd, d], dim=3)
+        # reference column order per head is [q | k | v]; the kernel wants (B, N, 3, H, 64)
+        packed = torch.stack([F.pad(q, (0, D - kd)), F.pad(k, (0, D - kd)), F.pad(v, (0, D - d))], dim=2)
+        dense = self.attention_biases[:, self.attention_bias_idxs].float().unsqueeze(0)      # (1, H, N, N)
+        out = DenseAttentionFn.apply(packed.reshape(B, N, 3 * H * D), H, float(self.scale), dense.contiguous())
+        out = out.view(B, N, H, D)[..., :d].reshape(B, N, self.dh)
+        return SlicedLinearFn.apply(out, self.proj.weight, self.proj.bias, self.dh, self.proj.out_features, False)

@@ -320,3 +320,34 @@ def clip_attention(x, in_proj_weight, in_proj_bias, out_w, out_b, n_head: int, a
     if hidden_z is not None:
         out = out * hidden_z
     return out
+
+
+def tinyvit_bias_idxs(resolution):
+    """attention_bias_idxs of TinyViT Attention.__init__, TinyViT/models/tiny_vit.py:237-252: offsets
+    (|dr|, |dc|) numbered in first-seen order over the row-major point pairs; returns (idxs (N, N)
+    int64, number of distinct offsets)."""
+    import itertools
+    points = list(itertools.product(range(resolution[0]), range(resolution[1])))
+    offsets, idxs = {}, []
+    for p1 in points:
+        for p2 in points:
+            off = (abs(p1[0] - p2[0]), abs(p1[1] - p2[1]))
+            if off not in offsets:
+                offsets[off] = len(offsets)
+            idxs.append(offsets[off])
+    n = len(points)
+    return torch.tensor(idxs, dtype=torch.long).view(n, n), len(offsets)
+
+
+def tinyvit_attention(x, P, num_heads: int, key_dim: int, d: int, idxs, eps: float = 1e-5):
+    """TinyViT Attention.forward, TinyViT/models/tiny_vit.py:262-286.  P: norm.{weight,bias},
+    qkv.{weight,bias}, proj.{weight,bias}, attention_biases (heads, n_offsets)."""
+    B, N, C = x.shape
+    x = F.layer_norm(x, (C,), P["norm.weight"], P["norm.bias"], eps)
+    qkv = F.linear(x, P["qkv.weight"], P["qkv.bias"])
+    q, k, v = qkv.view(B, N, num_heads, -1).split([key_dim, key_dim, d], dim=3)
+    q, k, v = q.permute(0, 2, 1, 3), k.permute(0, 2, 1, 3), v.permute(0, 2, 1, 3)
+    attn = (q @ k.transpose(-2, -1)) * key_dim ** -0.5 + P["attention_biases"][:, idxs]
+    attn = attn.softmax(dim=-1)
+    x = (attn @ v).transpose(1, 2).reshape(B, N, num_heads * d)
+    return F.linear(x, P["proj.weight"], P["proj.bias"])

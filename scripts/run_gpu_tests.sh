@@ -4,7 +4,7 @@ cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 LOG=gpurun_out/gpu_tests.log
 : > $LOG
-GROUPS_=${@:-"rpe_index sliced_or_gemm layernorm attention_autoformer attention_full_or_structured irpe supernet_vs_golden fused_matches supernet_s cpu_tensors dense_logit clip_attention"}
+GROUPS_=${@:-"rpe_index sliced_or_gemm layernorm attention_autoformer attention_full_or_structured irpe supernet_vs_golden fused_matches supernet_s cpu_tensors dense_logit clip_attention tinyvit"}
 for g in $GROUPS_; do
   k=$(echo $g | sed 's/_or_/ or /g')
   echo "===== group: $k" >> $LOG

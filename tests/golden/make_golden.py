@@ -75,7 +75,7 @@ def install_shims():
     mod("timm")
     mod("timm.data", IMAGENET_DEFAULT_MEAN=(0.485, 0.456, 0.406), IMAGENET_DEFAULT_STD=(0.229, 0.224, 0.225))
     mod("timm.models")
-    mod("timm.models.helpers", load_pretrained=lambda *a, **k: None)
+    mod("timm.models.helpers", load_pretrained=lambda *a, **k: None, build_model_with_cfg=lambda *a, **k: None)
     mod("timm.models.layers", DropPath=_Stub, to_2tuple=lambda x: (x, x),
         trunc_normal_=torch.nn.init.trunc_normal_)
     mod("timm.models.resnet", resnet26d=None, resnet50d=None)
@@ -241,6 +241,49 @@ def golden_irpe_attention():
     print("irpe_attention.npz", len(out), "arrays")
 
 
+TINYVIT_CASES = {
+    # name: (dim, key_dim, heads, attn_ratio, resolution, batch)
+    "win7": (64, 32, 2, 1, (7, 7), 6),        # 7 x 7 windows (TinyViT stages 2-3; batch = B * windows)
+    "full14": (128, 32, 4, 1, (14, 14), 2),   # 14 x 14, the last-stage resolution at 224 / 16
+}
+
+
+def golden_tinyvit_attention():
+    """TinyViT/models/tiny_vit.py:215-286 `Attention` (LayerNorm -> qkv -> per-head bias gather ->
+    softmax -> proj), imported unmodified (timm stubbed)."""
+    sys.path.insert(0, str(REF / "TinyViT"))
+    from models.tiny_vit import Attention  # reference, unmodified
+
+    out = {}
+    for name, (dim, key_dim, heads, ratio, res, B) in TINYVIT_CASES.items():
+        attn = Attention(dim, key_dim, heads, attn_ratio=ratio, resolution=res)
+        attn.train()
+        seed = 300
+        with torch.no_grad():
+            for pn, p in attn.named_parameters():
+                seed += 1
+                if pn == "norm.weight":
+                    p.copy_(1.0 + rand(tuple(p.shape), seed, 0.1))
+                else:
+                    p.copy_(rand(tuple(p.shape), seed, 0.5 if "attention_biases" in pn else 0.08))
+        N = res[0] * res[1]
+        x = rand((B, N, dim), 299).requires_grad_(True)
+        gy = rand((B, N, dim), 298)
+        y = attn(x)
+        y.backward(gy)
+        out[f"{name}_idxs"] = attn.attention_bias_idxs.numpy()
+        for sk, sv in summarize(y).items():
+            out[f"{name}_y_{sk}"] = sv
+        for sk, sv in summarize(x.grad).items():
+            out[f"{name}_gx_{sk}"] = sv
+        for pn, p in attn.named_parameters():
+            out[f"{name}_shape_{pn}"] = np.array(p.shape)
+            for sk, sv in summarize(p.grad).items():
+                out[f"{name}_grad_{pn}_{sk}"] = sv
+    np.savez_compressed(HERE / "tinyvit_attention.npz", **out)
+    print("tinyvit_attention.npz", len(out), "arrays")
+
+
 def golden_rpe_index():
     """The reference's own self-check shape (rpe_ops/rpe_index.py:59-100), through the
     reference C++ op compiled by oracle/build_ref.py."""
@@ -269,4 +312,5 @@ if __name__ == "__main__":
     golden_index_tables()
     golden_supernet()
     golden_irpe_attention()
+    golden_tinyvit_attention()
     golden_rpe_index()

@@ -598,3 +598,34 @@ def test_clip_attention_module(L, B, heads, causal, prune):
     assert rel_err(x.grad.float().cpu(), xr.grad) < 2e-2
     for pn, p in m.named_parameters():
         assert rel_err(p.grad.float().cpu(), P[pn].grad) < 2e-2, pn
+
+
+@pytest.mark.parametrize("name", ["win7", "full14"])
+def test_tinyvit_attention_module(golden_dir, name):
+    """TinyViT Attention mirror (LayerNorm, qkv, per-head bias gather, softmax, proj; head_dim 32 run
+    zero-padded to 64) against the fixture written by the reference's own module."""
+    from cream_b200.tinyvit_attention import Attention
+    from make_golden import TINYVIT_CASES
+    g = np.load(golden_dir / "tinyvit_attention.npz")
+    dim, key_dim, heads, ratio, res, B = TINYVIT_CASES[name]
+    m = Attention(dim, key_dim, heads, attn_ratio=ratio, resolution=res).cuda().train()
+    np.testing.assert_array_equal(m.attention_bias_idxs.cpu().numpy(), g[f"{name}_idxs"])
+    shapes = {k[len(name) + 7:]: tuple(int(v) for v in g[k]) for k in g.files if k.startswith(name + "_shape_")}
+    seed = 300
+    with torch.no_grad():
+        for pn, shape in shapes.items():
+            seed += 1
+            p = dict(m.named_parameters())[pn]
+            assert tuple(p.shape) == shape, pn
+            if pn == "norm.weight":
+                p.copy_(1.0 + rand(shape, seed, 0.1))
+            else:
+                p.copy_(rand(shape, seed, 0.5 if "attention_biases" in pn else 0.08))
+    N = res[0] * res[1]
+    x = rand((B, N, dim), 299).cuda().requires_grad_(True)
+    y = m(x)
+    y.backward(rand((B, N, dim), 298).cuda().to(y.dtype))
+    check_summary(g, f"{name}_y", y.float(), 1.5e-2)
+    check_summary(g, f"{name}_gx", x.grad.float(), 3e-2)
+    for pn, p in m.named_parameters():
+        check_summary(g, f"{name}_grad_{pn}", p.grad.float(), 3e-2, what=pn)

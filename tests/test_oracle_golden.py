@@ -175,3 +175,36 @@ def test_clip_attention_oracle_matches_torch_mha(L, B, heads, causal):
     y.backward(gy)
     assert torch.allclose(y, ref, atol=2e-5, rtol=1e-4)
     assert torch.allclose(x2.grad, x.grad, atol=2e-5, rtol=1e-4)
+
+
+from make_golden import TINYVIT_CASES  # noqa: E402
+
+
+def _tinyvit_params(g, name):
+    shapes = {k[len(name) + 7:]: tuple(int(v) for v in g[k]) for k in g.files if k.startswith(name + "_shape_")}
+    params, seed = {}, 300
+    for pn, shape in shapes.items():
+        seed += 1
+        if pn == "norm.weight":
+            params[pn] = (1.0 + rand(shape, seed, 0.1)).requires_grad_(True)
+        else:
+            params[pn] = rand(shape, seed, 0.5 if "attention_biases" in pn else 0.08).requires_grad_(True)
+    return params
+
+
+@pytest.mark.parametrize("name", list(TINYVIT_CASES))
+def test_tinyvit_attention_oracle_matches_reference(golden_dir, name):
+    g = np.load(golden_dir / "tinyvit_attention.npz")
+    dim, key_dim, heads, ratio, res, B = TINYVIT_CASES[name]
+    idxs, n_off = vo.tinyvit_bias_idxs(res)
+    np.testing.assert_array_equal(idxs.numpy(), g[f"{name}_idxs"])           # integer table: bit exact
+    P = _tinyvit_params(g, name)
+    assert P["attention_biases"].shape == (heads, n_off)
+    N = res[0] * res[1]
+    x = rand((B, N, dim), 299).requires_grad_(True)
+    y = vo.tinyvit_attention(x, P, heads, key_dim, int(ratio * key_dim), idxs)
+    y.backward(rand((B, N, dim), 298))
+    check_summary(g, f"{name}_y", y, 1e-5)
+    check_summary(g, f"{name}_gx", x.grad, 1e-4)
+    for pn, p in P.items():
+        check_summary(g, f"{name}_grad_{pn}", p.grad, 1e-4, what=f"{name} grad {pn}")
