@@ -155,6 +155,8 @@ class SupernetTrainer:
             self._slots[i] = slot
             self._slot_free[i] = None
             self.copy_stream.wait_stream(torch.cuda.current_stream())
+            for t in slot:                      # allocated on the compute stream, written on the copy stream
+                t.record_stream(self.copy_stream)
         with torch.cuda.stream(self.copy_stream):
             if self._slot_free[i] is not None:
                 self.copy_stream.wait_event(self._slot_free[i])     # the previous user of the slot has read it
