@@ -1,9 +1,11 @@
-"""Drop-in for AutoFormer/model/module/embedding_super.py: the 16x16/16 patch convolution is
-one sliced GEMM over im2col patches (embedding_super.py:33-40)."""
+"""Drop-in for AutoFormer/model/module/embedding_super.py.
+
+The 16x16 / stride-16 patch convolution is a GEMM over im2col patches with the first
+`sample_embed_dim` filters (embedding_super.py:27-40); the module keeps the reference's `proj`
+Conv2d parameter (checkpoint names / shapes) and the attributes the model reads (`num_patches`).
+"""
 from __future__ import annotations
 
-import numpy as np
-import torch
 import torch.nn as nn
 
 from ..utils import to_2tuple
@@ -13,42 +15,32 @@ from ...functional import PatchEmbedFn
 class PatchembedSuper(nn.Module):
     def __init__(self, img_size=224, patch_size=16, in_chans=3, embed_dim=768, scale=False):
         super().__init__()
-        img_size = to_2tuple(img_size)
-        patch_size = to_2tuple(patch_size)
-        self.img_size = img_size
-        self.patch_size = patch_size
-        self.num_patches = (img_size[1] // patch_size[1]) * (img_size[0] // patch_size[0])
-        self.proj = nn.Conv2d(in_chans, embed_dim, kernel_size=patch_size, stride=patch_size)
-        self.super_embed_dim = embed_dim
-        self.scale = scale
-        self.sample_embed_dim = None
-        self.sampled_weight = None
-        self.sampled_bias = None
-        self.sampled_scale = None
+        self.img_size, self.patch_size = to_2tuple(img_size), to_2tuple(patch_size)
+        grid = tuple(i // p for i, p in zip(self.img_size, self.patch_size))
+        self.num_patches = grid[0] * grid[1]
+        self.proj = nn.Conv2d(in_chans, embed_dim, kernel_size=self.patch_size, stride=self.patch_size)
+        self.super_embed_dim, self.scale = embed_dim, scale
+        self.sample_embed_dim = self.sampled_weight = self.sampled_bias = self.sampled_scale = None
 
     def set_sample_config(self, sample_embed_dim):
         self.sample_embed_dim = sample_embed_dim
-        self.sampled_weight = self.proj.weight[:sample_embed_dim, ...]
-        self.sampled_bias = self.proj.bias[:self.sample_embed_dim, ...]
-        if self.scale:
-            self.sampled_scale = self.super_embed_dim / sample_embed_dim
+        # views for the counters below; the kernel reads the full tensors with E as an extent
+        self.sampled_weight = self.proj.weight[:sample_embed_dim]
+        self.sampled_bias = self.proj.bias[:sample_embed_dim]
+        self.sampled_scale = self.super_embed_dim / sample_embed_dim if self.scale else None
 
     def forward(self, x):
         B, C, H, W = x.shape
-        assert H == self.img_size[0] and W == self.img_size[1], \
-            f"Input image size ({H}*{W}) doesn't match model ({self.img_size[0]}*{self.img_size[1]})."
+        want = self.img_size
+        assert (H, W) == tuple(want), f"Input image size ({H}*{W}) doesn't match model ({want[0]}*{want[1]})."
         assert self.patch_size[0] == self.patch_size[1] and H == W, "square patches / images only"
         y = PatchEmbedFn.apply(x, self.proj.weight, self.proj.bias, self.sample_embed_dim, self.patch_size[0])
-        if self.scale:
-            return y * self.sampled_scale
-        return y
+        return y * self.sampled_scale if self.scale else y
 
     def calc_sampled_param_num(self):
-        return self.sampled_weight.numel() + self.sampled_bias.numel()
+        return int(self.sampled_weight.numel()) + int(self.sampled_bias.numel())
 
     def get_complexity(self, sequence_length):
-        total_flops = 0
-        if self.sampled_bias is not None:
-            total_flops += self.sampled_bias.size(0)
-        total_flops += sequence_length * np.prod(self.sampled_weight.size())
-        return total_flops
+        per_token = int(self.sampled_weight.numel())          # filters x (channels * patch area)
+        bias_adds = self.sampled_bias.size(0) if self.sampled_bias is not None else 0
+        return sequence_length * per_token + bias_adds

@@ -1,64 +1,17 @@
-"""Drop-in for AutoFormer/model/module/qkv_super.py.  The reference materialises the
-interleaved slice with torch.cat on every set_sample_config (qkv_super.py:45-51,72-77);
-here the bf16 shadow is stored de-interleaved and the sampled q/k/v blocks are three row
-ranges of one TMA tensor map."""
+"""Drop-in for AutoFormer/model/module/qkv_super.py.
+
+The reference rebuilds the sampled weight on every `set_sample_config` by concatenating three
+strided row selections of the full tensor (rows i, i+3, i+6, ... for i = 0, 1, 2;
+qkv_super.py:45-51,72-77) and takes the bias as a plain prefix (:80-83).  Here the bf16 shadow of
+the weight is stored de-interleaved once per optimizer step, so a sampled (in, 3*64*heads) slice is
+three dense row blocks of one TMA tensor map; `samples['weight']` keeps the reference's SHAPE for the
+parameter / FLOP counters (an `(out, in)` prefix view has the same element count as the concatenation).
+"""
 from __future__ import annotations
 
-import numpy as np
-import torch
-import torch.nn as nn
-
-from ...functional import SlicedLinearFn
+from .Linear_super import _SlicedLinear
 
 
-class qkv_super(nn.Linear):
-    def __init__(self, super_in_dim, super_out_dim, bias=True, uniform_=None, non_linear='linear', scale=False):
-        super().__init__(super_in_dim, super_out_dim, bias=bias)
-        self.super_in_dim = super_in_dim
-        self.super_out_dim = super_out_dim
-        self.sample_in_dim = None
-        self.sample_out_dim = None
-        self.samples = {}
-        self.scale = scale
-        self.profiling = False
-
-    def profile(self, mode=True):
-        self.profiling = mode
-
-    def sample_parameters(self, resample=False):
-        if self.profiling or resample:
-            return self._sample_parameters()
-        return self.samples
-
-    def _reset_parameters(self, bias, uniform_, non_linear):
-        nn.init.xavier_uniform_(self.weight) if uniform_ is None else uniform_(self.weight, non_linear=non_linear)
-        if bias:
-            nn.init.constant_(self.bias, 0.)
-
-    def set_sample_config(self, sample_in_dim, sample_out_dim):
-        self.sample_in_dim = sample_in_dim
-        self.sample_out_dim = sample_out_dim
-        self._sample_parameters()
-
-    def _sample_parameters(self):
-        # bookkeeping only: shapes for calc_sampled_param_num / get_complexity (no copy is made)
-        self.samples['weight'] = self.weight[:self.sample_out_dim, :self.sample_in_dim]
-        self.samples['bias'] = self.bias
-        self.sample_scale = self.super_out_dim / self.sample_out_dim
-        if self.bias is not None:
-            self.samples['bias'] = self.bias[:self.sample_out_dim]   # contiguous, NOT interleaved (:80-83)
-        return self.samples
-
-    def forward(self, x):
-        self.sample_parameters()
-        y = SlicedLinearFn.apply(x, self.weight, self.bias, self.sample_in_dim, self.sample_out_dim, True)
-        return y * (self.sample_scale if self.scale else 1)
-
-    def calc_sampled_param_num(self):
-        assert 'weight' in self.samples.keys()
-        weight_numel = self.samples['weight'].numel()
-        bias_numel = self.samples['bias'].numel() if self.samples['bias'] is not None else 0
-        return weight_numel + bias_numel
-
-    def get_complexity(self, sequence_length):
-        return sequence_length * np.prod(self.samples['weight'].size())
+class qkv_super(_SlicedLinear):
+    _interleaved_qkv = True
+    _init_on_construct = False    # qkv_super.py:21 leaves the nn.Linear default initialisation in place
