@@ -163,3 +163,33 @@ def test_reference_model_file_runs_unchanged_on_the_drop_in_modules():
         for k in [k for k in sys.modules if k == "model" or k.startswith("model.")]:
             del sys.modules[k]
         sys.modules.update({k: v for k, v in saved.items() if v is not None})
+
+
+def test_adapter_mirrors_surface_and_fail_loudly(golden_dir):
+    """TinyViT / TinyCLIP / iRPE attention mirrors: the reference's parameter names and shapes, and
+    no CPU path."""
+    from cream_b200.clip_attention import ClipAttention
+    from cream_b200.irpe_attention import RPEAttention
+    from cream_b200.tinyvit_attention import Attention
+    from make_golden import IRPE_CASES, TINYVIT_CASES
+    g = np.load(golden_dir / "tinyvit_attention.npz")
+    for name, (dim, key_dim, heads, ratio, res, B) in TINYVIT_CASES.items():
+        m = Attention(dim, key_dim, heads, attn_ratio=ratio, resolution=res)
+        want = {k[len(name) + 7:]: tuple(int(v) for v in g[k]) for k in g.files if k.startswith(name + "_shape_")}
+        assert {k: tuple(v.shape) for k, v in m.named_parameters()} == want
+        np.testing.assert_array_equal(m.attention_bias_idxs.numpy(), g[f"{name}_idxs"])
+        with pytest.raises(RuntimeError):
+            m(torch.randn(1, res[0] * res[1], dim))
+    mha = torch.nn.MultiheadAttention(128, 2)
+    clip = ClipAttention(128, 2)
+    assert {k: tuple(v.shape) for k, v in clip.named_parameters()} == {k: tuple(v.shape) for k, v in mha.named_parameters()}
+    with pytest.raises(RuntimeError):
+        clip(torch.randn(5, 2, 128))
+    gi = np.load(golden_dir / "irpe_attention.npz")
+    for name, (rpe_on, mode, shared, method, C, heads, grid) in IRPE_CASES.items():
+        if C // heads != 64:
+            continue
+        m = RPEAttention(C, num_heads=heads, qkv_bias=True, rpe_on=rpe_on, method=method,
+                         mode="bias" if mode == "bias" else "contextual", shared_head=shared)
+        want = {k[len(name) + 7:]: tuple(int(v) for v in gi[k]) for k in gi.files if k.startswith(name + "_shape_")}
+        assert {k: tuple(v.shape) for k, v in m.named_parameters()} == want, name
