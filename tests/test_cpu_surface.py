@@ -193,3 +193,26 @@ def test_adapter_mirrors_surface_and_fail_loudly(golden_dir):
                          mode="bias" if mode == "bias" else "contextual", shared_head=shared)
         want = {k[len(name) + 7:]: tuple(int(v) for v in gi[k]) for k in gi.files if k.startswith(name + "_shape_")}
         assert {k: tuple(v.shape) for k, v in m.named_parameters()} == want, name
+
+
+def test_host_irpe_bucket_ids_property(lib):
+    """Property test of the bit-exact integer contract: the library's host tables equal the numpy
+    restatement of irpe.py for random grids, skips and ratios (incl. non-square grids, the
+    height/width arguments DETR passes, rpe_attention_function.py:327-376)."""
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=150, deadline=None)
+    @given(mid=st.sampled_from([0, 1, 3, 41, 42]), h=st.integers(1, 16), w=st.integers(1, 16),
+           skip=st.integers(0, 2), ratio=st.floats(1.0, 4.0, allow_nan=False, width=32))
+    def check(mid, h, w, skip, ratio):
+        n = skip + h * w
+        out = np.empty((n, n), np.int32)
+        nb = ctypes.c_int(0)
+        rc = lib.cream_irpe_bucket_ids_host(mid, h, w, skip, 1 * ratio, 2 * ratio, 8 * ratio, out.ctypes.data,
+                                            ctypes.byref(nb))
+        assert rc == 0
+        ids, nb2 = rel_index.irpe_bucket_ids(mid, h, w, skip, 1 * ratio, 2 * ratio, 8 * ratio)
+        assert nb.value == nb2
+        np.testing.assert_array_equal(out, ids)
+
+    check()

@@ -208,3 +208,27 @@ def test_tinyvit_attention_oracle_matches_reference(golden_dir, name):
     check_summary(g, f"{name}_gx", x.grad, 1e-4)
     for pn, p in P.items():
         check_summary(g, f"{name}_grad_{pn}", p.grad, 1e-4, what=f"{name} grad {pn}")
+
+
+@pytest.mark.skipif(not Path("/root/reference").exists(), reason="reference checkout only exists in the build container")
+def test_irpe_bucket_ids_property_against_the_reference():
+    """Beyond the committed fixtures: random (method, grid, skip, ratio) draws, the numpy restatement
+    against the reference's own get_bucket_ids_2d (irpe.py:364-415) imported in place — bit exact."""
+    from hypothesis import given, settings, strategies as st
+    import make_golden as mg
+    mg.install_shims()
+    sys.path.insert(0, "/root/reference/iRPE/DeiT-with-iRPE")
+    sys.dont_write_bytecode = True
+    import irpe
+
+    @settings(max_examples=120, deadline=None)
+    @given(mid=st.sampled_from([0, 1, 3, 41, 42]), h=st.integers(1, 15), w=st.integers(1, 15),
+           skip=st.integers(0, 2), ratio=st.floats(1.0, 4.0, allow_nan=False, width=32))
+    def check(mid, h, w, skip, ratio):
+        irpe.BUCKET_IDS_BUF.clear()
+        want, nb_want = irpe.get_bucket_ids_2d(mid, h, w, skip, 1 * ratio, 2 * ratio, 8 * ratio)
+        ids, nb = rel_index.irpe_bucket_ids(mid, h, w, skip, 1 * ratio, 2 * ratio, 8 * ratio)
+        assert nb == int(nb_want)
+        np.testing.assert_array_equal(ids, want.numpy())
+
+    check()
