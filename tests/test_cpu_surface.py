@@ -216,3 +216,16 @@ def test_host_irpe_bucket_ids_property(lib):
         np.testing.assert_array_equal(out, ids)
 
     check()
+
+
+def test_host_autoformer_rel_index_property(lib):
+    """Library host table vs the numpy restatement for every (grid, max_rel) in a range that includes
+    binding clamps (max_rel < grid - 1) — bit exact."""
+    for grid in range(1, 17):
+        for max_rel in (1, 2, 5, grid - 1 if grid > 1 else 1, 14, 20):
+            n = grid * grid + 1
+            iv, ih = np.empty((n, n), np.int32), np.empty((n, n), np.int32)
+            assert lib.cream_autoformer_rel_index_host(grid, max_rel, iv.ctypes.data, ih.ctypes.data) == 0
+            ov, oh = rel_index.autoformer_rel_index(grid, max_rel)
+            np.testing.assert_array_equal(iv, ov)
+            np.testing.assert_array_equal(ih, oh)

@@ -232,3 +232,43 @@ def test_irpe_bucket_ids_property_against_the_reference():
         np.testing.assert_array_equal(ids, want.numpy())
 
     check()
+
+
+@pytest.mark.skipif(not Path("/root/reference").exists(), reason="reference checkout only exists in the build container")
+def test_autoformer_rel_index_property_against_the_reference():
+    """Random (grid, max_relative_position) draws — including clamps that bind — against the reference's
+    RelativePosition2D_super (multihead_super.py:40-66) imported in place: its tables are set to
+    arange so the returned embedding decodes to (idx_v, idx_h)."""
+    import importlib.util
+    from hypothesis import given, settings, strategies as st
+    import make_golden as mg
+    mg.install_shims()
+    sys.dont_write_bytecode = True
+    saved = {k: sys.modules.get(k) for k in list(sys.modules) if k == "model" or k.startswith("model.")}
+    sys.path.insert(0, "/root/reference/AutoFormer")
+    try:
+        for k in saved:
+            sys.modules.pop(k, None)
+        from model.module.multihead_super import RelativePosition2D_super  # reference, unmodified
+
+        @settings(max_examples=80, deadline=None)
+        @given(grid=st.integers(1, 15), max_rel=st.integers(1, 15))
+        def check(grid, max_rel):
+            n = grid * grid + 1
+            m = RelativePosition2D_super(1, max_rel)
+            rows = 2 * max_rel + 2
+            with torch.no_grad():
+                m.embeddings_table_v.copy_(torch.arange(rows, dtype=torch.float32).view(rows, 1))
+                m.embeddings_table_h.copy_(1000.0 * torch.arange(rows, dtype=torch.float32).view(rows, 1))
+            m.set_sample_config(1)
+            code = m(n, n)[..., 0].round().long()
+            iv, ih = rel_index.autoformer_rel_index(grid, max_rel)
+            np.testing.assert_array_equal(iv, (code % 1000).numpy())
+            np.testing.assert_array_equal(ih, (code // 1000).numpy())
+
+        check()
+    finally:
+        sys.path.remove("/root/reference/AutoFormer")
+        for k in [k for k in sys.modules if k == "model" or k.startswith("model.")]:
+            del sys.modules[k]
+        sys.modules.update({k: v for k, v in saved.items() if v is not None})
