@@ -272,3 +272,103 @@ def test_autoformer_rel_index_property_against_the_reference():
         for k in [k for k in sys.modules if k == "model" or k.startswith("model.")]:
             del sys.modules[k]
         sys.modules.update({k: v for k, v in saved.items() if v is not None})
+
+
+@pytest.mark.skipif(not Path("/root/reference").exists(), reason="reference checkout only exists in the build container")
+@pytest.mark.parametrize("rpe_on,mode,method,shared", [
+    ("k", "ctx", "euc", True), ("qk", "ctx", "quant", False), ("qkv", "ctx", "product", True),
+    ("kv", "ctx", "cross", False), ("v", "ctx", "product", False), ("q", "ctx", "cross", True),
+    ("qk", "bias", "product", False), ("k", "bias", "cross", True), ("q", "bias", "euc", False),
+])
+def test_rpe_attention_oracle_against_the_reference_module(rpe_on, mode, method, shared):
+    """A sweep beyond the committed fixtures: the oracle's RPEAttention restatement against the
+    reference's own module (rpe_vision_transformer.py:45-97, timm stubbed) on small grids, every
+    rpe_on / mode / method / head-sharing family, forward and all gradients."""
+    import make_golden as mg
+    mg.install_shims()
+    sys.dont_write_bytecode = True
+    sys.path.insert(0, "/root/reference/iRPE/DeiT-with-iRPE")
+    try:
+        import irpe
+        from rpe_vision_transformer import RPEAttention
+        irpe.BUCKET_IDS_BUF.clear()
+        C, heads, grid, B = 32, 2, 4, 2
+        cfg = irpe.get_rpe_config(ratio=1.9, method=method, mode=mode, shared_head=shared, skip=1, rpe_on=rpe_on)
+        attn = RPEAttention(C, num_heads=heads, qkv_bias=True, rpe_config=cfg)
+        seed = 700
+        with torch.no_grad():
+            for pn, p in attn.named_parameters():
+                seed += 1
+                p.copy_(rand(tuple(p.shape), seed, 0.3 if "lookup" in pn else 0.1))
+        N = grid * grid + 1
+        x = rand((B, N, C), 699).requires_grad_(True)
+        gy = rand((B, N, C), 698)
+        y = attn(x)
+        y.backward(gy)
+        P = {k: v.detach().clone().requires_grad_(True) for k, v in attn.named_parameters()}
+        if method == "cross":
+            ids = tuple(rel_index.irpe_bucket_ids(m, grid, grid, 1, 1.9, 3.8, 15.2)[0]
+                        for m in (rel_index.CROSS_ROWS, rel_index.CROSS_COLS))
+        else:
+            mid = {"product": rel_index.PRODUCT, "euc": rel_index.EUCLIDEAN, "quant": rel_index.QUANT}[method]
+            ids = rel_index.irpe_bucket_ids(mid, grid, grid, 1, 1.9, 3.8, 15.2)[0]
+
+        def tab(w):
+            hits = [v for k, v in P.items() if k.startswith(f"rpe_{w}.")]
+            return None if not hits else (hits[0] if len(hits) == 1 else tuple(hits))
+        x2 = x.detach().clone().requires_grad_(True)
+        y2 = vo.rpe_attention(x2, P["qkv.weight"], P["qkv.bias"], P["proj.weight"], P["proj.bias"], heads, ids,
+                              rpe_q=tab("q"), rpe_k=tab("k"), rpe_v=tab("v"),
+                              mode="bias" if mode == "bias" else "contextual")
+        y2.backward(gy)
+        assert torch.allclose(y2, y, atol=1e-5, rtol=1e-4)
+        assert torch.allclose(x2.grad, x.grad, atol=1e-5, rtol=1e-4)
+        for k, p in attn.named_parameters():
+            assert torch.allclose(P[k].grad, p.grad, atol=1e-5, rtol=1e-4), k
+    finally:
+        sys.path.remove("/root/reference/iRPE/DeiT-with-iRPE")
+
+
+@pytest.mark.skipif(not Path("/root/reference").exists(), reason="reference checkout only exists in the build container")
+def test_supernet_t_oracle_against_the_reference_model():
+    """The shipped supernet-T geometry (BASELINE config 1 family) with two subnets drawn by the
+    reference's own sampling rule: oracle logits and a few gradients against the reference model
+    imported in place (supernet_transformer.py, torch._six shimmed)."""
+    import random
+    import make_golden as mg
+    mg.install_shims()
+    sys.dont_write_bytecode = True
+    saved = {k: sys.modules.get(k) for k in list(sys.modules) if k == "model" or k.startswith("model.")}
+    sys.path.insert(0, "/root/reference/AutoFormer")
+    try:
+        for k in saved:
+            sys.modules.pop(k, None)
+        from model.supernet_transformer import Vision_TransformerSuper  # reference, unmodified
+        spec = vo.SUPERNET_T
+        net = Vision_TransformerSuper(img_size=224, patch_size=16, embed_dim=spec.embed_dim, depth=spec.depth,
+                                      num_heads=spec.num_heads, mlp_ratio=spec.mlp_ratio, qkv_bias=True, drop_rate=0.0,
+                                      drop_path_rate=0.0, gp=True, num_classes=1000, max_relative_position=14,
+                                      relative_position=True, change_qkv=True, abs_pos=True)
+        sd = vo.init_params(spec, seed=3)
+        net.load_state_dict(sd)
+        net.train()
+        rnd = random.Random(1)
+        images = rand((1, 3, 224, 224), seed=41)
+        for _ in range(2):
+            cfg = vo.sample_configs(vo.SEARCH_SPACE["T"], rnd)
+            net.zero_grad(set_to_none=True)
+            net.set_sample_config(cfg)
+            ref = net(images)
+            ref.sum().backward()
+            P = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+            out = vo.supernet_forward(P, cfg, images, spec)
+            out.sum().backward()
+            assert torch.allclose(out, ref, atol=2e-4, rtol=1e-3)
+            for name in ("cls_token", "blocks.0.attn.qkv.weight", "blocks.0.attn.rel_pos_embed_k.embeddings_table_v",
+                         "blocks.1.fc1.weight", "head.weight"):
+                assert torch.allclose(P[name].grad, dict(net.named_parameters())[name].grad, atol=2e-4, rtol=1e-3), name
+    finally:
+        sys.path.remove("/root/reference/AutoFormer")
+        for k in [k for k in sys.modules if k == "model" or k.startswith("model.")]:
+            del sys.modules[k]
+        sys.modules.update({k: v for k, v in saved.items() if v is not None})
