@@ -288,6 +288,12 @@ def test_rpe_attention_oracle_against_the_reference_module(rpe_on, mode, method,
     mg.install_shims()
     sys.dont_write_bytecode = True
     sys.path.insert(0, "/root/reference/iRPE/DeiT-with-iRPE")
+    # the reference must take its pure-PyTorch gather (irpe.py:8-15 falls back on ImportError), not a
+    # drop-in rpe_ops another test may have registered: import it fresh with rpe_ops blocked
+    names = ("irpe", "rpe_vision_transformer", "rpe_ops", "rpe_ops.rpe_index")
+    held = {k: sys.modules.pop(k, None) for k in names}
+    sys.modules["rpe_ops"] = None
+    sys.modules["rpe_ops.rpe_index"] = None
     try:
         import irpe
         from rpe_vision_transformer import RPEAttention
@@ -327,6 +333,9 @@ def test_rpe_attention_oracle_against_the_reference_module(rpe_on, mode, method,
             assert torch.allclose(P[k].grad, p.grad, atol=1e-5, rtol=1e-4), k
     finally:
         sys.path.remove("/root/reference/iRPE/DeiT-with-iRPE")
+        for k in names:
+            sys.modules.pop(k, None)
+        sys.modules.update({k: v for k, v in held.items() if v is not None})
 
 
 @pytest.mark.skipif(not Path("/root/reference").exists(), reason="reference checkout only exists in the build container")
