@@ -36,6 +36,9 @@ class ClipAttention(nn.Module):
         qkv = SlicedLinearFn.apply(xb, self.in_proj_weight, self.in_proj_bias, E, 3 * E, False)
         dense = None
         if attn_mask is not None:
+            if attn_mask.dtype == torch.bool:      # nn.MultiheadAttention: True = "may not attend"
+                attn_mask = torch.zeros(attn_mask.shape, dtype=torch.float32, device=attn_mask.device) \
+                    .masked_fill_(attn_mask, float("-inf"))
             dense = attn_mask.to(device=x.device, dtype=torch.float32).reshape(1, 1, L, L).contiguous()
         out = DenseAttentionFn.apply(qkv, H, float(ops.HEAD_DIM ** -0.5), dense)       # (B, L, E)
         if head_z is not None:

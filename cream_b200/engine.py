@@ -45,6 +45,7 @@ class SupernetGeometry:
     relative_position: bool = True
     abs_pos: bool = True
     eps: float = 1e-5
+    qkv_bias: bool = True
 
     @property
     def grid(self) -> int:
@@ -55,9 +56,11 @@ class SupernetGeometry:
         return self.grid * self.grid + 1
 
 
-def block_param_names(i: int, relative_position: bool = True) -> List[str]:
+def block_param_names(i: int, relative_position: bool = True, qkv_bias: bool = True) -> List[str]:
     p = f"blocks.{i}."
-    names = [p + "attn_layer_norm.weight", p + "attn_layer_norm.bias", p + "attn.qkv.weight", p + "attn.qkv.bias"]
+    names = [p + "attn_layer_norm.weight", p + "attn_layer_norm.bias", p + "attn.qkv.weight"]
+    if qkv_bias:
+        names.append(p + "attn.qkv.bias")
     if relative_position:
         names += [p + f"attn.rel_pos_embed_{kv}.embeddings_table_{vh}" for kv in "kv" for vh in "vh"]
     names += [p + "attn.proj.weight", p + "attn.proj.bias", p + "ffn_layer_norm.weight", p + "ffn_layer_norm.bias",
@@ -71,7 +74,7 @@ def sampled_param_names(geo: SupernetGeometry, config: dict) -> List[str]:
     if geo.abs_pos:
         names.append("pos_embed")
     for i in range(config["layer_num"]):
-        names += block_param_names(i, geo.relative_position)
+        names += block_param_names(i, geo.relative_position, geo.qkv_bias)
     names += ["norm.weight", "norm.bias", "head.weight", "head.bias"]
     return names
 
@@ -157,7 +160,7 @@ def forward(P: Dict[str, torch.Tensor], geo: SupernetGeometry, config: dict, ima
         ln1, mu1, rs1 = ops.layernorm_fwd(x, P[pre + "attn_layer_norm.weight"], P[pre + "attn_layer_norm.bias"],
                                           geo.eps, E, save_stats=save)
         wq = sh.get(P[pre + "attn.qkv.weight"], qkv=True)
-        qkv = ops.qkv_fwd(ln1, wq, h, E, Es, P[pre + "attn.qkv.bias"])
+        qkv = ops.qkv_fwd(ln1, wq, h, E, Es, P.get(pre + "attn.qkv.bias"))
         tk = tv = None
         if geo.relative_position:
             tk, tv = packs[2 * i:2 * i + 1], packs[2 * i + 1:2 * i + 2]
@@ -267,7 +270,8 @@ def backward(P: Dict[str, torch.Tensor], geo: SupernetGeometry, saved: Saved, dl
             ops.unpack_table_grads_batch(dpacks[2 * i:2 * i + 2], [
                 (G[pre + f"attn.rel_pos_embed_{kv}.embeddings_table_v"], G[pre + f"attn.rel_pos_embed_{kv}.embeddings_table_h"])
                 for kv in "kv"])
-        ops.bias_grad(dqkv, G[pre + "attn.qkv.bias"])
+        if geo.qkv_bias:
+            ops.bias_grad(dqkv, G[pre + "attn.qkv.bias"])
         ops.qkv_wgrad(dqkv, s["ln1"], h, E, G[pre + "attn.qkv.weight"])
         dln1 = ops.qkv_dgrad(dqkv, sh.get(P[pre + "attn.qkv.weight"], qkv=True), h, E, Es)
         g = ops.layernorm_bwd(dln1, s["x"], P[pre + "attn_layer_norm.weight"], s["mu1"], s["rs1"], E,

@@ -80,10 +80,25 @@ def _check_2d(t: torch.Tensor, dtype, name: str, mult: int):
 # --------------------------------------------------------------------------------------------
 class ShadowCache:
     """bf16 shadows of fp32 master weights, refreshed when the parameter's version changes
-    (i.e. once per optimizer step).  QKV weights are stored de-interleaved."""
+    (i.e. once per optimizer step).  QKV weights are stored de-interleaved.
+
+    The staleness tag is (tensor version, storage, shape).  In-place updates that go through `.data`
+    (`p.data.add_()`, some third-party optimizers, manual EMA / weight surgery) do NOT bump the version
+    counter: after such an update call `SHADOWS.invalidate()` (or `invalidate(p)`), e.g. from an
+    optimizer post-step hook; `load_state_dict` and torch's own optimizers bump the version and need
+    nothing.  Entries hold the bf16 copy of a live parameter; `clear()` releases them all."""
 
     def __init__(self):
         self._store = {}
+
+    def invalidate(self, w: Optional[torch.Tensor] = None) -> None:
+        """Force a re-cast on next use: of every shadow, or only of parameter `w`."""
+        if w is None:
+            self._store = {k: (sh, None) for k, (sh, _) in self._store.items()}
+        else:
+            for k in [(w.data_ptr(), False), (w.data_ptr(), True)]:
+                if k in self._store:
+                    self._store[k] = (self._store[k][0], None)
 
     def get(self, w: torch.Tensor, qkv: bool = False) -> torch.Tensor:
         key = (w.data_ptr(), qkv)

@@ -87,19 +87,32 @@ class StagedBatch:
 class SupernetTrainer:
     def __init__(self, model: Vision_TransformerSuper, choices: dict, lr: float = 5e-4, weight_decay: float = 0.05,
                  process_group=None, grad_dtype: torch.dtype = torch.float32):
+        if not model.fusable():
+            raise ValueError("SupernetTrainer drives the fused engine: the model must be pre-norm, change_qkv=True, "
+                             "scale=False, drop_rate=0, attn_drop_rate=0 (DropPath is supported); use the module "
+                             "path under a stock torch loop otherwise")
         self.model = model
         self.choices = choices
-        self.geo = model._geo
+        self.geo = model.engine_geometry()
         self.params = dict(model.named_parameters())
         self.buckets = GradBuckets(model)
         self.pg = process_group
         self.world = dist.get_world_size(process_group) if (dist.is_available() and dist.is_initialized()) else 1
-        # timm create_optimizer('adamw') (supernet_train.py:296): no decay on 1-D params and the
-        # names in no_weight_decay(); torch's fused AdamW is the same update rule on device.
+        if self.world > 1:
+            # what DDP's constructor does (supernet_train.py:288): replicas start from rank 0's weights and
+            # buffers, whatever each rank's seed was (the reference seeds with args.seed + rank, :197-198)
+            with torch.no_grad():
+                for t in list(model.parameters()) + list(model.buffers()):
+                    dist.broadcast(t.data, src=dist.get_global_rank(process_group, 0) if process_group is not None else 0,
+                                   group=process_group)
+        # timm create_optimizer('adamw') (supernet_train.py:296) -> add_weight_decay: no decay on 1-D
+        # params, biases and names that are EXACTLY in no_weight_decay() — so 'rel_pos_embed' matches
+        # nothing and the 2-D relative-position tables ARE decayed, as in the reference recipe; torch's
+        # fused AdamW is the same update rule on device.
         skip = model.no_weight_decay()
         decay, no_decay = [], []
         for n, p in self.params.items():
-            (no_decay if (p.ndim <= 1 or n.endswith(".bias") or any(s in n for s in skip)) else decay).append(p)
+            (no_decay if (p.ndim <= 1 or n.endswith(".bias") or n in skip) else decay).append(p)
         self.optimizer = torch.optim.AdamW([{"params": decay, "weight_decay": weight_decay},
                                             {"params": no_decay, "weight_decay": 0.0}], lr=lr, fused=model.pos_embed.is_cuda)
         self.comm_stream = torch.cuda.Stream() if (self.world > 1 and model.pos_embed.is_cuda) else None
@@ -183,7 +196,7 @@ class SupernetTrainer:
         cfg = config if config is not None else sample_configs(self.choices, rnd)
         self.last_config = cfg
         model.set_sample_config(cfg)
-        scales = model._drop_path_scales(images.shape[0], dev)
+        scales = model.drop_path_scales(images.shape[0], dev)
         logits, saved = engine.forward(self.params, self.geo, cfg, images.float().contiguous(), scales, save=True)
         lg = logits.detach().requires_grad_(True)
         loss = F.cross_entropy(lg, targets)

@@ -26,12 +26,17 @@ def _worker(rank, world, port, ret):
         from cream_b200 import engine
         from cream_b200.autoformer.model.supernet_transformer import Vision_TransformerSuper
         from cream_b200.trainer import SupernetTrainer, sample_configs
-        torch.manual_seed(0)
+        torch.manual_seed(100 + rank)      # the reference seeds with args.seed + rank (supernet_train.py:197-198)
         model = Vision_TransformerSuper(img_size=64, embed_dim=128, depth=3, num_heads=2, mlp_ratio=4.0,
                                         qkv_bias=True, gp=True, relative_position=True, change_qkv=True)
         choices = dict(mlp_ratio=[3.0, 3.5, 4.0], num_heads=[1, 2], depth=[2, 3], embed_dim=[64, 96, 128])
         tr = SupernetTrainer(model, choices)
         assert tr.world == world
+        # 0. replicas start from rank 0's weights whatever the per-rank seed was (DDP's init broadcast)
+        digest = torch.stack([p.detach().double().sum() for p in model.parameters()])
+        both = [torch.zeros_like(digest) for _ in range(world)]
+        dist.all_gather(both, digest)
+        assert all(torch.equal(b, both[0]) for b in both), "parameters differ across ranks after construction"
         # 1. the config stream is identical on every rank (the engine seeds `random` with the epoch)
         random.seed(3)
         cfgs = [sample_configs(choices) for _ in range(5)]
@@ -55,7 +60,7 @@ def _worker(rank, world, port, ret):
             assert torch.allclose(tr.buckets.flat[g], torch.full_like(tr.buckets.flat[g], want))
         assert float(tr.buckets.flat["block2"].abs().sum()) == 0.0      # un-sampled layer untouched
         # 4. grads are assigned only to sampled parameters
-        sampled = set(engine.sampled_param_names(model._geo, cfg))
+        sampled = set(engine.sampled_param_names(model.engine_geometry(), cfg))
         for n, p in tr.params.items():
             p.grad = tr.buckets.views[n] if n in sampled else None
         assert model.blocks[2].fc1.weight.grad is None and model.blocks[0].fc1.weight.grad is not None
