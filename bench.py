@@ -31,6 +31,14 @@ UNIT = "images/s"
 PER_GPU_BATCH = 128
 WORKLOAD = ("AutoFormer-S supernet random-sample training step (embed 320-448, heads 5-7, depth 12-14, "
             "mlp 3-4), 224^2, bs128/GPU, relative position on K and V, DropPath 0.1, AdamW")
+# BASELINE.json configs that are bench lines (the others are parity-test cases): c3 is the headline
+# (`metric` is quoted on it), c5 the largest search space.
+CONFIGS = {
+    "c3": dict(size="S", batch=128, metric=METRIC, workload=WORKLOAD),
+    "c5": dict(size="B", batch=64, metric="supernet images/sec (224^2, bs64/GPU)",
+               workload=("AutoFormer-B supernet random-sample training step (embed 528-624, heads 9-10, depth 14-16, "
+                         "mlp 3-4), 224^2, bs64/GPU, relative position on K and V, DropPath 0.1, AdamW")),
+}
 
 
 def flops_per_image(cfg, n_tokens=197):
@@ -79,15 +87,39 @@ class ClockSampler(threading.Thread):
                 "reasons": reasons, "samples": len(self.rows)}
 
 
-def cpu_baseline(steps: int, warmup: int, batch: int = 4):
-    """The reference's CPU path for this workload: the oracle port (PyTorch fp32 restatement of
-    Vision_TransformerSuper forward + autograd backward + AdamW) on the host cores."""
+def cpu_baseline(steps: int, warmup: int, batch: int = 4, config: str = "c3"):
+    """The reference's CPU path for this workload on the host cores: the reference's OWN
+    Vision_TransformerSuper (unmodified, loaded from the staged checkout: kind "reference") when
+    available, else the oracle port (PyTorch fp32 restatement: kind "port"); forward + autograd
+    backward + AdamW on a bounded sample (small batch, same config stream)."""
     import torch
     import torch.nn.functional as F
-    from oracle import vit_oracle as vo
-    spec = vo.SUPERNET_S
-    sd = {k: v.requires_grad_(True) for k, v in vo.init_params(spec, seed=0).items()}
-    opt = torch.optim.AdamW(list(sd.values()), lr=5e-4, weight_decay=0.05)
+    from oracle import refload, vit_oracle as vo
+    size = CONFIGS[config]["size"]
+    spec = {"S": vo.SUPERNET_S, "B": vo.SUPERNET_B, "T": vo.SUPERNET_T}[size]
+    space = vo.SEARCH_SPACE[size]
+    sd0 = vo.init_params(spec, seed=0)
+    if refload.available():
+        kind = "reference"
+        net = refload.autoformer("reference").Vision_TransformerSuper(
+            img_size=224, patch_size=16, embed_dim=spec.embed_dim, depth=spec.depth, num_heads=spec.num_heads,
+            mlp_ratio=spec.mlp_ratio, qkv_bias=True, drop_rate=0.0, drop_path_rate=0.1, gp=True, num_classes=1000,
+            max_relative_position=14, relative_position=True, change_qkv=True, abs_pos=True)
+        net.load_state_dict(sd0)
+        net.train()
+        params = list(net.parameters())
+
+        def fwd(cfg, images):
+            net.set_sample_config(cfg)
+            return net(images)
+        what = "AutoFormer/model/supernet_transformer.py (unmodified, staged checkout)"
+    else:
+        kind = "port"
+        sd = {k: v.requires_grad_(True) for k, v in sd0.items()}
+        params = list(sd.values())
+        fwd = lambda cfg, images: vo.supernet_forward(sd, cfg, images, spec)
+        what = "oracle/vit_oracle.py"
+    opt = torch.optim.AdamW(params, lr=5e-4, weight_decay=0.05)
     rnd = random.Random(0)
     torch.manual_seed(0)
     images = torch.randn(batch, 3, 224, 224)
@@ -95,12 +127,12 @@ def cpu_baseline(steps: int, warmup: int, batch: int = 4):
     # give the CPU path its best thread count (oversubscribing a 128-thread host with a batch of
     # 4 is ~50x slower than 16-32 threads): one probe step per candidate, keep the fastest
     ncpu = os.cpu_count() or 1
-    probe_cfg = vo.sample_configs(vo.SEARCH_SPACE["S"], random.Random(1))
+    probe_cfg = vo.sample_configs(space, random.Random(1))
     best = (float("inf"), ncpu)
     for n in sorted({min(ncpu, c) for c in (8, 16, 32, 64, ncpu)}):
         torch.set_num_threads(n)
         t0 = time.perf_counter()
-        F.cross_entropy(vo.supernet_forward(sd, probe_cfg, images, spec), targets).backward()
+        F.cross_entropy(fwd(probe_cfg, images), targets).backward()
         dt = time.perf_counter() - t0
         if dt < best[0]:
             best = (dt, n)
@@ -110,30 +142,31 @@ def cpu_baseline(steps: int, warmup: int, batch: int = 4):
     opt.zero_grad(set_to_none=True)
     times = []
     for s in range(warmup + steps):
-        cfg = vo.sample_configs(vo.SEARCH_SPACE["S"], rnd)
+        cfg = vo.sample_configs(space, rnd)
         t0 = time.perf_counter()
         opt.zero_grad(set_to_none=True)
-        loss = F.cross_entropy(vo.supernet_forward(sd, cfg, images, spec), targets)
+        loss = F.cross_entropy(fwd(cfg, images), targets)
         loss.backward()
         opt.step()
         loss.item()
         if s >= warmup:
             times.append(time.perf_counter() - t0)
     total = sum(times)
-    return {"value": batch * len(times) / total, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
-            "sample": f"{len(times)} training steps of batch {batch} (same supernet-S config stream), fp32, "
-                      f"oracle/vit_oracle.py on {torch.get_num_threads()} host threads"}, total / len(times)
+    return {"value": batch * len(times) / total, "unit": UNIT, "cores": torch.get_num_threads(), "kind": kind,
+            "sample": f"{len(times)} training steps of batch {batch} (same supernet-{size} config stream), fp32, "
+                      f"{what} on {torch.get_num_threads()} host threads"}, total / len(times)
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    base, sec_per_step = cpu_baseline(args.steps, max(1, min(args.warmup, 2)))
-    line = {"impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": args.gpus,
+    conf = CONFIGS[args.config]
+    base, sec_per_step = cpu_baseline(args.steps, max(1, min(args.warmup, 2)), config=args.config)
+    line = {"impl": "reference", "metric": conf["metric"], "value": base["value"], "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec_per_step * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "note": "reference CPU path (oracle port), bounded sample"},
+            "config": {"workload": conf["workload"], "note": f"reference CPU path ({base['kind']}), bounded sample"},
             "cpu_baseline": base,
             "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
@@ -145,7 +178,8 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="cream_b200", choices=["cream_b200", "reference"])
-    ap.add_argument("--batch", type=int, default=PER_GPU_BATCH, help="per-GPU batch (default = BASELINE's 128)")
+    ap.add_argument("--config", default="c3", choices=sorted(CONFIGS), help="BASELINE.json configuration")
+    ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (default = the configuration's own)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -155,7 +189,7 @@ def main():
     import torch.distributed as dist
     from cream_b200 import _lib, ops
     from cream_b200.autoformer.model.supernet_transformer import Vision_TransformerSuper
-    from cream_b200.trainer import SupernetTrainer
+    from cream_b200.trainer import SupernetTrainer, sample_configs
     from cream_b200.configs import SEARCH_SPACE, SUPERNETS
 
     rank = int(os.environ.get("RANK", "0"))
@@ -168,23 +202,32 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
     _lib.load()
+    conf = CONFIGS[args.config]
     W = max(3, args.warmup)
     K = args.steps
-    B = args.batch
+    B = args.batch or conf["batch"]
 
-    spec = SUPERNETS["S"]
+    spec = SUPERNETS[conf["size"]]
+    ss = SEARCH_SPACE[conf["size"]]
     torch.manual_seed(0)
     model = Vision_TransformerSuper(img_size=224, patch_size=16, embed_dim=spec["embed_dim"], depth=spec["depth"],
                                     num_heads=spec["num_heads"], mlp_ratio=spec["mlp_ratio"], qkv_bias=True, drop_rate=0.0,
                                     drop_path_rate=0.1, gp=True, num_classes=1000, max_relative_position=14,
                                     relative_position=True, change_qkv=True, abs_pos=True).to(dev).train()
-    trainer = SupernetTrainer(model, SEARCH_SPACE["S"])
+    trainer = SupernetTrainer(model, ss)
     g = torch.Generator().manual_seed(1234 + rank)
     n_host = 4
     host_imgs = [torch.randn(B, 3, 224, 224, generator=g).pin_memory() for _ in range(n_host)]
     host_tgts = [torch.randint(0, 1000, (B,), generator=g).pin_memory() for _ in range(n_host)]
     dev_imgs = [t.to(dev) for t in host_imgs]     # 77 MB each: > 126 MB L2 in aggregate with activations
     dev_tgts = [t.to(dev) for t in host_tgts]
+
+    # ONE list of subnet configurations (sample_configs with random.Random(0): identical on every rank,
+    # supernet_engine.py:36) shared by the warm-up, the `value` region, the `e2e` region and the
+    # per-kernel roofline pass, so that all of them time the same work.
+    rnd = random.Random(0)
+    cfg_warm = [sample_configs(ss, rnd) for _ in range(W)]
+    cfg_timed = [sample_configs(ss, rnd) for _ in range(K)]
 
     def barrier():
         if world > 1:
@@ -194,7 +237,8 @@ def main():
     host_ms = [0.0]
     loss_pins = [torch.zeros((), dtype=torch.float32).pin_memory() for _ in range(2)]
 
-    def timed(n_steps, from_host, rnd):
+    def timed(cfgs, from_host):
+        n_steps = len(cfgs)
         flops = attn_flops = 0.0
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -209,11 +253,11 @@ def main():
         # that is faster than the GPU never drains the launch queue.
         staged = trainer.stage(host_imgs[0], host_tgts[0]) if from_host else None
         pending = None
-        for s in range(n_steps):
+        for s, cfg in enumerate(cfgs):
             t_host0 = time.perf_counter()
             i = s % n_host
             if from_host:
-                loss = trainer.step(staged, rnd=rnd)
+                loss = trainer.step(staged, config=cfg)
                 buf = loss_pins[s & 1]
                 buf.copy_(loss, non_blocking=True)          # device -> pinned host, every step
                 done = torch.cuda.Event()
@@ -228,8 +272,8 @@ def main():
                     done.synchronize()
                     loss_host = float(buf)
             else:
-                loss = trainer.step(dev_imgs[i], dev_tgts[i], rnd=rnd)
-            f, a = flops_per_image(trainer.last_config)
+                loss = trainer.step(dev_imgs[i], dev_tgts[i], config=cfg)
+            f, a = flops_per_image(cfg)
             flops += 3.0 * f * B
             attn_flops += 3.0 * a * B
             per_step.append((time.perf_counter() - t_host0) * 1e3)
@@ -247,7 +291,6 @@ def main():
     # allocator priming (initialisation, not a step of the workload): the largest and the smallest
     # subnet once each, so the caching allocator owns its pools before any timed or warm-up step
     # (the search space changes every activation shape from step to step).
-    ss = SEARCH_SPACE["S"]
     prime = random.Random(12345)
     for e in sorted(ss["embed_dim"], reverse=True):
         for pick in (max, min):
@@ -258,24 +301,26 @@ def main():
         trainer.step(dev_imgs[0], dev_tgts[0], rnd=prime)      # one mixed (per-layer h, r) subnet
     torch.cuda.synchronize()
     segments0 = torch.cuda.memory_stats().get("segment.all.allocated", 0)
-    # identical config stream on every rank (supernet_engine.py:36 seeds `random` with the epoch)
-    rnd = random.Random(0)
-    timed(W, False, rnd)                                   # warm-up (untimed)
+    timed(cfg_warm, False)                                 # warm-up (untimed)
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
-        sampler.start()
-    ms, flops, attn_flops, launches, _ = timed(K, False, rnd)
+        sampler.start()                                    # samples clocks through BOTH timed regions
+    ms, flops, attn_flops, launches, _ = timed(cfg_timed, False)
     host_enqueue_ms = host_ms[0]
+    timed(cfg_warm[:3], True)
+    ms_e2e, _, _, _, last_loss = timed(cfg_timed, True)
     clocks = sampler.stop() if sampler else None
-    timed(3, True, rnd)
-    ms_e2e, _, _, _, last_loss = timed(K, True, rnd)
 
-    # ---- per-kernel roofline pass (instrumented; separate from the timed region) ----
+    # ---- per-kernel roofline pass (instrumented; separate from the timed regions, same configs) ----
+    # Every launch is bracketed by CUDA events on its own stream.  So that the events time the kernel
+    # and not the host's enqueue gaps, each profiled step starts behind a spin kernel long enough for
+    # the host to queue the step's launches before the GPU starts draining them.
     ops.PROFILE = []
-    rnd_p = random.Random(0)
-    for s in range(3):
-        trainer.step(dev_imgs[s % n_host], dev_tgts[s % n_host], rnd=rnd_p)
-    torch.cuda.synchronize()
+    spin = int(25e-3 * 1.9e9)
+    for s, cfg in enumerate(cfg_timed[:4]):
+        torch.cuda._sleep(spin)
+        trainer.step(dev_imgs[s % n_host], dev_tgts[s % n_host], config=cfg)
+        torch.cuda.synchronize()
     prof, ops.PROFILE = ops.PROFILE, None
     agg = {}
     for kind, a, b, fl, by in prof:
@@ -305,23 +350,30 @@ def main():
             traffic = sum(v["dram_bytes_per_launch"] * v["launches"] for v in gl) / sum(v["launches"] for v in gl)
     gsec, gfl, _, gcnt = agg.get("gemm", [1e-9, 0, 0, 0])
     asec, afl, aby, acnt = agg.get("attn_fwd", [1e-9, 0, 0, 0])
+    bsec, bfl, bby, bcnt = agg.get("attn_bwd", [1e-9, 0, 0, 0])
     roofline = {"kernel": "gemm_bf16_kernel (all sliced linears: fwd, dgrad, wgrad)", "bound": "tensor",
                 "achieved": gfl / gsec / 1e12, "peak": peak_tf, "unit": "TFLOP/s",
                 "frac": gfl / gsec / 1e12 / peak_tf, "traffic": traffic,
                 "traffic_note": "avg DRAM bytes per launch over the gemm launches in profiles/ncu_traffic.json", "launches": gcnt,
-                "avg_launch_us": gsec / max(gcnt, 1) * 1e6, "peak_source": peak_src}
+                "avg_launch_us": gsec / max(gcnt, 1) * 1e6, "peak_source": peak_src,
+                "timing": "CUDA events around each launch on its stream, launches pre-queued behind a spin kernel"}
     attn = {"kernel": "attn_fwd_kernel (fused QK^T + RPE gather + softmax + PV)", "bound": "hbm",
             "achieved": aby / asec / 1e9, "peak": hbm, "unit": "GB/s", "frac": aby / asec / 1e9 / hbm,
             "tflops": afl / asec / 1e12, "tflops_frac_of_peak": afl / asec / 1e12 / peak_tf, "launches": acnt,
             "avg_launch_us": asec / max(acnt, 1) * 1e6}
+    attn_bwd = {"kernel": "attention backward (all launches of cream_attn_bwd)", "bound": "hbm",
+                "achieved": bby / bsec / 1e9, "peak": hbm, "unit": "GB/s", "frac": bby / bsec / 1e9 / hbm,
+                "tflops": bfl / bsec / 1e12, "launches": bcnt, "avg_launch_us": bsec / max(bcnt, 1) * 1e6}
     imgs = B * world * K
     value = imgs / (ms * 1e-3)
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+        "metric": conf["metric"], "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
         "data": "synthetic",
-        "config": {"workload": WORKLOAD, "global_batch": B * world, "per_gpu_batch": B, "parallelism": f"dp{world}",
-                   "config_stream": "sample_configs with random.Random(0), identical on all ranks",
+        "config": {"workload": conf["workload"], "baseline_config": args.config, "global_batch": B * world,
+                   "per_gpu_batch": B, "parallelism": f"dp{world}",
+                   "config_stream": "sample_configs with random.Random(0), identical on all ranks; the SAME K "
+                                    "configurations are used for value, e2e and the roofline pass",
                    "l2": "inputs + activations per step (> 5 GB) far exceed the 126 MB L2; 4 rotating batches"},
         "e2e": {"value": imgs / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": B * 3 * 224 * 224 * 4 + B * 8,
                 "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / K, "last_loss": last_loss},
@@ -331,12 +383,18 @@ def main():
         "clocks": clocks,
         "roofline": roofline,
         "attention": attn,
-        "model_tflops": flops / (ms * 1e-3) / 1e12 / world,
-        "model_flops_frac_of_peak": flops / (ms * 1e-3) / 1e12 / world / peak_tf,
+        "attention_bwd": attn_bwd,
+        "byte_movers": {k: {"GB/s": agg[k][2] / agg[k][0] / 1e9, "frac_of_hbm_peak": agg[k][2] / agg[k][0] / 1e9 / hbm,
+                            "launches": agg[k][3], "avg_launch_us": agg[k][0] / agg[k][3] * 1e6}
+                        for k in ("ln_fwd", "ln_bwd", "cast_scale", "bias_grad") if k in agg and agg[k][0] > 0},
+        "gpu_time_share": {k: v[0] / max(sum(x[0] for x in agg.values()), 1e-12) for k, v in agg.items()},
+        "model_tflops": flops * world / (ms * 1e-3) / 1e12,
+        "model_tflops_per_gpu": flops / (ms * 1e-3) / 1e12,
+        "model_flops_frac_of_peak": flops / (ms * 1e-3) / 1e12 / peak_tf,
         "attn_core_share_of_flops": attn_flops / max(flops, 1.0),
     }
     if not args.no_cpu_baseline and world == 1:
-        line["cpu_baseline"], _ = cpu_baseline(2, 1)
+        line["cpu_baseline"], _ = cpu_baseline(2, 1, config=args.config)
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

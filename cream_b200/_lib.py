@@ -58,6 +58,62 @@ class AttnDesc(C.Structure):
     ]
 
 
+VIT_MAX_DEPTH = 32
+
+
+class VitLayer(C.Structure):
+    _fields_ = [
+        ("heads", c_int), ("ffn", c_int),
+        ("ln1_g", c_void_p), ("ln1_b", c_void_p), ("ln2_g", c_void_p), ("ln2_b", c_void_p),
+        ("wqkv", c_void_p), ("bqkv", c_void_p), ("wproj", c_void_p), ("bproj", c_void_p),
+        ("wfc1", c_void_p), ("bfc1", c_void_p), ("wfc2", c_void_p), ("bfc2", c_void_p),
+        ("tab", c_void_p * 4), ("g_tab", c_void_p * 4),
+        ("dp_scale", c_void_p),
+        ("g_ln1_g", c_void_p), ("g_ln1_b", c_void_p), ("g_ln2_g", c_void_p), ("g_ln2_b", c_void_p),
+        ("g_wqkv", c_void_p), ("g_bqkv", c_void_p), ("g_wproj", c_void_p), ("g_bproj", c_void_p),
+        ("g_wfc1", c_void_p), ("g_bfc1", c_void_p), ("g_wfc2", c_void_p), ("g_bfc2", c_void_p),
+    ]
+
+
+class VitDesc(C.Structure):
+    _fields_ = [
+        ("B", c_int), ("N", c_int), ("E", c_int), ("depth", c_int),
+        ("num_classes", c_int), ("in_chans", c_int), ("img_size", c_int), ("patch_size", c_int),
+        ("eps", c_float),
+        ("pool_first", c_int), ("pool_count", c_int),
+        ("qkv_interleaved", c_int), ("qkv_group_rows", c_int),
+        ("ld_wqkv", c_i64), ("ld_wproj", c_i64), ("ld_wfc1", c_i64), ("ld_wfc2", c_i64), ("ld_wpatch", c_i64), ("ld_whead", c_i64),
+        ("ld_gqkv", c_i64), ("ld_gproj", c_i64), ("ld_gfc1", c_i64), ("ld_gfc2", c_i64), ("ld_gpatch", c_i64), ("ld_ghead", c_i64),
+        ("scale", c_float),
+        ("af_grid", c_int), ("af_max_rel", c_int),
+        ("idx_a", c_void_p), ("idx_b", c_void_p), ("idx_va", c_void_p), ("idx_vb", c_void_p), ("ld_idx", c_int),
+        ("tab_nb", c_int), ("tab_row_off1", c_int),
+        ("tab_stride_b", c_i64), ("tab_stride_d", c_i64), ("tabv_stride_b", c_i64), ("tabv_stride_d", c_i64),
+        ("images", c_void_p),
+        ("wpatch", c_void_p), ("bpatch", c_void_p),
+        ("cls", c_void_p), ("pos", c_void_p), ("ld_pos", c_i64),
+        ("norm_g", c_void_p), ("norm_b", c_void_p),
+        ("whead", c_void_p), ("bhead", c_void_p),
+        ("logits", c_void_p), ("ld_logits", c_i64),
+        ("dlogits", c_void_p), ("ld_dlogits", c_i64),
+        ("g_wpatch", c_void_p), ("g_bpatch", c_void_p), ("g_cls", c_void_p), ("g_pos", c_void_p),
+        ("g_norm_g", c_void_p), ("g_norm_b", c_void_p), ("g_whead", c_void_p), ("g_bhead", c_void_p),
+        ("arena", c_void_p), ("arena_bytes", c_i64),
+        ("layers", VitLayer * VIT_MAX_DEPTH),
+    ]
+
+
+class AdamwSeg(C.Structure):
+    _fields_ = [
+        ("p", c_void_p), ("g", c_void_p), ("m", c_void_p), ("v", c_void_p),
+        ("shadow", c_void_p),
+        ("numel", c_i64),
+        ("rows", C.c_int32), ("cols", C.c_int32), ("shadow_ld", C.c_int32), ("qkv_group_rows", C.c_int32),
+        ("weight_decay", c_float),
+        ("step", C.c_int32),
+    ]
+
+
 # name -> (restype, argtypes); every symbol declared in include/cream_b200.h
 SIGNATURES = {
     "cream_version": (C.c_char_p, []),
@@ -93,6 +149,12 @@ SIGNATURES = {
     "cream_pack_tables_batch": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_i64, c_i64, c_void_p]),
     "cream_unpack_table_grads_batch": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_i64, c_i64,
                                                c_void_p]),
+    "cream_vit_arena_bytes": (c_i64, [C.POINTER(VitDesc)]),
+    "cream_vit_fwd": (c_int, [C.POINTER(VitDesc), c_void_p]),
+    "cream_vit_bwd": (c_int, [C.POINTER(VitDesc), c_int, c_int, c_void_p]),
+    "cream_vit_last_launches": (c_int, []),
+    "cream_xent_fwd_bwd": (c_int, [c_void_p, c_i64, c_void_p, c_void_p, c_void_p, c_i64, c_int, c_int, c_void_p]),
+    "cream_adamw_step": (c_int, [c_void_p, c_void_p, c_int, c_i64, c_float, c_float, c_float, c_float, c_void_p]),
     "cream_unpack_table_grads": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_i64, c_i64, c_i64,
                                          c_void_p, c_int, c_int, c_i64, c_i64, c_i64, c_void_p]),
 }

@@ -94,7 +94,7 @@ class FusedSupernet:
             geo = self._geo = self.engine_geometry()
         params = dict(self.named_parameters())
         scales = self.drop_path_scales(x.shape[0], x.device)
-        return engine.supernet_apply(params, geo, self.sampled_config(), x.float().contiguous(), scales)
+        return engine.supernet_apply(params, geo, self.sampled_config(), x.float().contiguous(), scales, owner=self)
 
 
 def fuse_reference(target):

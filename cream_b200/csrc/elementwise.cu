@@ -404,7 +404,8 @@ extern "C" int cream_pack_tables_batch(void* dst_bf16, int n_packs, int head_dim
                                        const float* const* src1_host, int nb, int row_off1, int64_t stride_b,
                                        int64_t stride_d, void* stream) {
   CB_REQUIRE(dst_bf16 && src0_host && n_packs > 0 && n_packs <= kMaxBatchPacks, "1..64 packs per call");
-  CB_REQUIRE(head_dim > 0 && head_dim <= 64 && nb > 0 && nb <= 64 && row_off1 + nb <= 64 && row_off1 >= nb, "pack geometry");
+  CB_REQUIRE(head_dim > 0 && head_dim <= 64 && nb > 0 && nb <= 64, "pack geometry");
+  if (src1_host != nullptr) CB_REQUIRE(row_off1 + nb <= 64 && row_off1 >= nb, "second table must fit rows [row_off1, 64)");
   PackBatch b{};
   for (int i = 0; i < n_packs; ++i) {
     b.src0[i] = src0_host[i];
@@ -419,7 +420,8 @@ extern "C" int cream_unpack_table_grads_batch(const float* dpack, int n_packs, i
                                               float* const* grad1_host, int nb, int row_off1, int64_t stride_b,
                                               int64_t stride_d, void* stream) {
   CB_REQUIRE(dpack && grad0_host && n_packs > 0 && n_packs <= kMaxBatchPacks, "1..64 packs per call");
-  CB_REQUIRE(head_dim > 0 && head_dim <= 64 && nb > 0 && nb <= 64 && row_off1 + nb <= 64 && row_off1 >= nb, "pack geometry");
+  CB_REQUIRE(head_dim > 0 && head_dim <= 64 && nb > 0 && nb <= 64, "pack geometry");
+  if (grad1_host != nullptr) CB_REQUIRE(row_off1 + nb <= 64 && row_off1 >= nb, "second table must fit rows [row_off1, 64)");
   PackBatch b{};
   for (int i = 0; i < n_packs; ++i) {
     b.grad0[i] = grad0_host[i];

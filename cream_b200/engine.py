@@ -299,7 +299,9 @@ def backward(P: Dict[str, torch.Tensor], geo: SupernetGeometry, saved: Saved, dl
 
 
 class _SupernetFn(torch.autograd.Function):
-    """autograd bridge: logits = f(images; sampled params); grads for exactly the sampled params."""
+    """autograd bridge over the PYTHON sequencing of the kernels (one ctypes call per launch).  Kept as
+    the readable statement of the launch sequence and as the cross-check of the native runtime, which
+    issues the very same launches from C++ (tests assert bit-identical results)."""
 
     @staticmethod
     def forward(ctx, geo, config, names, drop_path_scales, images, *params):
@@ -317,10 +319,72 @@ class _SupernetFn(torch.autograd.Function):
         return (None, None, None, None, None) + tuple(G[n] for n in ctx.names)
 
 
+# --------------------------------------------------------------------------------------------------
+# native runtime (csrc/vit_engine.cu): the default execution path
+# --------------------------------------------------------------------------------------------------
+USE_NATIVE = True
+
+
+def native_geometry(geo: SupernetGeometry):
+    from .native import VitGeometry
+    return VitGeometry(embed_dim=geo.embed_dim, depth=geo.depth, num_classes=geo.num_classes, img_size=geo.img_size,
+                       patch_size=geo.patch_size, in_chans=geo.in_chans, eps=geo.eps, gp=geo.gp, scale=64 ** -0.5,
+                       rpe="autoformer" if geo.relative_position else "none",
+                       max_relative_position=geo.max_relative_position)
+
+
+def native_runner(P: Dict[str, torch.Tensor], geo: SupernetGeometry, owner=None):
+    """The NativeVit bound to this parameter set (cached on `owner` when given, rebuilt if the
+    parameters moved)."""
+    from .native import AUTOFORMER, NativeVit
+    key = tuple(P[n].data_ptr() for n in ("cls_token", "head.weight")) + (geo.num_classes,)
+    cache = owner.__dict__.setdefault("_cream_native", {}) if owner is not None else {}
+    r = cache.get("runner")
+    if r is None or cache.get("key") != key:
+        r = NativeVit(P, native_geometry(geo), AUTOFORMER)
+        cache["runner"], cache["key"] = r, key
+    return r
+
+
+class _NativeFn(torch.autograd.Function):
+    """autograd bridge over the native runtime: ONE C call for the forward, one for the backward."""
+
+    @staticmethod
+    def forward(ctx, runner, config, names, drop_path_scales, images, *params):
+        runner.refresh_shadows(only_stale=True)
+        logits = runner.forward(config, images, drop_path_scales)
+        ctx.runner, ctx.names, ctx.generation = runner, names, runner.generation
+        ctx.shapes = [(p.shape, p.device) for p in params]
+        return logits.clone()
+
+    @staticmethod
+    def backward(ctx, dlogits):
+        r = ctx.runner
+        if r.generation != ctx.generation:
+            raise RuntimeError("cream_b200: the activations of this forward were overwritten by a later forward of the "
+                               "same model (the native runtime keeps ONE set of saved activations per model); run "
+                               "backward before the next forward, or set cream_b200.engine.USE_NATIVE = False")
+        G = {n: torch.zeros(shape, dtype=torch.float32, device=dev) for n, (shape, dev) in zip(ctx.names, ctx.shapes)}
+        r.bind_grads(G)
+        dl = ops.empty_f32(dlogits.shape[0], dlogits.shape[1], dlogits.device)
+        dl.copy_(dlogits)
+        r.backward(dl)
+        return (None, None, None, None, None) + tuple(G[n] for n in ctx.names)
+
+
 def supernet_apply(P: Dict[str, torch.Tensor], geo: SupernetGeometry, config: dict, images: torch.Tensor,
-                   drop_path_scales=None) -> torch.Tensor:
+                   drop_path_scales=None, owner=None) -> torch.Tensor:
     """Differentiable fused forward over a {name: parameter} dict (reference names)."""
-    if not torch.is_grad_enabled() or not any(p.requires_grad for p in P.values()):
+    validate_config(geo, config)
+    grad = torch.is_grad_enabled() and any(p.requires_grad for p in P.values())
+    if USE_NATIVE:
+        runner = native_runner(P, geo, owner)
+        if not grad:
+            runner.refresh_shadows(only_stale=True)
+            return runner.forward(config, images, drop_path_scales).clone()
+        names = sampled_param_names(geo, config)
+        return _NativeFn.apply(runner, config, names, drop_path_scales, images, *[P[n] for n in names])
+    if not grad:
         return forward(P, geo, config, images, drop_path_scales, save=False)[0].contiguous()
     names = sampled_param_names(geo, config)
     return _SupernetFn.apply(geo, config, names, drop_path_scales, images, *[P[n] for n in names])

@@ -25,6 +25,18 @@ PROFILE = None   # set to a list to record (kind, start_event, end_event, flops,
 _tls = threading.local()
 
 
+def _profiled(kind: str, flops: float, nbytes: float, launch):
+    """Run `launch()`; when PROFILE is a list, bracket it with CUDA events on the current stream."""
+    if PROFILE is None:
+        return launch()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    r = launch()
+    e1.record()
+    PROFILE.append((kind, e0, e1, flops, nbytes))
+    return r
+
+
 def _stream() -> int:
     """Current torch stream handle; also binds this host thread (autograd workers included) to
     torch's current device inside the library's own CUDA runtime instance."""
@@ -148,14 +160,8 @@ def gemm(M, N, K, a, lda, b, ldb, out, ldo, epi, *, groups=1, a_mn=0, b_mn=0, a_
     d.resid, d.ldr = _p(resid), ldr
     d.row_scale, d.rows_per_scale = _p(row_scale), rows_per_scale
     d.alpha, d.split_k = alpha, split_k
-    if PROFILE is not None:
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        check(_lib.load().cream_gemm_bf16(C.byref(d), _stream()), "cream_gemm_bf16")
-        e1.record()
-        PROFILE.append(("gemm", e0, e1, 2.0 * M * N * K * groups, 0.0))
-        return
-    check(_lib.load().cream_gemm_bf16(C.byref(d), _stream()), "cream_gemm_bf16")
+    _profiled("gemm", 2.0 * M * N * K * groups, 0.0,
+              lambda: check(_lib.load().cream_gemm_bf16(C.byref(d), _stream()), "cream_gemm_bf16"))
 
 
 def linear_fwd(x, w_sh, n_out, k_in, bias=None, *, epi=EPI_BF16, out=None, aux=None, resid=None,
@@ -223,8 +229,9 @@ def qkv_wgrad(dqkv, x, heads, k_in, dw_full):
 
 def bias_grad(dy, dbias_full):
     _check_2d(dy, torch.bfloat16, "dy", 2)
-    check(_lib.load().cream_bias_grad(_p(dy), dy.stride(0), _p(dbias_full), dy.shape[0], dy.shape[1], _stream()),
-          "cream_bias_grad")
+    _profiled("bias_grad", 0.0, 2.0 * dy.shape[0] * dy.shape[1],
+              lambda: check(_lib.load().cream_bias_grad(_p(dy), dy.stride(0), _p(dbias_full), dy.shape[0], dy.shape[1],
+                                                        _stream()), "cream_bias_grad"))
 
 
 def cast_scale(g, row_scale=None, rows_per_scale=1, dbias=None):
@@ -233,8 +240,9 @@ def cast_scale(g, row_scale=None, rows_per_scale=1, dbias=None):
     rows, cols = g.shape
     assert cols % 4 == 0
     out = empty_bf16(rows, cols, g.device)
-    check(_lib.load().cream_cast_scale(_p(g), g.stride(0), _p(out), out.stride(0), _p(row_scale), rows_per_scale,
-                                       _p(dbias), rows, cols, _stream()), "cream_cast_scale")
+    _profiled("cast_scale", 0.0, 6.0 * rows * cols,
+              lambda: check(_lib.load().cream_cast_scale(_p(g), g.stride(0), _p(out), out.stride(0), _p(row_scale),
+                                                         rows_per_scale, _p(dbias), rows, cols, _stream()), "cream_cast_scale"))
     return out
 
 
@@ -247,9 +255,10 @@ def layernorm_fwd(x, gamma, beta, eps, E, *, out_f32=False, save_stats=True):
     out = empty_f32(rows, E, x.device) if out_f32 else empty_bf16(rows, E, x.device)
     mean = torch.empty(rows, dtype=torch.float32, device=x.device) if save_stats else None
     rstd = torch.empty(rows, dtype=torch.float32, device=x.device) if save_stats else None
-    check(_lib.load().cream_layernorm_fwd(_p(x), x.stride(0), _p(gamma), _p(beta), eps, _p(out), out.stride(0),
-                                          int(out_f32), _p(mean), _p(rstd), rows, E, _stream()),
-          "cream_layernorm_fwd")
+    _profiled("ln_fwd", 0.0, rows * E * (4.0 + (4.0 if out_f32 else 2.0)),
+              lambda: check(_lib.load().cream_layernorm_fwd(_p(x), x.stride(0), _p(gamma), _p(beta), eps, _p(out),
+                                                            out.stride(0), int(out_f32), _p(mean), _p(rstd), rows, E,
+                                                            _stream()), "cream_layernorm_fwd"))
     return out, mean, rstd
 
 
@@ -257,11 +266,13 @@ def layernorm_bwd(dy, x, gamma, mean, rstd, E, dgamma_full, dbeta_full, resid_gr
     dy_f32 = dy.dtype == torch.float32
     rows = x.shape[0]
     dx = empty_f32(rows, E, x.device)
-    check(_lib.load().cream_layernorm_bwd(_p(dy), dy.stride(0), int(dy_f32), _p(x), x.stride(0), _p(gamma),
-                                          _p(mean), _p(rstd), _p(resid_grad),
-                                          resid_grad.stride(0) if resid_grad is not None else 0, _p(dx),
-                                          dx.stride(0), _p(dgamma_full), _p(dbeta_full), rows, E, _stream()),
-          "cream_layernorm_bwd")
+    nbytes = rows * E * ((4.0 if dy_f32 else 2.0) + 4.0 + 4.0 + (4.0 if resid_grad is not None else 0.0))
+    _profiled("ln_bwd", 0.0, nbytes,
+              lambda: check(_lib.load().cream_layernorm_bwd(_p(dy), dy.stride(0), int(dy_f32), _p(x), x.stride(0), _p(gamma),
+                                                            _p(mean), _p(rstd), _p(resid_grad),
+                                                            resid_grad.stride(0) if resid_grad is not None else 0, _p(dx),
+                                                            dx.stride(0), _p(dgamma_full), _p(dbeta_full), rows, E,
+                                                            _stream()), "cream_layernorm_bwd"))
     return dx
 
 
@@ -401,16 +412,9 @@ def attention_fwd(qkv, B, H, N, scale, *, tk=None, tv=None, per_head=False, idx=
     d = _attn_desc(B, H, N, scale, qkv, tk, tv, per_head, idx, bias, af)
     _set_dense(d, dense, B, H, N)
     d.out, d.ld_out, d.lse = _p(out), out.stride(0), _p(lse)
-    if PROFILE is not None:
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        check(_lib.load().cream_attn_fwd(C.byref(d), _stream()), "cream_attn_fwd")
-        e1.record()
-        nb = (NB_PACK if tk is not None else 0) + (NB_PACK if tv is not None else 0)
-        PROFILE.append(("attn_fwd", e0, e1, 4.0 * B * H * N * N * HEAD_DIM + 2.0 * B * H * N * HEAD_DIM * nb,
-                        4.0 * B * H * N * HEAD_DIM * 2))
-        return out, lse
-    check(_lib.load().cream_attn_fwd(C.byref(d), _stream()), "cream_attn_fwd")
+    nb = (NB_PACK if tk is not None else 0) + (NB_PACK if tv is not None else 0)
+    _profiled("attn_fwd", 4.0 * B * H * N * N * HEAD_DIM + 2.0 * B * H * N * HEAD_DIM * nb, 4.0 * B * H * N * HEAD_DIM * 2,
+              lambda: check(_lib.load().cream_attn_fwd(C.byref(d), _stream()), "cream_attn_fwd"))
     return out, lse
 
 
@@ -440,7 +444,11 @@ def attention_bwd(qkv, out, lse, dout, B, H, N, scale, *, tk=None, tv=None, per_
     if ddense is not None:
         assert ddense.dtype == torch.float32 and ddense.is_contiguous() and tuple(ddense.shape) == (B, H, N, N)
         d.ddense = _p(ddense)
-    check(_lib.load().cream_attn_bwd(C.byref(d), _stream()), "cream_attn_bwd", kernels=2)
+    nb = (NB_PACK if tk is not None else 0) + (NB_PACK if tv is not None else 0)
+    # backward = 2.5 x forward FLOPs (S recomputed); algorithmic bytes: q, k, v, o, do in, dq, dk, dv out
+    _profiled("attn_bwd", 2.5 * (4.0 * B * H * N * N * HEAD_DIM + 2.0 * B * H * N * HEAD_DIM * nb),
+              8.0 * B * H * N * HEAD_DIM * 2,
+              lambda: check(_lib.load().cream_attn_bwd(C.byref(d), _stream()), "cream_attn_bwd", kernels=2))
     return dqkv, dtk, dtv, dbias
 
 

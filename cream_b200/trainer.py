@@ -86,7 +86,11 @@ class StagedBatch:
 
 class SupernetTrainer:
     def __init__(self, model: Vision_TransformerSuper, choices: dict, lr: float = 5e-4, weight_decay: float = 0.05,
-                 process_group=None, grad_dtype: torch.dtype = torch.float32):
+                 process_group=None, native: bool = True):
+        """native=True (default): the step is a handful of C calls - cream_vit_fwd, cream_xent_fwd_bwd,
+        cream_vit_bwd (one call per all-reduce group when world > 1), cream_adamw_step (AdamW fused with
+        the bf16 shadow refresh).  native=False: the same kernels sequenced from Python with torch's
+        fused AdamW and torch's cross-entropy (kept as the cross-check of the native runtime)."""
         if not model.fusable():
             raise ValueError("SupernetTrainer drives the fused engine: the model must be pre-norm, change_qkv=True, "
                              "scale=False, drop_rate=0, attn_drop_rate=0 (DropPath is supported); use the module "
@@ -112,9 +116,24 @@ class SupernetTrainer:
         skip = model.no_weight_decay()
         decay, no_decay = [], []
         for n, p in self.params.items():
-            (no_decay if (p.ndim <= 1 or n.endswith(".bias") or n in skip) else decay).append(p)
-        self.optimizer = torch.optim.AdamW([{"params": decay, "weight_decay": weight_decay},
-                                            {"params": no_decay, "weight_decay": 0.0}], lr=lr, fused=model.pos_embed.is_cuda)
+            (no_decay if (p.ndim <= 1 or n.endswith(".bias") or n in skip) else decay).append(n)
+        self.native = None
+        if native and model.pos_embed.is_cuda:
+            from .native import FlatAdamW
+            self.native = engine.native_runner(self.params, self.geo, owner=model)   # shared with model(x)
+            self.native.bind_grads(self.buckets.views)
+            qkv_names = {f"blocks.{i}.attn.qkv.weight" for i in range(self.geo.depth)}
+            self.optimizer = FlatAdamW(self.params, self.buckets.views, set(decay), lr, weight_decay,
+                                       shadows=self.native.shadows, qkv_interleaved_names=qkv_names)
+            d = max(choices["depth"])
+            self.native.reserve({"layer_num": d, "embed_dim": [max(choices["embed_dim"])] * d,
+                                 "num_heads": [max(choices["num_heads"])] * d,
+                                 "mlp_ratio": [max(choices["mlp_ratio"])] * d}, 1)
+        else:
+            self.optimizer = torch.optim.AdamW([{"params": [self.params[n] for n in decay], "weight_decay": weight_decay},
+                                                {"params": [self.params[n] for n in no_decay], "weight_decay": 0.0}],
+                                               lr=lr, fused=model.pos_embed.is_cuda)
+        self._sampled_cache: Dict[int, tuple] = {}
         self.comm_stream = torch.cuda.Stream() if (self.world > 1 and model.pos_embed.is_cuda) else None
         self.copy_stream = torch.cuda.Stream() if model.pos_embed.is_cuda else None
         # two persistent device staging slots (no allocator traffic, hence no cudaMalloc, in steady state)
@@ -136,19 +155,49 @@ class SupernetTrainer:
         with torch.cuda.stream(self.comm_stream):
             dist.all_reduce(buf, op=dist.ReduceOp.AVG, group=self.pg)
 
+    def _sampled(self, cfg) -> tuple:
+        """Names of the parameters that take part in a subnet of this depth (identity layers excluded)."""
+        L = cfg["layer_num"]
+        if L not in self._sampled_cache:
+            self._sampled_cache[L] = tuple(engine.sampled_param_names(self.geo, cfg))
+        return self._sampled_cache[L]
+
+    def _assign_grads(self, names) -> None:
+        sampled = set(names)
+        for n, p in self.params.items():
+            p.grad = self.buckets.views[n] if n in sampled else None
+
     def _backward(self, saved, dlogits):
-        """engine.backward with per-layer bucket all-reduce interleaved."""
+        """engine.backward (Python sequencing) with per-layer bucket all-reduce interleaved."""
         cfg = saved.config
-        names = engine.sampled_param_names(self.geo, cfg)
+        names = self._sampled(cfg)
         self.buckets.master.zero_()          # one memset (140 MB for supernet-S, ~25 us) instead of one per group
         G = {n: self.buckets.views[n] for n in names}
         engine.backward(self.params, self.geo, saved, dlogits, grads=G,
                         on_group_done=self._allreduce if self.world > 1 else None)
         if self.comm_stream is not None:
             torch.cuda.current_stream().wait_stream(self.comm_stream)
-        sampled = set(names)
-        for n, p in self.params.items():
-            p.grad = self.buckets.views[n] if n in sampled else None
+        self._assign_grads(names)
+
+    def _backward_native(self, cfg, dlogits):
+        """cream_vit_bwd: one C call when single-GPU; one call per all-reduce group otherwise, each
+        group's bucket reduced (NCCL, side stream) as soon as its stage has been enqueued."""
+        self.buckets.master.zero_()
+        if self.native.G is not self.buckets.views:      # an autograd call through model(x) re-bound them
+            self.native.bind_grads(self.buckets.views)
+        L = cfg["layer_num"]
+        if self.world == 1:
+            self.native.backward(dlogits)
+            return
+        self.native.backward(dlogits, 0, 0)
+        self._allreduce("head")
+        for stage in range(1, L + 1):
+            self.native.backward(dlogits, stage, stage)
+            self._allreduce("block%d" % (L - stage))
+        self.native.backward(dlogits, L + 1, L + 1)
+        self._allreduce("embed")
+        if self.comm_stream is not None:
+            torch.cuda.current_stream().wait_stream(self.comm_stream)
 
     def stage(self, images: torch.Tensor, targets: torch.Tensor) -> StagedBatch:
         """Start the host->device copy of the NEXT batch on a side stream and return a handle for
@@ -179,10 +228,11 @@ class SupernetTrainer:
             ready.record(self.copy_stream)
         return StagedBatch(slot[0], slot[1], ready, i)
 
-    def step(self, images, targets: Optional[torch.Tensor] = None, config: Optional[dict] = None,
-             rnd=random) -> torch.Tensor:
-        """One training step; returns the (device) loss tensor without synchronising.
-        `images` is a tensor (host or device) or a StagedBatch from `stage`."""
+    def forward_backward(self, images, targets: Optional[torch.Tensor] = None, config: Optional[dict] = None,
+                         rnd=random) -> torch.Tensor:
+        """Sample (or take) a subnet, run forward, cross-entropy and backward with the overlapped
+        gradient all-reduce; parameters' `.grad` hold the (rank-averaged) gradients afterwards.
+        Returns the (device) loss tensor of the LOCAL batch without synchronising."""
         model = self.model
         dev = model.pos_embed.device
         staged = images if isinstance(images, StagedBatch) else None
@@ -197,14 +247,41 @@ class SupernetTrainer:
         self.last_config = cfg
         model.set_sample_config(cfg)
         scales = model.drop_path_scales(images.shape[0], dev)
-        logits, saved = engine.forward(self.params, self.geo, cfg, images.float().contiguous(), scales, save=True)
-        lg = logits.detach().requires_grad_(True)
-        loss = F.cross_entropy(lg, targets)
-        (dlogits,) = torch.autograd.grad(loss, lg)
+        images = images.float().contiguous()
+        if self.native is not None:
+            engine.validate_config(self.geo, cfg)
+            logits = self.native.forward(cfg, images, scales)
+            loss, dlogits = self.native.xent(logits, targets)
+            loss = loss[0]
+        else:
+            logits, saved = engine.forward(self.params, self.geo, cfg, images, scales, save=True)
+            lg = logits.detach().requires_grad_(True)
+            loss = F.cross_entropy(lg, targets)
+            (dlogits,) = torch.autograd.grad(loss, lg)
         if staged is not None and staged.slot >= 0:      # images (im2col) and targets (loss) have been consumed
             ev = torch.cuda.Event()
             ev.record()
             self._slot_free[staged.slot] = ev
-        self._backward(saved, dlogits)
-        self.optimizer.step()
+        if self.native is not None:
+            self._backward_native(cfg, dlogits)
+        else:
+            self._backward(saved, dlogits)
         return loss.detach()
+
+    def step(self, images, targets: Optional[torch.Tensor] = None, config: Optional[dict] = None,
+             rnd=random) -> torch.Tensor:
+        """One training step (the loop body of supernet_engine.py:49-107); returns the (device) loss
+        tensor without synchronising.  `images` is a tensor (host or device) or a StagedBatch."""
+        loss = self.forward_backward(images, targets, config, rnd)
+        if self.native is not None:
+            self.optimizer.step(self._sampled(self.last_config), cache_key=self.last_config["layer_num"])
+            self.native.mark_shadows_fresh()
+        else:
+            self.optimizer.step()
+        return loss
+
+    def sync_grads_to_params(self) -> None:
+        """Expose the gradients of the last step as `p.grad` (views of the flat buckets; None for the
+        parameters of un-sampled layers).  The native step does not need it; tests and external
+        optimizers do."""
+        self._assign_grads(self._sampled(self.last_config))

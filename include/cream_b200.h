@@ -255,6 +255,108 @@ int cream_unpack_table_grads_batch(const float* dpack, int n_packs, int head_dim
                                    float* const* grad1_host, int nb, int row_off1, int64_t stride_b,
                                    int64_t stride_d, void* stream);
 
+/* ------------------------------------------------------------------------- *
+ * Whole sampled-subnet forward / backward in ONE call each (the native runtime under
+ * Vision_TransformerSuper.forward, AutoFormer/model/supernet_transformer.py:147-172, 251-287, and
+ * under the DeiT + iRPE VisionTransformer, iRPE/DeiT-with-iRPE/rpe_vision_transformer.py:107-201):
+ * patch-embed GEMM, token assembly, per block LN -> QKV GEMM -> fused attention + RPE -> proj GEMM
+ * (+bias, DropPath, residual) -> LN -> fc1 GEMM (+bias, GELU) -> fc2 GEMM (+bias, DropPath,
+ * residual), final LN, pooling, head GEMM - about 11 kernel launches per block enqueued from C++
+ * with no allocation: every activation lives at a fixed offset of a caller-provided arena
+ * (cream_vit_arena_bytes), so the TMA descriptors are cache hits from the second step on.
+ *
+ * All parameter pointers are the reference's FULL supernet tensors (fp32 masters, bf16 shadows);
+ * the sampled slice is (E, heads, ffn) per layer.  Gradients are accumulated (+=) into full-size
+ * fp32 tensors that the caller zeroed; layers >= depth are not touched (grad stays "None").
+ * ------------------------------------------------------------------------- */
+#define CREAM_VIT_MAX_DEPTH 32
+
+typedef struct cream_vit_layer {
+  int heads, ffn;                                     /* sampled head count / hidden width   */
+  const float *ln1_g, *ln1_b, *ln2_g, *ln2_b;         /* attn_layer_norm / ffn_layer_norm    */
+  const void* wqkv; const float* bqkv;                /* bf16 shadow (see qkv_interleaved)    */
+  const void* wproj; const float* bproj;
+  const void* wfc1; const float* bfc1;
+  const void* wfc2; const float* bfc2;
+  /* relative-position tables of this layer, fp32 masters: K side [0], [1]; V side [2], [3]
+   * (AutoFormer: embeddings_table_v / _h of rel_pos_embed_k / _v; iRPE: lookup_table_weight in
+   * [0] or [2], the second of a pair only for the cross method).  NULL = absent. */
+  const float* tab[4];
+  float* g_tab[4];
+  const float* dp_scale;                              /* (2, B) DropPath factors or NULL     */
+  float *g_ln1_g, *g_ln1_b, *g_ln2_g, *g_ln2_b;
+  float *g_wqkv, *g_bqkv, *g_wproj, *g_bproj, *g_wfc1, *g_bfc1, *g_wfc2, *g_bfc2;
+} cream_vit_layer;
+
+typedef struct cream_vit_desc {
+  int B, N, E, depth;                /* batch, tokens (1 + grid^2), sampled embed dim, layers */
+  int num_classes, in_chans, img_size, patch_size;
+  float eps;                         /* LayerNorm epsilon                                     */
+  int pool_first, pool_count;        /* gp: (1, N-1); cls token: (0, 1)                       */
+  int qkv_interleaved;               /* 1: AutoFormer qkv_super rows (de-interleaved shadow, rows_per_group =
+                                      * qkv_group_rows); 0: plain [q; k; v] row blocks (DeiT)  */
+  int qkv_group_rows;
+  int64_t ld_wqkv, ld_wproj, ld_wfc1, ld_wfc2, ld_wpatch, ld_whead;   /* shadow row pitches    */
+  int64_t ld_gqkv, ld_gproj, ld_gfc1, ld_gfc2, ld_gpatch, ld_ghead;   /* fp32 gradient row pitches
+                                      * (= columns of the full master weights)                 */
+  /* attention */
+  float scale;
+  int af_grid, af_max_rel;           /* AutoFormer structure hint (see cream_attn_desc)        */
+  const uint8_t *idx_a, *idx_b, *idx_va, *idx_vb; int ld_idx;
+  int tab_nb, tab_row_off1;          /* buckets per table; packed row offset of the 2nd table  */
+  int64_t tab_stride_b, tab_stride_d;/* element strides of a table: (bucket, channel)          */
+  int64_t tabv_stride_b, tabv_stride_d; /* same for the V-side tables                          */
+  /* embedding / head parameters */
+  const float* images;               /* (B, C, img, img) fp32                                  */
+  const void* wpatch; const float* bpatch;
+  const float* cls; const float* pos; int64_t ld_pos;   /* pos may be NULL                     */
+  const float *norm_g, *norm_b;
+  const void* whead; const float* bhead;
+  float* logits; int64_t ld_logits;  /* out: (B, num_classes) fp32                             */
+  /* backward */
+  const float* dlogits; int64_t ld_dlogits;   /* (B, num_classes) fp32                         */
+  float *g_wpatch, *g_bpatch, *g_cls, *g_pos, *g_norm_g, *g_norm_b, *g_whead, *g_bhead;
+  /* activations + scratch */
+  void* arena; int64_t arena_bytes;
+  cream_vit_layer layers[CREAM_VIT_MAX_DEPTH];
+} cream_vit_desc;
+
+/* Bytes of arena needed for `desc` (uses B, N, E, depth, num_classes, geometry and the per-layer
+ * heads / ffn); size it once for the largest subnet of the search space. */
+int64_t cream_vit_arena_bytes(const cream_vit_desc* desc);
+int cream_vit_fwd(const cream_vit_desc* desc, void* stream);
+/* Backward stages run in order head (0), layers depth-1 .. 0 (stages 1 .. depth), embedding
+ * (stage depth+1).  One call may run any contiguous range [first_stage, last_stage], so a caller
+ * can start the gradient all-reduce of a layer as soon as its stage has been enqueued. */
+int cream_vit_bwd(const cream_vit_desc* desc, int first_stage, int last_stage, void* stream);
+/* Kernels enqueued by the last cream_vit_fwd / cream_vit_bwd call of this thread. */
+int cream_vit_last_launches(void);
+
+/* Mean cross-entropy over the batch and its gradient in one kernel:
+ * loss[0] = mean_b(logsumexp(logits[b]) - logits[b, target[b]]); dlogits = (softmax - onehot) / B. */
+int cream_xent_fwd_bwd(const float* logits, int64_t ld, const int64_t* targets, float* loss,
+                       float* dlogits, int64_t ldd, int B, int C, void* stream);
+
+/* ------------------------------------------------------------------------- *
+ * AdamW over a flat list of parameter segments, fused with the refresh of the bf16 weight shadows
+ * (torch.optim.AdamW semantics: decoupled weight decay, bias correction from a PER-PARAMETER step
+ * count, parameters without a gradient this step - identity layers - are skipped entirely).
+ * `segs` is a DEVICE array of n_segs descriptors; `active` a device int array (1 = has a gradient
+ * this step, the step counter is advanced by the kernel).
+ * ------------------------------------------------------------------------- */
+typedef struct cream_adamw_seg {
+  float* p; const float* g; float* m; float* v;   /* fp32, `numel` contiguous elements          */
+  void* shadow;                                   /* bf16 shadow or NULL                        */
+  int64_t numel;
+  int32_t rows, cols;                             /* 2-D view (rows, cols) of p for the shadow  */
+  int32_t shadow_ld;                              /* shadow row pitch (elements)                */
+  int32_t qkv_group_rows;                         /* > 0: de-interleave rows (cream_shadow_qkv) */
+  float weight_decay;
+  int32_t step;                                   /* updated in place by the kernel             */
+} cream_adamw_seg;
+int cream_adamw_step(cream_adamw_seg* segs_dev, const int32_t* active_dev, int n_segs, int64_t max_numel,
+                     float lr, float beta1, float beta2, float eps, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
