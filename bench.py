@@ -34,6 +34,9 @@ WORKLOAD = ("AutoFormer-S supernet random-sample training step (embed 320-448, h
 # BASELINE.json configs that are bench lines (the others are parity-test cases): c3 is the headline
 # (`metric` is quoted on it), c5 the largest search space.
 CONFIGS = {
+    "c2": dict(size="deit_s", batch=256, metric="DeiT-S + iRPE training images/sec (224^2, bs256)",
+               workload=("DeiT-S + iRPE (product method, contextual mode on keys, 50 buckets, shared head) training step, "
+                         "224^2, bs256, 12 blocks, DropPath 0.1, AdamW; 1 GPU")),
     "c3": dict(size="S", batch=128, metric=METRIC, workload=WORKLOAD),
     "c5": dict(size="B", batch=64, metric="supernet images/sec (224^2, bs64/GPU)",
                workload=("AutoFormer-B supernet random-sample training step (embed 528-624, heads 9-10, depth 14-16, "
@@ -96,6 +99,8 @@ def cpu_baseline(steps: int, warmup: int, batch: int = 4, config: str = "c3"):
     import torch.nn.functional as F
     from oracle import refload, vit_oracle as vo
     size = CONFIGS[config]["size"]
+    if size == "deit_s":
+        return cpu_baseline_deit(steps, warmup, batch)
     spec = {"S": vo.SUPERNET_S, "B": vo.SUPERNET_B, "T": vo.SUPERNET_T}[size]
     space = vo.SEARCH_SPACE[size]
     sd0 = vo.init_params(spec, seed=0)
@@ -157,6 +162,193 @@ def cpu_baseline(steps: int, warmup: int, batch: int = 4, config: str = "c3"):
                       f"{what} on {torch.get_num_threads()} host threads"}, total / len(times)
 
 
+def _reference_deit(device):
+    """The reference's own DeiT-S + iRPE VisionTransformer (unmodified files from the staged checkout)."""
+    import torch
+    from functools import partial
+    from oracle import refload
+    over = "reference"
+    if device != "cpu":
+        over = "reference_cuda" if refload.reference_rpe_ops_cuda() is not None else "reference"
+    vit = refload.rpe_vision_transformer(over)
+    cfg = vit.irpe.get_rpe_config(ratio=1.9, method='product', mode='ctx', shared_head=True, skip=1, rpe_on='k')
+    torch.manual_seed(0)
+    net = vit.VisionTransformer(patch_size=16, embed_dim=384, depth=12, num_heads=6, mlp_ratio=4, qkv_bias=True,
+                                drop_path_rate=0.1, norm_layer=partial(torch.nn.LayerNorm, eps=1e-6), rpe_config=cfg)
+    with torch.no_grad():
+        for n, p in net.named_parameters():
+            if "lookup_table" in n:
+                p.normal_(std=0.02)
+    return net.to(device).train(), over
+
+
+def cpu_baseline_deit(steps: int, warmup: int, batch: int = 4):
+    import torch
+    import torch.nn.functional as F
+    from oracle import refload
+    assert refload.available(), "config c2's CPU arm needs the staged reference (scripts/stage_reference.py)"
+    net, _ = _reference_deit("cpu")
+    opt = torch.optim.AdamW(net.parameters(), lr=5e-4, weight_decay=0.05)
+    torch.manual_seed(0)
+    images, targets = torch.randn(batch, 3, 224, 224), torch.randint(0, 1000, (batch,))
+    torch.set_num_threads(min(os.cpu_count() or 1, 16))
+    times = []
+    for s in range(warmup + steps):
+        t0 = time.perf_counter()
+        opt.zero_grad(set_to_none=True)
+        loss = F.cross_entropy(net(images), targets)
+        loss.backward()
+        opt.step()
+        loss.item()
+        if s >= warmup:
+            times.append(time.perf_counter() - t0)
+    total = sum(times)
+    return {"value": batch * len(times) / total, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "reference",
+            "sample": f"{len(times)} training steps of batch {batch}, fp32, iRPE/DeiT-with-iRPE rpe_vision_transformer.py "
+                      f"(unmodified, pure-PyTorch rpe fallback) on {torch.get_num_threads()} host threads"}, total / len(times)
+
+
+def bench_deit(args):
+    """BASELINE config 2: DeiT-S + iRPE (product, contextual, keys) bs256 on ONE B200: the native
+    runtime's training step against the reference model + the reference rpe_ops CUDA build on the same GPU."""
+    import torch
+    import torch.nn.functional as F
+    from cream_b200 import _lib, ops
+    from cream_b200.deit import DeitIrpe, DeitTrainer
+    from oracle import refload
+    assert int(os.environ.get("WORLD_SIZE", "1")) == 1, "config c2 is a single-GPU configuration"
+    conf = CONFIGS["c2"]
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(0)
+    _lib.load()
+    W, K, B = max(3, args.warmup), args.steps, args.batch or conf["batch"]
+    torch.manual_seed(0)
+    net = DeitIrpe(drop_path_rate=0.1).to(dev).train()
+    tr = DeitTrainer(net)
+    g = torch.Generator().manual_seed(1234)
+    n_host = 4
+    host_imgs = [torch.randn(B, 3, 224, 224, generator=g).pin_memory() for _ in range(n_host)]
+    host_tgts = [torch.randint(0, 1000, (B,), generator=g).pin_memory() for _ in range(n_host)]
+    dev_imgs, dev_tgts = [t.to(dev) for t in host_imgs], [t.to(dev) for t in host_tgts]
+    pin_loss = torch.zeros((), dtype=torch.float32).pin_memory()
+
+    def timed(n, from_host):
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = _lib.LAUNCHES[0]
+        host = []
+        e0.record()
+        last = 0.0
+        for s in range(n):
+            t0 = time.perf_counter()
+            if from_host:
+                loss = tr.step(host_imgs[s % n_host], host_tgts[s % n_host])       # pinned host -> device inside the step
+                pin_loss.copy_(loss, non_blocking=True)
+                torch.cuda.current_stream().synchronize() if s + 1 == n else None
+            else:
+                loss = tr.step(dev_imgs[s % n_host], dev_tgts[s % n_host])
+            host.append((time.perf_counter() - t0) * 1e3)
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1), _lib.LAUNCHES[0] - l0, host, float(pin_loss)
+
+    timed(W, False)
+    sampler = ClockSampler(0)
+    sampler.start()
+    ms, launches, host, _ = timed(K, False)
+    timed(2, True)
+    ms_e2e, _, _, last_loss = timed(K, True)
+    clocks = sampler.stop()
+
+    # roofline of the kernel north_star names (fused attention + iRPE): the attention kernels of one block
+    # at this configuration's shape, timed alone with CUDA events after the step measurements
+    H, N = 6, 197
+    qkv = ops.empty_bf16(B * N, 3 * 64 * H)
+    qkv.copy_(torch.randn(B * N, 3 * 64 * H, device=dev))
+    P = dict(net.named_parameters())
+    r = tr.native
+    tk = ops.new_pack(1, dev)
+    t0 = P["blocks.0.attn.rpe_k.lookup_table_weight"].detach()
+    ops.pack_tables(tk, 1, t0, t0.shape[2], 0, (t0.stride(0), t0.stride(2), t0.stride(1)))
+    from cream_b200 import ops as _o
+    ids, nb = _o.irpe_bucket_ids(3, 14, 14, 1, 1.9, 3.8, 15.2)
+    it = _o.irpe_index_table_u8(ids, dev)
+    dout = ops.empty_bf16(B * N, 64 * H)
+    dout.copy_(torch.randn(B * N, 64 * H, device=dev))
+    def attn_times(reps=10):
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        out, lse = ops.attention_fwd(qkv, B, H, N, 0.125, tk=tk, idx=(it, None, None, None))
+        ops.attention_bwd(qkv, out, lse, dout, B, H, N, 0.125, tk=tk, idx=(it, None, None, None))
+        torch.cuda.synchronize()
+        ev[0].record()
+        for _ in range(reps):
+            out, lse = ops.attention_fwd(qkv, B, H, N, 0.125, tk=tk, idx=(it, None, None, None))
+        ev[1].record()
+        for _ in range(reps):
+            ops.attention_bwd(qkv, out, lse, dout, B, H, N, 0.125, tk=tk, idx=(it, None, None, None))
+        ev[2].record()
+        torch.cuda.synchronize()
+        return ev[0].elapsed_time(ev[1]) / reps * 1e-3, ev[1].elapsed_time(ev[2]) / reps * 1e-3
+    t_fwd, t_bwd = attn_times()
+    fl_fwd = 4.0 * B * H * N * N * 64 + 2.0 * B * H * N * 64 * 64
+    by_fwd = 4.0 * B * H * N * 64 * 2
+    peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text()) if (ROOT / "MEASURED_PEAKS.json").exists() else {}
+    hbm, peak_tf = peaks.get("hbm_gbs", 6650.0), peaks.get("bf16_tflops_sustained", 1400.0)
+    roofline = {"kernel": "attn_fwd_kernel, iRPE contextual product gather on keys (the fused attention+iRPE kernel)",
+                "bound": "hbm", "achieved": by_fwd / t_fwd / 1e9, "peak": hbm, "unit": "GB/s", "frac": by_fwd / t_fwd / 1e9 / hbm,
+                "tflops": fl_fwd / t_fwd / 1e12, "tflops_frac_of_peak": fl_fwd / t_fwd / 1e12 / peak_tf, "avg_launch_us": t_fwd * 1e6,
+                "bwd_avg_us": t_bwd * 1e6, "bwd_tflops": 2.5 * fl_fwd / t_bwd / 1e12, "traffic": None,
+                "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md)"}
+
+    # ---- GPU-side reference on the same B200: reference model + reference rpe_ops CUDA build ----
+    gpu_ref = None
+    if refload.available():
+        try:
+            ref, over = _reference_deit(dev)
+            opt = torch.optim.AdamW(ref.parameters(), lr=5e-4, weight_decay=0.05, fused=True)
+            scaler = torch.amp.GradScaler("cuda")
+            def ref_step(x, y):
+                opt.zero_grad(set_to_none=True)
+                with torch.autocast("cuda", dtype=torch.float16):     # the reference trains with fp16 autocast (engine.py)
+                    loss = F.cross_entropy(ref(x), y)
+                scaler.scale(loss).backward()
+                scaler.step(opt)
+                scaler.update()
+                return loss
+            for s in range(3):
+                ref_step(dev_imgs[s % n_host], dev_tgts[s % n_host])
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            kk = max(3, K // 2)
+            for s in range(kk):
+                ref_step(dev_imgs[s % n_host], dev_tgts[s % n_host])
+            e1.record()
+            torch.cuda.synchronize()
+            rms = e0.elapsed_time(e1)
+            gpu_ref = {"value": B * kk / (rms * 1e-3), "unit": UNIT, "ms_per_step": rms / kk,
+                       "what": f"reference VisionTransformer (rpe_vision_transformer.py, unmodified) + rpe_ops={over}, "
+                               "fp16 autocast + GradScaler + fused AdamW, same GPU, same batch"}
+            del ref, opt
+        except Exception as e:   # noqa: BLE001
+            gpu_ref = {"unavailable": repr(e)[:300]}
+    imgs = B * K
+    line = {"metric": conf["metric"], "value": imgs / (ms * 1e-3), "unit": UNIT, "n_gpus": 1, "steps": K, "warmup": W,
+            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+            "data": "synthetic",
+            "config": {"workload": conf["workload"], "baseline_config": "c2", "global_batch": B, "per_gpu_batch": B,
+                       "parallelism": "dp1", "l2": "activations per step (> 5 GB) exceed the 126 MB L2; 4 rotating batches"},
+            "e2e": {"value": imgs / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": B * 3 * 224 * 224 * 4 + B * 8,
+                    "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / K, "last_loss": last_loss},
+            "gpu_launches": launches, "host_enqueue_ms_per_step": {"mean": sum(host) / len(host), "min": min(host)},
+            "clocks": clocks, "roofline": roofline, "gpu_reference": gpu_ref}
+    if gpu_ref and "value" in gpu_ref:
+        line["speedup_vs_gpu_reference"] = line["value"] / gpu_ref["value"]
+    if not args.no_cpu_baseline and refload.available():
+        line["cpu_baseline"], _ = cpu_baseline_deit(1, 1)
+    print(json.dumps(line))
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -184,6 +376,8 @@ def main():
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
+    if args.config == "c2":
+        return bench_deit(args)
 
     import torch
     import torch.distributed as dist

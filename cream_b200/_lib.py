@@ -55,6 +55,8 @@ class AttnDesc(C.Structure):
         ("workspace", c_void_p), ("workspace_bytes", c_i64),
         ("dense_bias", c_void_p), ("dense_stride_b", c_i64), ("dense_stride_h", c_i64), ("dense_stride_i", c_i64),
         ("ddense", c_void_p),
+        ("gp_grid", c_int), ("gp_w", c_int), ("gp_skip_id", c_int),
+        ("gp_lut_a", C.c_uint8 * 32), ("gp_lut_b", C.c_uint8 * 32),
     ]
 
 
@@ -87,6 +89,8 @@ class VitDesc(C.Structure):
         ("scale", c_float),
         ("af_grid", c_int), ("af_max_rel", c_int),
         ("idx_a", c_void_p), ("idx_b", c_void_p), ("idx_va", c_void_p), ("idx_vb", c_void_p), ("ld_idx", c_int),
+        ("gp_grid", c_int), ("gp_w", c_int), ("gp_skip_id", c_int),
+        ("gp_lut_a", C.c_uint8 * 32), ("gp_lut_b", C.c_uint8 * 32),
         ("tab_nb", c_int), ("tab_row_off1", c_int),
         ("tab_stride_b", c_i64), ("tab_stride_d", c_i64), ("tabv_stride_b", c_i64), ("tabv_stride_d", c_i64),
         ("images", c_void_p),

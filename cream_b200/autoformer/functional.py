@@ -266,21 +266,27 @@ class IrpeAttentionFn(torch.autograd.Function):
             ids_list = list(ids) if cross else [ids]
             dense, qsave = IrpeAttentionFn._q_term(qkv2, B, N, heads, scale, ids_list,
                                                    [rpe_q, rpe_q2] if cross else [rpe_q], mode)
+        gp = None
+        if not cross and tk is not None and tv is None and bias is None and dense is None:
+            side = int(round((N - 1) ** 0.5))
+            st = ops.irpe_grid_product_structure(ids, side, N - side * side) if side * side + 1 == N else None
+            if st is not None:
+                gp = (side,) + st
         out, lse = ops.attention_fwd(qkv2, B, heads, N, scale, tk=tk, tv=tv, per_head=per_head, idx=idx, bias=bias,
-                                     dense=dense)
+                                     dense=dense, gp=gp)
         ctx.save_for_backward(qkv2, out, lse, tk, tv, bias, rpe_k, rpe_v, rpe_k2, rpe_v2, rpe_q, rpe_q2, dense)
-        ctx.meta = (B, heads, N, scale, idx, per_head, mode, qkv.dtype, cross, ids, qsave)
+        ctx.meta = (B, heads, N, scale, idx, per_head, mode, qkv.dtype, cross, ids, qsave, gp)
         return out.reshape(B, N, ops.HEAD_DIM * heads)
 
     @staticmethod
     def backward(ctx, dout):
         qkv2, out, lse, tk, tv, bias, rpe_k, rpe_v, rpe_k2, rpe_v2, rpe_q, rpe_q2, dense = ctx.saved_tensors
-        B, heads, N, scale, idx, per_head, mode, dtype, cross, ids, qsave = ctx.meta
+        B, heads, N, scale, idx, per_head, mode, dtype, cross, ids, qsave, gp = ctx.meta
         half = ops.NB_PACK // 2
         d2 = ops.as_bf16_2d(dout)
         ddense = torch.empty((B, heads, N, N), dtype=torch.float32, device=qkv2.device) if dense is not None else None
         dqkv, dtk, dtv, dbias = ops.attention_bwd(qkv2, out, lse, d2, B, heads, N, scale, tk=tk, tv=tv,
-                                                  per_head=per_head, idx=idx, bias=bias, dense=dense, ddense=ddense)
+                                                  per_head=per_head, idx=idx, bias=bias, dense=dense, ddense=ddense, gp=gp)
         gk = gv = gk2 = gv2 = gq = gq2 = None
         if rpe_q is not None:
             tabs = [rpe_q, rpe_q2] if cross else [rpe_q]

@@ -18,6 +18,7 @@
 // The workspace round trip (2 x B*H*N*(Npad+64) bf16) costs about 3x the algorithmic bytes of the
 // fused ideal; a single fused kernel needs the dK/dV accumulators of all keys resident (CTA pairs).
 #include <cstdlib>
+#include <cstring>
 
 #include "attention_common.cuh"
 
@@ -36,6 +37,8 @@ struct BwdRowsParams {
   float scale;
   int ctx_k, ctx_v, shared_tables;
   int af_grid, af_max_rel;
+  int gp_grid, gp_w, gp_skip;          // iRPE grid-product structured mode (0 = off), see attention_fwd.cu
+  uint8_t lut_a[32], lut_b[32];
   const uint8_t* idx_a; const uint8_t* idx_b; const uint8_t* idx_va; const uint8_t* idx_vb;
   int ldi;
   const float* bias;
@@ -64,7 +67,7 @@ struct RowCtx {
   uint32_t trow;        // TMEM address of this thread's lane
   uint32_t s_r, s_dpb;  // shared addresses of this row's staged R (scaled) and dPB, fp32[kStride]
   uint32_t s_pb, s_dr;  // shared addresses of this row's PB (64 floats, rotated by sw) and dR (kStride)
-  uint32_t s_bias;
+  uint32_t s_bias, s_lut;
   int row, row_c, sw, half;
   float delta, lsel;
   int64_t wrow;
@@ -309,6 +312,128 @@ __device__ __forceinline__ void bwd_row_af(const BwdRowsParams& p, const RowCtx&
   rows_barrier();
 }
 
+// iRPE product method on a 14 x 14 grid + cls, contextual table on keys only (see softmax_gridprod in
+// attention_fwd.cu): id(i, j) = A[rj - ri] * W + B[cj - ci], the skip bucket when i or j is cls.
+// Gather: the staged R row is read at  base[rj] + off[cj]  (one integer add per element, registers).
+// Bucket sums dR[i, id] = sum_j dT[i, j] [id(i,j) = id]: A and B are monotone in the offsets, so the
+// keys of one bucket form a RECTANGLE of the grid; column sums are kept in 14 registers over a run of
+// grid rows with the same A and folded into the row's shared-memory buckets once per run - a plain
+// store per rectangle, no per-element read-modify-write.  The two threads of a row (keys 0..111 /
+// 112..207, see bwd_row_af) write to separate bucket rows (s_dr / the rotated s_pb), summed by the tail.
+template <int G>
+__device__ __forceinline__ void bwd_row_gridprod(const BwdRowsParams& p, const RowCtx& x) {
+  static_assert(G == 14 && kAfSplitCols == kAfSplitRows * G, "split is tied to the 14 x 14 grid");
+  constexpr int N = G * G + 1;
+  constexpr int LR = kAfSplitRows;
+  constexpr int NCC = kAfSplitCols / 16;
+  const bool patch = x.row >= 1 && x.row < N;
+  const bool live = x.row < N;
+  const int hi = x.half;
+  const int qi = patch ? x.row - 1 : 0;
+  const int ri = qi / G, ci = qi - ri * G;
+  const float sl = p.scale * kLog2e;
+  const float lsel = live ? x.lsel : 1e30f;
+  const uint32_t skip4 = 4u * p.gp_skip;
+  auto lut = [&](int which, int delta) -> uint32_t {   // component of the bucket id for an offset
+    uint32_t v;
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(x.s_lut + 32 * which + (delta + G - 1)));
+    return v;
+  };
+  // byte offsets into a 64-float bucket row: row part (A * W) per local grid row, column part per column
+  uint32_t offa[LR], offb[G];
+  const int rows_here = hi ? G - LR : LR;             // grid rows of this half: 8 / 6
+#pragma unroll
+  for (int t = 0; t < LR; ++t) {
+    const int rj = min(t, rows_here - 1) + LR * hi;   // rows that do not exist repeat the last one (never flushed)
+    offa[t] = patch ? 4u * lut(0, rj - ri) * p.gp_w : skip4;
+  }
+#pragma unroll
+  for (int t = 0; t < G; ++t) offb[t] = patch ? 4u * lut(1, t - ci) : 0u;
+  // local key 0: the cls key (skip bucket) for half 0, grid position (7, 13) for half 1
+  const uint32_t first4 = (hi && patch) ? 4u * (lut(0, LR - 1 - ri) * p.gp_w + lut(1, G - 1 - ci)) : skip4;
+  auto bucket_addr = [&](uint32_t off4) -> uint32_t {  // this half's private bucket row
+    return hi ? x.s_pb + 4u * (((off4 >> 2) + x.sw) & 63u) : x.s_dr + off4;
+  };
+  for (int k = 0; k < kNB; ++k) sts_f32(bucket_addr(4u * k), 0.f);
+
+  float colacc[G], df = 0.f;
+#pragma unroll
+  for (int t = 0; t < G; ++t) colacc[t] = 0.f;
+  auto flush = [&](uint32_t oa) {
+    float acc = 0.f;
+#pragma unroll
+    for (int cj = 0; cj < G; ++cj) {
+      acc += colacc[cj];
+      colacc[cj] = 0.f;
+      const bool end = (cj == G - 1) || (offb[(cj + 1) % G] != offb[cj]);
+      if (end) { sts_f32(bucket_addr(oa + offb[cj]), acc); acc = 0.f; }
+    }
+  };
+
+  const uint32_t t_in = x.trow + kAfSplitCols * hi;
+  const uint32_t t_out = hi ? x.trow + kDtHiCol : x.trow;
+  const int64_t w0 = x.wrow + kAfSplitCols * hi;
+  uint32_t rtb[2][16], rpb[2][16];
+  tmem_ld16(t_in, rtb[0]);
+  tmem_ld16(t_in + 256, rpb[0]);
+#pragma unroll
+  for (int cc = 0; cc < NCC; ++cc) {
+    if (cc == NCC - 1 && hi) break;
+    uint32_t (&rt)[16] = rtb[cc & 1];
+    uint32_t (&rp)[16] = rpb[cc & 1];
+    tmem_ld_wait();
+    if (cc + 1 < NCC && !(cc + 1 == NCC - 1 && hi)) {
+      tmem_ld16(t_in + (cc + 1) * 16, rtb[(cc + 1) & 1]);
+      tmem_ld16(t_in + 256 + (cc + 1) * 16, rpb[(cc + 1) & 1]);
+    }
+    float pv[16], dt[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      const int j0 = cc * 16 + k;
+      float pr, d;
+      if (j0 == 0) {
+        const float e = fmaf(lds_f32(x.s_r + first4), kLog2e, -lsel);
+        pr = fast_exp2(fmaf(sl, __uint_as_float(rt[k]), e));
+        d = pr * (__uint_as_float(rp[k]) - x.delta);
+        df = d;
+      } else {
+        const int rj = (j0 - 1) / G, cj = (j0 - 1) % G;
+        const bool exists = hi == 0 || rj < G - LR;
+        const float e = exists ? fmaf(lds_f32(x.s_r + offa[rj] + offb[cj]), kLog2e, -lsel) : -1e30f;
+        pr = fast_exp2(fmaf(sl, __uint_as_float(rt[k]), e));
+        d = pr * (__uint_as_float(rp[k]) - x.delta);
+        colacc[cj] += d;
+        if (cj == G - 1 && rj + 1 < LR) {               // end of a grid row: fold the run if A changes
+          if (offa[rj + 1] != offa[rj]) flush(offa[rj]);
+        }
+      }
+      pv[k] = pr;
+      dt[k] = d;
+    }
+    uint32_t pk[8], dk[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      pk[k] = pack_bf16x2(pv[2 * k], pv[2 * k + 1]);
+      dk[k] = pack_bf16x2(dt[2 * k], dt[2 * k + 1]);
+    }
+    tmem_st8(t_out + cc * 8, dk);
+    if (live) {
+      uint4* wp = reinterpret_cast<uint4*>(p.ws_p + w0 + cc * 16);
+      uint4* wd = reinterpret_cast<uint4*>(p.ws_dt + w0 + cc * 16);
+      wp[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+      wp[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+      wd[0] = make_uint4(dk[0], dk[1], dk[2], dk[3]);
+      wd[1] = make_uint4(dk[4], dk[5], dk[6], dk[7]);
+    }
+  }
+  flush(offa[LR - 1]);                                  // the last run (rows past the half's end repeat its offset)
+  {                                                     // local key 0 may share a bucket with a rectangle
+    const uint32_t a = bucket_addr(first4);
+    sts_f32(a, lds_f32(a) + df);
+  }
+  rows_barrier();
+}
+
 __global__ void __launch_bounds__(kRowsThreads, 1)
 attn_bwd_rows_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_kv,
                      const __grid_constant__ CUtensorMap map_do, const __grid_constant__ CUtensorMap map_tk,
@@ -327,7 +452,8 @@ attn_bwd_rows_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
   uint8_t* sdPB = sR + 128 * kStride * 4;   // fp32 [128][kStride]
   uint8_t* sBias = sdPB + 128 * kStride * 4;
   uint8_t* sDbias = sBias + 64 * 4;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sDbias + 64 * 4);
+  uint8_t* sLut = sDbias + 64 * 4;          // 64 bytes: grid-product row / column components
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sLut + 64);
   uint64_t* bar_ld = bars + 0;
   uint64_t* bar_r = bars + 1;
   uint64_t* bar_rfree = bars + 2;
@@ -360,6 +486,8 @@ attn_bwd_rows_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
     sts_f32(smem_u32(sBias) + 4 * (threadIdx.x - 32), p.bias ? p.bias[tab * 64 + threadIdx.x - 32] : 0.f);
     sts_f32(smem_u32(sDbias) + 4 * (threadIdx.x - 32), 0.f);
   }
+  if (p.gp_grid != 0 && threadIdx.x >= 96 && threadIdx.x < 160)
+    sLut[threadIdx.x - 96] = threadIdx.x < 128 ? p.lut_a[threadIdx.x - 96] : p.lut_b[threadIdx.x - 128];
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -431,6 +559,7 @@ attn_bwd_rows_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
     x.s_pb = smem_u32(sQ) + r_local * 64 * 4;
     x.s_dr = smem_u32(sV) + r_local * kStride * 4;
     x.s_bias = smem_u32(sBias);
+    x.s_lut = smem_u32(sLut);
     x.row = row;
     x.row_c = min(row, p.N - 1);
     x.drow = p.dense ? p.dense + b * p.dense_sb + head * p.dense_sh + x.row_c * p.dense_si : nullptr;
@@ -491,6 +620,7 @@ attn_bwd_rows_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
     RT(4);
 
     if (p.af_grid == 14) bwd_row_af<14>(p, x);
+    else if (p.gp_grid == 14) bwd_row_gridprod<14>(p, x);
     else bwd_row_generic(p, x);
     RT(5);
 
@@ -501,8 +631,15 @@ attn_bwd_rows_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
 #pragma unroll
       for (int k = 0; k < 16; ++k) {
         const int b0 = c * 32 + 2 * k;
-        pk[k] = pack_bf16x2(lds_f32(x.s_pb + 4 * ((b0 + x.sw) & 63)), lds_f32(x.s_pb + 4 * (((b0 + 1) + x.sw) & 63)));
-        dk[k] = pack_bf16x2(lds_f32(x.s_dr + 4 * b0), lds_f32(x.s_dr + 4 * (b0 + 1)));
+        const float q0 = lds_f32(x.s_pb + 4 * ((b0 + x.sw) & 63)), q1 = lds_f32(x.s_pb + 4 * (((b0 + 1) + x.sw) & 63));
+        const float r0 = lds_f32(x.s_dr + 4 * b0), r1 = lds_f32(x.s_dr + 4 * (b0 + 1));
+        if (p.gp_grid != 0) {          // grid-product path: the two halves' dR rows; no value-side bucket sums
+          pk[k] = 0u;
+          dk[k] = pack_bf16x2(q0 + r0, q1 + r1);
+        } else {
+          pk[k] = pack_bf16x2(q0, q1);
+          dk[k] = pack_bf16x2(r0, r1);
+        }
       }
       if (p.ctx_k) tmem_st16(x.trow + Npad / 2 + c * 16, dk);
       if (row < p.N) {
@@ -775,6 +912,17 @@ extern "C" int cream_attn_bwd(const cream_attn_desc* d, void* stream_) {
   p.dense = d->dense_bias; p.dense_sb = d->dense_stride_b; p.dense_sh = d->dense_stride_h; p.dense_si = d->dense_stride_i;
   p.ddense = d->ddense;
   if (p.dense != nullptr || p.ddense != nullptr) p.af_grid = 0;   // generic gather path only
+  if (d->gp_grid == 14 && d->gp_grid * d->gp_grid + 1 == d->N && ctx_k && !ctx_v && d->idx_b == nullptr && !d->bias_pack &&
+      p.dense == nullptr && p.ddense == nullptr && p.af_grid == 0 && d->gp_w >= 1 && d->gp_skip_id >= 0 && d->gp_skip_id < kNB) {
+    bool ok = true;
+    for (int t = 0; t < 2 * d->gp_grid - 1; ++t)
+      ok = ok && d->gp_lut_a[t] * d->gp_w + d->gp_lut_b[t] < kNB && d->gp_lut_b[t] < d->gp_w;
+    if (ok) {
+      p.gp_grid = d->gp_grid; p.gp_w = d->gp_w; p.gp_skip = d->gp_skip_id;
+      std::memcpy(p.lut_a, d->gp_lut_a, 32);
+      std::memcpy(p.lut_b, d->gp_lut_b, 32);
+    }
+  }
 
   const uint64_t dims[3] = {static_cast<uint64_t>(3 * d->H * kD), static_cast<uint64_t>(d->N), static_cast<uint64_t>(d->B)};
   const uint64_t strides[3] = {1, static_cast<uint64_t>(d->ld_qkv), static_cast<uint64_t>(d->N) * d->ld_qkv};
@@ -806,7 +954,7 @@ extern "C" int cream_attn_bwd(const cream_attn_desc* d, void* stream_) {
     attr_set = true;
   }
   const size_t smem_rows = 2 * 16384 + static_cast<size_t>(Npad) * 128 + 8192 +
-                           std::max<size_t>(Npad * 128, 26 * 1024) + 8192 + 2 * 128 * kStride * 4 + 2 * 64 * 4 + 128;
+                           std::max<size_t>(Npad * 128, 26 * 1024) + 8192 + 2 * 128 * kStride * 4 + 2 * 64 * 4 + 64 + 128;
   CB_REQUIRE(smem_rows <= 227 * 1024, "shared memory budget");
   dim3 grid(ceil_div(d->N, 128), d->H, d->B);
 #ifdef CREAM_TRACE

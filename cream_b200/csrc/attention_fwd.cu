@@ -19,6 +19,8 @@
 //   warps 1..4       : one thread per query row: R copy-out, softmax, epilogue
 // TMEM columns: S fp32 [0,Npad) -> P bf16x2 in place [0,Npad/2) | PB [Npad/2,Npad/2+32);
 //               R fp32 [192,256) (dead before S cols >= 192 are produced); O fp32 [192,256).
+#include <cstring>
+
 #include "attention_common.cuh"
 
 namespace cb {
@@ -37,6 +39,8 @@ struct AttnFwdParams {
   int ctx_k, ctx_v;                    // contextual tables on K / V present
   int shared_tables;                   // 1: one table pack for all heads
   int af_grid, af_max_rel;             // AutoFormer structured mode (0 = generic index tables)
+  int gp_grid, gp_w, gp_skip;          // iRPE grid-product structured mode (0 = off)
+  uint8_t lut_a[32], lut_b[32];        // bucket row / column components by (delta + grid - 1)
   const uint8_t* idx_a; const uint8_t* idx_b;   // K-side gather indices (N, ldi), values < 64
   const uint8_t* idx_va; const uint8_t* idx_vb; // V-side
   int ldi;
@@ -240,6 +244,77 @@ __device__ __forceinline__ void softmax_af(const AttnFwdParams& p, uint32_t trow
   sum_out = sum;
 }
 
+// ---------------------------------------------------------------------------------------
+// iRPE product method on a G x G grid + cls (irpe.py:176-202), contextual table on keys only:
+//   id(i, j) = A[rj - ri] * W + B[cj - ci]   for patch tokens,  the skip bucket when i or j is cls.
+// The byte offsets of a row's 2 x G components live in registers; with the column loop fully
+// unrolled one element costs an integer add, a 16-bit shared load and an FFMA - no index bytes
+// from global memory, no byte extraction.  (V-side tables take the generic path.)
+// ---------------------------------------------------------------------------------------
+template <int G>
+__device__ __forceinline__ void softmax_gridprod(const AttnFwdParams& p, uint32_t trow, uint32_t sr_row, uint32_t slut,
+                                                 int row, float& mx_out, float& sum_out) {
+  constexpr int N = G * G + 1;
+  constexpr int NPAD = (N + 15) / 16 * 16;
+  constexpr int NCH = NPAD / 16;
+  const bool patch = row >= 1 && row < N;
+  const int qi = patch ? row - 1 : 0;
+  const int ri = qi / G, ci = qi - ri * G;
+  const uint32_t skip_addr = sr_row + 2 * p.gp_skip;
+  uint32_t base_a[G], off_b[G];
+#pragma unroll
+  for (int t = 0; t < G; ++t) {
+    uint32_t a, b;
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(a) : "r"(slut + (t - ri + G - 1)));
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(b) : "r"(slut + 32 + (t - ci + G - 1)));
+    base_a[t] = patch ? sr_row + 2 * a * p.gp_w : skip_addr;
+    off_b[t] = patch ? 2 * b : 0;
+  }
+  const float r0 = lds_f16(skip_addr);
+  float mx = -INFINITY;
+  uint32_t rb[2][16];
+  tmem_ld16(trow, rb[0]);
+#pragma unroll
+  for (int c = 0; c < NCH; ++c) {
+    uint32_t (&raw)[16] = rb[c & 1];
+    tmem_ld_wait();
+    if (c + 1 < NCH) tmem_ld16(trow + (c + 1) * 16, rb[(c + 1) & 1]);
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      const int j = c * 16 + k;
+      float t;
+      if (j >= N) t = -INFINITY;
+      else if (j == 0) t = fmaf(p.scale, __uint_as_float(raw[k]), r0);
+      else t = fmaf(p.scale, __uint_as_float(raw[k]), lds_f16(base_a[(j - 1) / G] + off_b[(j - 1) % G]));
+      mx = fmaxf(mx, t);
+      raw[k] = __float_as_uint(t);
+    }
+    tmem_st16(trow + c * 16, raw);
+  }
+  tmem_st_wait();
+  float sum = 0.f;
+  const float mxl = mx * kLog2e;
+  tmem_ld16(trow, rb[0]);
+#pragma unroll
+  for (int c = 0; c < NCH; ++c) {
+    uint32_t (&raw)[16] = rb[c & 1];
+    tmem_ld_wait();
+    if (c + 1 < NCH) tmem_ld16(trow + (c + 1) * 16, rb[(c + 1) & 1]);
+    float pv[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      pv[k] = fast_exp2(fmaf(__uint_as_float(raw[k]), kLog2e, -mxl));
+      sum += pv[k];
+    }
+    uint32_t pk[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) pk[k] = pack_bf16x2(pv[2 * k], pv[2 * k + 1]);
+    tmem_st8(trow + c * 8, pk);
+  }
+  mx_out = mx;
+  sum_out = sum;
+}
+
 __global__ void __launch_bounds__(kThreads, 2)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_kv,
                 const __grid_constant__ CUtensorMap map_tk, const __grid_constant__ CUtensorMap map_tv,
@@ -255,7 +330,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
   uint8_t* sTV = sV + kv_bytes;
   uint8_t* sR = sTV + 8192;          // fp16 [128][kRStride]
   uint8_t* sBias = sR + 128 * kRStride * 2;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sBias + 64 * 4);
+  uint8_t* sLut = sBias + 64 * 4;    // 64 bytes: grid-product row / column components
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sLut + 64);
   uint64_t* bar_qk = bars + 0;
   uint64_t* bar_v = bars + 1;
   uint64_t* bar_r = bars + 2;
@@ -287,6 +363,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
   if (p.bias != nullptr && threadIdx.x >= 32 && threadIdx.x < 96)
     sts_f32(smem_u32(sBias) + 4 * (threadIdx.x - 32),
             p.bias[(p.shared_tables ? 0 : head) * 64 + threadIdx.x - 32]);
+  if (p.gp_grid != 0 && threadIdx.x >= 96 && threadIdx.x < 160)
+    sLut[threadIdx.x - 96] = threadIdx.x < 128 ? p.lut_a[threadIdx.x - 96] : p.lut_b[threadIdx.x - 128];
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -382,6 +460,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
     float mx, sum;
     if (p.af_grid == 14) {
       softmax_af<14>(p, trow, sr_row, smem_u32(smem) + r_local * kPBStrideAF * 4, row, mx, sum);
+    } else if (p.gp_grid == 14) {
+      softmax_gridprod<14>(p, trow, sr_row, smem_u32(sLut), row, mx, sum);
     } else {
       const float* drow = p.dense ? p.dense + b * p.dense_sb + head * p.dense_sh + row_c * p.dense_si : nullptr;
       softmax_generic(p, trow, sr_row, smem_u32(smem) + r_local * kPBStride * 4, smem_u32(sBias), row_c, drow, mx, sum);
@@ -465,6 +545,19 @@ extern "C" int cream_attn_fwd(const cream_attn_desc* d, void* stream_) {
     }
   }
 
+  // structured iRPE product gather: 14 x 14 grid + cls, one contextual table on keys, nothing else
+  if (d->gp_grid == 14 && d->gp_grid * d->gp_grid + 1 == d->N && ctx_k && !ctx_v && d->idx_b == nullptr && !d->bias_pack &&
+      d->dense_bias == nullptr && p.af_grid == 0 && d->gp_w >= 1 && d->gp_skip_id >= 0 && d->gp_skip_id < kNB) {
+    bool ok = true;
+    for (int t = 0; t < 2 * d->gp_grid - 1; ++t)
+      ok = ok && d->gp_lut_a[t] * d->gp_w + d->gp_lut_b[t] < kNB && d->gp_lut_b[t] < d->gp_w;
+    if (ok) {
+      p.gp_grid = d->gp_grid; p.gp_w = d->gp_w; p.gp_skip = d->gp_skip_id;
+      std::memcpy(p.lut_a, d->gp_lut_a, 32);
+      std::memcpy(p.lut_b, d->gp_lut_b, 32);
+    }
+  }
+
   const uint64_t dims[3] = {static_cast<uint64_t>(3 * d->H * kD), static_cast<uint64_t>(d->N),
                             static_cast<uint64_t>(d->B)};
   const uint64_t strides[3] = {1, static_cast<uint64_t>(d->ld_qkv),
@@ -488,7 +581,7 @@ extern "C" int cream_attn_fwd(const cream_attn_desc* d, void* stream_) {
   if (!mq || !mkv || !mtk || !mtv) return CREAM_ERR_CUDA;
 
   const size_t smem_bytes = 16384 + std::max<size_t>(Npad * 128, 11 * 1024) +
-                            static_cast<size_t>(Npad) * 128 + 2 * 8192 + 128 * kRStride * 2 + 64 * 4 + 128;
+                            static_cast<size_t>(Npad) * 128 + 2 * 8192 + 128 * kRStride * 2 + 64 * 4 + 64 + 128;
   static bool attr_set = false;
   if (!attr_set) {
     CB_CUDA_OK(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,

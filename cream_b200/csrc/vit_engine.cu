@@ -226,6 +226,9 @@ void fill_attn(const cream_vit_desc& d, const Bufs& b, int i, cream_attn_desc& a
   a.idx_va = a.tv_pack ? d.idx_va : nullptr; a.idx_vb = a.tv_pack ? d.idx_vb : nullptr;
   a.ld_idx = d.ld_idx;
   a.af_grid = d.af_grid; a.af_max_rel = d.af_max_rel;
+  a.gp_grid = d.gp_grid; a.gp_w = d.gp_w; a.gp_skip_id = d.gp_skip_id;
+  std::memcpy(a.gp_lut_a, d.gp_lut_a, sizeof(a.gp_lut_a));
+  std::memcpy(a.gp_lut_b, d.gp_lut_b, sizeof(a.gp_lut_b));
 }
 
 }  // namespace

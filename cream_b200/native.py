@@ -153,6 +153,11 @@ class NativeVit:
             ids, nb = ops.irpe_bucket_ids(3, geo.grid, geo.grid, skip, 1 * ratio, 2 * ratio, 8 * ratio)
             it = ops.irpe_index_table_u8(ids, self.device)
             d.idx_a, d.ld_idx = _p(it), it.stride(0)
+            gp = ops.irpe_grid_product_structure(ids, geo.grid, skip)
+            if gp is not None:
+                d.gp_grid, d.gp_w, d.gp_skip_id = geo.grid, gp[0], gp[1]
+                C.memmove(d.gp_lut_a, gp[2].ctypes.data, 32)
+                C.memmove(d.gp_lut_b, gp[3].ctypes.data, 32)
             t0 = P[lay.tables[0].format(i=0)]              # (1, 64, nb): [0, channel, bucket]
             assert t0.shape[0] == 1 and t0.shape[1] == ops.HEAD_DIM and t0.shape[2] == nb, "shared-head contextual table"
             d.tab_nb, d.tab_row_off1 = nb, 0

@@ -329,6 +329,39 @@ def irpe_index_table_u8(ids: np.ndarray, device, offset: int = 0) -> torch.Tenso
     return _INDEX_CACHE[key]
 
 
+def irpe_grid_product_structure(ids: np.ndarray, grid: int, skip: int):
+    """If the bucket ids of a (skip + grid*grid)-token sequence have the iRPE product structure
+    (irpe.py:176-202)  id(i, j) = A[rj - ri] * W + B[cj - ci]  for patch tokens and one skip bucket for
+    every pair that involves the cls token, return (W, skip_id, lut_a, lut_b) with the two components
+    indexed by (delta + grid - 1); otherwise None.  VERIFIED against the full table, so the kernels'
+    register-arithmetic gather is bit-for-bit the table gather."""
+    key = ("gp", ids.tobytes(), grid, skip)
+    if key in _INDEX_CACHE:
+        return _INDEX_CACHE[key]
+    out = None
+    n = skip + grid * grid
+    if skip == 1 and ids.shape == (n, n) and grid <= 16:
+        skip_id = int(ids[0, 0])
+        nb = int(ids.max()) + 1
+        W = int(round((nb - 1) ** 0.5))
+        patch = ids[1:, 1:].reshape(grid, grid, grid, grid)                 # (ri, ci, rj, cj)
+        if W * W == nb - 1 and skip_id == nb - 1 and (ids[0, :] == skip_id).all() and (ids[:, 0] == skip_id).all():
+            lut_a = np.zeros(32, np.uint8)
+            lut_b = np.zeros(32, np.uint8)
+            for dlt in range(-(grid - 1), grid):
+                r0, r1 = max(0, -dlt), max(0, dlt)
+                lut_a[dlt + grid - 1] = patch[r0, 0, r1, 0] // W
+                lut_b[dlt + grid - 1] = patch[0, r0, 0, r1] % W
+            r = np.arange(grid)
+            da = lut_a[(r[None, :] - r[:, None]) + grid - 1].astype(np.int64)      # (ri, rj)
+            db = lut_b[(r[None, :] - r[:, None]) + grid - 1].astype(np.int64)      # (ci, cj)
+            want = da[:, None, :, None] * W + db[None, :, None, :]
+            if (want == patch).all():
+                out = (W, skip_id, lut_a, lut_b)
+    _INDEX_CACHE[key] = out
+    return out
+
+
 def pack_tables(dst, num_tables, src0, nb0, off0, strides0, src1=None, nb1=0, off1=0, strides1=(0, 0, 0)):
     check(_lib.load().cream_pack_tables(_p(dst), num_tables, HEAD_DIM, _p(src0), nb0, off0, *strides0,
                                         _p(src1), nb1, off1, *strides1, _stream()), "cream_pack_tables")
@@ -386,10 +419,14 @@ def _set_dense(d, dense, B, H, N):
     d.dense_stride_i = dense.stride(2)
 
 
-def _attn_desc(B, H, N, scale, qkv, tk, tv, per_head, idx, bias, af=None):
+def _attn_desc(B, H, N, scale, qkv, tk, tv, per_head, idx, bias, af=None, gp=None):
     d = AttnDesc()
     if af is not None:
         d.af_grid, d.af_max_rel = af
+    if gp is not None:          # (grid, W, skip_id, lut_a, lut_b) from irpe_grid_product_structure
+        d.gp_grid, d.gp_w, d.gp_skip_id = gp[0], gp[1], gp[2]
+        C.memmove(d.gp_lut_a, gp[3].ctypes.data, 32)
+        C.memmove(d.gp_lut_b, gp[4].ctypes.data, 32)
     d.B, d.H, d.N, d.head_dim = B, H, N, HEAD_DIM
     d.scale = scale
     d.qkv, d.ld_qkv = _p(qkv), qkv.stride(0)
@@ -403,13 +440,13 @@ def _attn_desc(B, H, N, scale, qkv, tk, tv, per_head, idx, bias, af=None):
 
 
 def attention_fwd(qkv, B, H, N, scale, *, tk=None, tv=None, per_head=False, idx=(None, None, None, None),
-                  bias=None, need_lse=True, af=None, dense=None):
+                  bias=None, need_lse=True, af=None, dense=None, gp=None):
     """Fused attention forward.  qkv: (B*N, 3*H*64) bf16.  Returns (out (B*N, H*64) bf16, lse).
     dense: optional fp32 (B|1, H|1, N, N) term added to the logits (see cream_attn_desc.dense_bias)."""
     _check_2d(qkv, torch.bfloat16, "qkv", 8)
     out = empty_bf16(B * N, H * HEAD_DIM, qkv.device)
     lse = torch.empty((B, H, N), dtype=torch.float32, device=qkv.device) if need_lse else None
-    d = _attn_desc(B, H, N, scale, qkv, tk, tv, per_head, idx, bias, af)
+    d = _attn_desc(B, H, N, scale, qkv, tk, tv, per_head, idx, bias, af, gp)
     _set_dense(d, dense, B, H, N)
     d.out, d.ld_out, d.lse = _p(out), out.stride(0), _p(lse)
     nb = (NB_PACK if tk is not None else 0) + (NB_PACK if tv is not None else 0)
@@ -419,7 +456,7 @@ def attention_fwd(qkv, B, H, N, scale, *, tk=None, tv=None, per_head=False, idx=
 
 
 def attention_bwd(qkv, out, lse, dout, B, H, N, scale, *, tk=None, tv=None, per_head=False,
-                  idx=(None, None, None, None), bias=None, af=None, dtk=None, dtv=None, dense=None, ddense=None):
+                  idx=(None, None, None, None), bias=None, af=None, dtk=None, dtv=None, dense=None, ddense=None, gp=None):
     """Returns (dqkv bf16, dtk_pack fp32|None, dtv_pack fp32|None, dbias fp32|None).  dtk / dtv may
     be caller-provided zeroed (T, 64, 64) fp32 accumulators.  With `dense`, pass `ddense` = an fp32
     (B, H, N, N) tensor to receive the logit gradient dS."""
@@ -434,7 +471,7 @@ def attention_bwd(qkv, out, lse, dout, B, H, N, scale, *, tk=None, tv=None, per_
     dbias = torch.zeros((T, NB_PACK), dtype=torch.float32, device=dev) if bias is not None else None
     nbytes = _lib.load().cream_attn_bwd_workspace_bytes(B, H, N)
     ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
-    d = _attn_desc(B, H, N, scale, qkv, tk, tv, per_head, idx, bias, af)
+    d = _attn_desc(B, H, N, scale, qkv, tk, tv, per_head, idx, bias, af, gp)
     d.out, d.ld_out, d.lse = _p(out), out.stride(0), _p(lse)
     d.dout, d.ld_dout = _p(dout), dout.stride(0)
     d.dqkv, d.ld_dqkv = _p(dqkv), dqkv.stride(0)

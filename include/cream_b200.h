@@ -184,6 +184,16 @@ typedef struct cream_attn_desc {
    * receives dS = P * (dP - delta). */
   const float* dense_bias; int64_t dense_stride_b, dense_stride_h, dense_stride_i;
   float* ddense;
+  /* ---- optional grid-product structure hint (iRPE product method on a g x g grid + cls, irpe.py:176-202):
+   * for patch tokens i = (ri, ci), j = (rj, cj) the K-side bucket id is
+   *     idx_a[i, j] = gp_lut_a[rj - ri + g - 1] * gp_w + gp_lut_b[cj - ci + g - 1]
+   * and every pair that involves the cls token uses bucket gp_skip_id (the `skip` bucket, irpe.py:364-415).
+   * Lets the kernel replace the index-table gather by per-thread registers, and the per-element
+   * bucket-sum read-modify-writes of the backward by rectangle sums.  Used only when gp_grid > 0, the K
+   * table is the single table of the pack (idx_b == NULL) and there is no V-side table, bias or dense term;
+   * idx_a must still be the matching table (it is what the caller verified the structure against). */
+  int gp_grid, gp_w, gp_skip_id;
+  uint8_t gp_lut_a[32], gp_lut_b[32];
 } cream_attn_desc;
 
 int cream_attn_fwd(const cream_attn_desc* desc, void* stream);
@@ -303,6 +313,8 @@ typedef struct cream_vit_desc {
   float scale;
   int af_grid, af_max_rel;           /* AutoFormer structure hint (see cream_attn_desc)        */
   const uint8_t *idx_a, *idx_b, *idx_va, *idx_vb; int ld_idx;
+  int gp_grid, gp_w, gp_skip_id;     /* grid-product structure hint (see cream_attn_desc)      */
+  uint8_t gp_lut_a[32], gp_lut_b[32];
   int tab_nb, tab_row_off1;          /* buckets per table; packed row offset of the 2nd table  */
   int64_t tab_stride_b, tab_stride_d;/* element strides of a table: (bucket, channel)          */
   int64_t tabv_stride_b, tabv_stride_d; /* same for the V-side tables                          */

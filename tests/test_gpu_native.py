@@ -232,3 +232,38 @@ def test_deit_trainer_step_runs_and_learns():
     targets = torch.randint(0, 1000, (8,), device="cuda")
     losses = [float(tr.step(images, targets)) for _ in range(6)]
     assert all(np.isfinite(losses)) and losses[-1] < losses[0], losses
+
+
+# ------------------------------------------------------------------------------------------------
+# iRPE product structure: register-arithmetic gather vs the index-table gather
+# ------------------------------------------------------------------------------------------------
+def test_attention_grid_product_path_matches_the_index_table_path():
+    """BASELINE config 2 shape (6 heads, N = 197, 50 buckets, contextual table on keys): the structured
+    path must gather exactly what the uint8 index tables say (forward bit-identical), and its
+    rectangle-sum bucket reduction must agree with the per-element one."""
+    from cream_b200 import ops
+    from oracle import rel_index
+    B, N, h = 8, 197, 6
+    ids, nb = rel_index.irpe_bucket_ids(rel_index.PRODUCT, 14, 14, 1, 1.9, 3.8, 15.2)
+    ids = ids.astype(np.int32)
+    st = ops.irpe_grid_product_structure(ids, 14, 1)
+    assert st is not None and st[0] == 7 and st[1] == 49
+    gp = (14,) + st
+    it = ops.irpe_index_table_u8(ids, "cuda")
+    torch.manual_seed(5)
+    qkv = ops.empty_bf16(B * N, 3 * 64 * h)
+    qkv.copy_(torch.randn(B * N, 3 * 64 * h, device="cuda"))
+    dout = ops.empty_bf16(B * N, 64 * h)
+    dout.copy_(torch.randn(B * N, 64 * h, device="cuda"))
+    tk = ops.new_pack(1, "cuda")
+    tk.zero_()
+    tk[0, :nb] = (torch.randn(nb, 64, device="cuda") * 0.3).to(torch.bfloat16)
+    res = {}
+    for name, g in (("table", None), ("structured", gp)):
+        out, lse = ops.attention_fwd(qkv, B, h, N, 0.125, tk=tk, idx=(it, None, None, None), gp=g)
+        dqkv, dtk, _, _ = ops.attention_bwd(qkv, out, lse, dout, B, h, N, 0.125, tk=tk, idx=(it, None, None, None), gp=g)
+        res[name] = (out.float(), lse, dqkv.float(), dtk)
+    assert torch.equal(res["table"][0], res["structured"][0]) and torch.equal(res["table"][1], res["structured"][1])
+    assert rel_err(res["structured"][2], res["table"][2]) < 5e-3
+    assert rel_err(res["structured"][3], res["table"][3]) < 5e-3
+    assert float(res["structured"][3][0, nb:].abs().max()) == 0.0, "rows of the pack beyond the table stay zero"
