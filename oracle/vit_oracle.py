@@ -255,7 +255,7 @@ def irpe_rpe_transposed(x, table, bucket_ids, mode: str):
     """iRPE.forward_rpe_transpose, irpe.py:585-647.  x (B,H,L,D); contextual table
     (H or 1, D, nb); bias table (H or 1, nb)."""
     B, H, L, D = x.shape
-    ids = torch.as_tensor(bucket_ids, dtype=torch.long)
+    ids = torch.as_tensor(bucket_ids, dtype=torch.long).to(x.device)
     if mode == "bias":
         return table[:, ids.flatten()].view(1, table.shape[0], L, L)
     lookup = torch.matmul(x.transpose(0, 1).reshape(-1, B * L, D), table).view(-1, B, L, table.shape[-1]).transpose(0, 1)
@@ -264,7 +264,7 @@ def irpe_rpe_transposed(x, table, bucket_ids, mode: str):
 
 def irpe_rpe_value(attn, table, bucket_ids):
     """iRPE.forward_rpe_no_transpose, irpe.py:649-687.  table (H or 1, nb, D)."""
-    ids = torch.as_tensor(bucket_ids, dtype=torch.long)
+    ids = torch.as_tensor(bucket_ids, dtype=torch.long).to(table.device)
     L = ids.shape[0]
     weight = table[:, ids.flatten()].view(table.shape[0], L, L, table.shape[-1])
     return torch.matmul(attn.permute(1, 2, 0, 3), weight).permute(2, 0, 1, 3)

@@ -24,3 +24,21 @@ for name, af in (("generic", None), ("structured", (14, 14))):
     fl = 4.0 * B * h * N * N * 64 + 2.0 * B * h * N * 64 * 128
     by = 4.0 * B * h * N * 64 * 2
     print(f"{name:10s} fwd {tf:7.1f} us  {fl / tf / 1e6:6.1f} TFLOP/s  {by / tf / 1e3:6.0f} GB/s | bwd (rows+cols) {tb:7.1f} us")
+# BASELINE config 2 shape: DeiT-S + iRPE product table on keys (B 256, 6 heads): index-table path vs structured path
+from oracle import rel_index
+import numpy as np
+B, h = 256, 6
+qkv = ops.empty_bf16(B * N, 3 * 64 * h); qkv.copy_(torch.randn(B * N, 3 * 64 * h, device="cuda"))
+dout = ops.empty_bf16(B * N, 64 * h); dout.copy_(torch.randn(B * N, 64 * h, device="cuda"))
+ids, nb = rel_index.irpe_bucket_ids(rel_index.PRODUCT, 14, 14, 1, 1.9, 3.8, 15.2)
+ids = ids.astype(np.int32)
+it = ops.irpe_index_table_u8(ids, "cuda")
+gp = (14,) + ops.irpe_grid_product_structure(ids, 14, 1)
+tk.zero_(); tk[0, :nb] = (torch.randn(nb, 64, device="cuda") * 0.3).to(torch.bfloat16)
+for name, g in (("c2 table", None), ("c2 struct", gp)):
+    out, lse = ops.attention_fwd(qkv, B, h, N, 0.125, tk=tk, idx=(it, None, None, None), gp=g)
+    tf = timeit(lambda: ops.attention_fwd(qkv, B, h, N, 0.125, tk=tk, idx=(it, None, None, None), gp=g))
+    tb = timeit(lambda: ops.attention_bwd(qkv, out, lse, dout, B, h, N, 0.125, tk=tk, idx=(it, None, None, None), gp=g))
+    fl = 4.0 * B * h * N * N * 64 + 2.0 * B * h * N * 64 * 64
+    by = 4.0 * B * h * N * 64 * 2
+    print(f"{name:10s} fwd {tf:7.1f} us  {fl / tf / 1e6:6.1f} TFLOP/s  {by / tf / 1e3:6.0f} GB/s | bwd (rows+cols) {tb:7.1f} us")

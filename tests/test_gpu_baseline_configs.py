@@ -289,7 +289,9 @@ def test_trainer_three_steps_follow_the_oracle_adamw_loop():
         num_c += float(d_cmp @ d_ref); den_c += float(d_cmp @ d_cmp)
         untouched = d_ref == 0      # identity layers (grad None) and un-sampled slices of un-decayed parameters
         if untouched.any():
-            assert float(d_our[untouched].abs().max()) == 0.0, f"{k}: update outside the sampled slices"
+            bad = d_our[untouched].abs()
+            assert float(bad.max()) == 0.0, (f"{k}: update outside the sampled slices: {int((bad > 0).sum())} of "
+                                             f"{int(untouched.sum())} untouched elements moved, max {float(bad.max()):.3e}")
     cos_our, cos_cmp = num / (den_a * den_b) ** 0.5, num_c / (den_c * den_b) ** 0.5
     print(f"[trainer] cosine(update, fp32 update): cream {cos_our:.4f}   autocast(bf16) {cos_cmp:.4f}")
     assert cos_our >= cos_cmp - 0.02
