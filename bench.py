@@ -511,11 +511,15 @@ def main():
     # Every launch is bracketed by CUDA events on its own stream.  So that the events time the kernel
     # and not the host's enqueue gaps, each profiled step starts behind a spin kernel long enough for
     # the host to queue the step's launches before the GPU starts draining them.
+    # The native runtime enqueues a whole forward / backward from C++, so the instrumented pass drives the
+    # SAME kernels (same launch sequence, bit-identical results: tests/test_gpu_native.py) through the
+    # Python sequencing, where every launch can be bracketed.
+    prof_trainer = trainer if args.python_engine else SupernetTrainer(model, ss, native=False)
     ops.PROFILE = []
     spin = int(25e-3 * 1.9e9)
     for s, cfg in enumerate(cfg_timed[:4]):
         torch.cuda._sleep(spin)
-        trainer.step(dev_imgs[s % n_host], dev_tgts[s % n_host], config=cfg)
+        prof_trainer.forward_backward(dev_imgs[s % n_host], dev_tgts[s % n_host], config=cfg)
         torch.cuda.synchronize()
     prof, ops.PROFILE = ops.PROFILE, None
     agg = {}
@@ -525,6 +529,22 @@ def main():
         d[1] += fl
         d[2] += by
         d[3] += 1
+    # cross-check from CUPTI (torch.profiler): per-kernel-name GPU time of the NATIVE path over the same steps
+    kernel_table = None
+    try:
+        from torch.profiler import ProfilerActivity, profile
+        with profile(activities=[ProfilerActivity.CUDA]) as tp:
+            for s, cfg in enumerate(cfg_timed[:4]):
+                trainer.step(dev_imgs[s % n_host], dev_tgts[s % n_host], config=cfg)
+            torch.cuda.synchronize()
+        rows = [(e.key, e.count, float(getattr(e, "device_time_total", getattr(e, "cuda_time_total", 0.0)))) for e in tp.key_averages()]
+        rows = [r for r in rows if r[2] > 0]
+        tot = sum(r[2] for r in rows) or 1.0
+        kernel_table = [{"kernel": k[:72], "launches": c, "us": round(t, 1), "share": round(t / tot, 4)}
+                        for k, c, t in sorted(rows, key=lambda r: -r[2])[:14]]
+        kernel_table.append({"kernel": "TOTAL (4 steps)", "launches": sum(r[1] for r in rows), "us": round(tot, 1), "share": 1.0})
+    except Exception as e:   # noqa: BLE001
+        kernel_table = [{"unavailable": repr(e)[:200]}]
 
     if rank != 0:
         if world > 1:
@@ -586,6 +606,7 @@ def main():
                             "launches": agg[k][3], "avg_launch_us": agg[k][0] / agg[k][3] * 1e6}
                         for k in ("ln_fwd", "ln_bwd", "cast_scale", "bias_grad") if k in agg and agg[k][0] > 0},
         "gpu_time_share": {k: v[0] / max(sum(x[0] for x in agg.values()), 1e-12) for k, v in agg.items()},
+        "kernel_table_cupti": kernel_table,
         "model_tflops": flops * world / (ms * 1e-3) / 1e12,
         "model_tflops_per_gpu": flops / (ms * 1e-3) / 1e12,
         "model_flops_frac_of_peak": flops / (ms * 1e-3) / 1e12 / peak_tf,

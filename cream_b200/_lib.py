@@ -158,7 +158,8 @@ SIGNATURES = {
     "cream_vit_bwd": (c_int, [C.POINTER(VitDesc), c_int, c_int, c_void_p]),
     "cream_vit_last_launches": (c_int, []),
     "cream_xent_fwd_bwd": (c_int, [c_void_p, c_i64, c_void_p, c_void_p, c_void_p, c_i64, c_int, c_int, c_void_p]),
-    "cream_adamw_step": (c_int, [c_void_p, c_void_p, c_int, c_i64, c_float, c_float, c_float, c_float, c_void_p]),
+    "cream_adamw_step": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_float, c_float, c_float, c_float, c_void_p]),
+    "cream_adamw_chunk": (c_int, []),
     "cream_unpack_table_grads": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_i64, c_i64, c_i64,
                                          c_void_p, c_int, c_int, c_i64, c_i64, c_i64, c_void_p]),
 }

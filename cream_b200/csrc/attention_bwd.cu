@@ -37,6 +37,7 @@ struct BwdRowsParams {
   float scale;
   int ctx_k, ctx_v, shared_tables;
   int af_grid, af_max_rel;
+  int af_mma;                          // AutoFormer structure through the tensor cores (see bwd_row_plain)
   int gp_grid, gp_w, gp_skip;          // iRPE grid-product structured mode (0 = off), see attention_fwd.cu
   uint8_t lut_a[32], lut_b[32];
   const uint8_t* idx_a; const uint8_t* idx_b; const uint8_t* idx_va; const uint8_t* idx_vb;
@@ -434,6 +435,70 @@ __device__ __forceinline__ void bwd_row_gridprod(const BwdRowsParams& p, const R
   rows_barrier();
 }
 
+// AutoFormer relative position through the tensor cores (the backward twin of softmax_plain in
+// attention_fwd.cu).  The gather terms have already been ADDED into the accumulators by MMAs against the
+// 0/1 feature matrix Ind (T = Q K^T + A_R . Ind,  dP = dO V^T + A_dPB . Ind), so a row is a plain
+//     p = 2^(scale log2e T - lse log2e),   dT = p (dP - delta)
+// over its keys: no gather adds, no compile-time (rj, cj), no bucket-sum accumulators - those come back
+// from the tensor cores as PBabs = P . Ind^T and dRabs = dT . Ind^T.  Two threads per row (keys 0..111 /
+// 112..207); each packs P and dT (bf16) in place over accumulator columns it has already read:
+//     dT: half 0 -> [0, 56), half 1 -> [464, 512);    P: half 0 -> [256, 312), half 1 -> [112, 160).
+constexpr int kPHiCol = 112;                      // TMEM columns of the second half's packed P
+constexpr int kAbsPB = 160, kAbsDR = 56;          // TMEM columns of PBabs / dRabs (32 fp32 columns each)
+constexpr int kDrPackCol = 320;                   // packed dR (A operand of the table part of dQ)
+constexpr int kAvecR = 208, kAvecDPB = 240, kAvecDPBlo = 464;   // A vectors: R hi | lo at [208, 240), dPB hi [240, 256), lo [464, 480)
+
+__device__ __forceinline__ void bwd_row_plain(const BwdRowsParams& p, const RowCtx& x) {
+  constexpr int NCC = kAfSplitCols / 16;
+  const bool live = x.row < p.N;
+  const int hi = x.half;
+  const float sl = p.scale * kLog2e;
+  const float lsel = live ? x.lsel : 1e30f;
+  const uint32_t t_in = x.trow + kAfSplitCols * hi;
+  const uint32_t dt_out = hi ? x.trow + kDtHiCol : x.trow;
+  const uint32_t p_out = hi ? x.trow + kPHiCol : x.trow + 256;
+  const int64_t w0 = x.wrow + kAfSplitCols * hi;
+  const int n_left = p.N - kAfSplitCols * hi;     // valid keys of this half: 112 / 85
+  uint32_t rtb[2][16], rpb[2][16];
+  tmem_ld16(t_in, rtb[0]);
+  tmem_ld16(t_in + 256, rpb[0]);
+#pragma unroll
+  for (int cc = 0; cc < NCC; ++cc) {
+    if (cc == NCC - 1 && hi) break;               // the second half owns 6 chunks (keys 112..207)
+    uint32_t (&rt)[16] = rtb[cc & 1];
+    uint32_t (&rp)[16] = rpb[cc & 1];
+    tmem_ld_wait();
+    if (cc + 1 < NCC && !(cc + 1 == NCC - 1 && hi)) {
+      tmem_ld16(t_in + (cc + 1) * 16, rtb[(cc + 1) & 1]);
+      tmem_ld16(t_in + 256 + (cc + 1) * 16, rpb[(cc + 1) & 1]);
+    }
+    float pv[16], dt[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      float pr = fast_exp2(fmaf(sl, __uint_as_float(rt[k]), -lsel));
+      if (cc * 16 + k >= n_left) pr = 0.f;        // key padding (only the last chunk of the second half)
+      pv[k] = pr;
+      dt[k] = pr * (__uint_as_float(rp[k]) - x.delta);
+    }
+    uint32_t pk[8], dk[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      pk[k] = pack_bf16x2(pv[2 * k], pv[2 * k + 1]);
+      dk[k] = pack_bf16x2(dt[2 * k], dt[2 * k + 1]);
+    }
+    tmem_st8(dt_out + cc * 8, dk);
+    tmem_st8(p_out + cc * 8, pk);
+    if (live) {
+      uint4* wp = reinterpret_cast<uint4*>(p.ws_p + w0 + cc * 16);
+      uint4* wd = reinterpret_cast<uint4*>(p.ws_dt + w0 + cc * 16);
+      wp[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+      wp[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+      wd[0] = make_uint4(dk[0], dk[1], dk[2], dk[3]);
+      wd[1] = make_uint4(dk[4], dk[5], dk[6], dk[7]);
+    }
+  }
+}
+
 __global__ void __launch_bounds__(kRowsThreads, 1)
 attn_bwd_rows_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_kv,
                      const __grid_constant__ CUtensorMap map_do, const __grid_constant__ CUtensorMap map_tk,
@@ -450,7 +515,8 @@ attn_bwd_rows_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
   uint8_t* sTV = sV + v_slot;
   uint8_t* sR = sTV + 8192;                 // fp32 [128][kStride]
   uint8_t* sdPB = sR + 128 * kStride * 4;   // fp32 [128][kStride]
-  uint8_t* sBias = sdPB + 128 * kStride * 4;
+  uint8_t* sInd = sdPB + 128 * kStride * 4;  // 16 KB: 0/1 feature matrix (tensor-core structured mode; 1024-aligned at N = 197)
+  uint8_t* sBias = sInd + 4 * kIndChunk;
   uint8_t* sDbias = sBias + 64 * 4;
   uint8_t* sLut = sDbias + 64 * 4;          // 64 bytes: grid-product row / column components
   uint64_t* bars = reinterpret_cast<uint64_t*>(sLut + 64);
@@ -460,6 +526,8 @@ attn_bwd_rows_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
   uint64_t* bar_s = bars + 3;
   uint64_t* bar_p = bars + 4;
   uint64_t* bar_o = bars + 5;
+  uint64_t* bar_abs = bars + 6;              // MMA -> rows: PBabs / dRabs ready (tensor-core structured mode)
+  uint64_t* bar_p2 = bars + 7;               // rows -> MMA: packed dR written
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
   // overlays: PB (128 x 64 fp32, each row rotated by 2*row) over sQ|sdO ; dR (128 x 65 fp32) over sV|sTV
 
@@ -479,9 +547,15 @@ attn_bwd_rows_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
     mbar_init(bar_s, 1);
     mbar_init(bar_p, kRowThreads);
     mbar_init(bar_o, 1);
+    mbar_init(bar_abs, 1);
+    mbar_init(bar_p2, kRowThreads);
     fence_mbar_init();
   }
   if (warp == 0) tmem_alloc<512>(tmem_slot);
+  if (p.af_mma && threadIdx.x >= 32) {
+    write_ind_matrix(smem_u32(sInd), threadIdx.x - 32, kRowThreads, 14, p.N);
+    fence_proxy_async_smem();
+  }
   if (threadIdx.x >= 32 && threadIdx.x < 96) {
     sts_f32(smem_u32(sBias) + 4 * (threadIdx.x - 32), p.bias ? p.bias[tab * 64 + threadIdx.x - 32] : 0.f);
     sts_f32(smem_u32(sDbias) + 4 * (threadIdx.x - 32), 0.f);
@@ -530,6 +604,18 @@ attn_bwd_rows_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
       for (int k = 0; k < 4; ++k)   // T = Q K^T
         umma_ss(tmem + 0, umma_smem_desc_sw128(aQ + k * 32, 16, 1024),
                 umma_smem_desc_sw128(aK + k * 32, 16, 1024), idN, k > 0);
+      const uint32_t aInd = smem_u32(sInd);
+      if (p.af_mma) {
+        // T += A_R(hi, lo) . Ind ;  dP += A_dPB(hi, lo) . Ind     (A vectors in TMEM, two K = 16 steps each)
+        const uint32_t id_g = umma_idesc_bf16(128, Npad, 0, 1);
+        const uint32_t acol[4] = {kAvecR, kAvecR + 16, kAvecDPB, kAvecDPBlo};
+#pragma unroll
+        for (int v = 0; v < 4; ++v)
+#pragma unroll
+          for (int k = 0; k < kFeat / 16; ++k)
+            umma_ts(tmem + (v < 2 ? 0 : 256), tmem + acol[v] + 8 * k, umma_smem_desc_sw128(aInd + k * 2048, kIndChunk, 1024),
+                    id_g, 1u);
+      }
       umma_commit(bar_s);
       ROWS_TRACE(2);
 
@@ -538,11 +624,32 @@ attn_bwd_rows_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
       ROWS_TRACE(3);
       const uint32_t id_o = umma_idesc_bf16(128, kD, 0, 1);
       const int ksteps = (Npad + (p.ctx_k ? kNB : 0)) / 16;
-      for (int k = 0; k < ksteps; ++k) {  // dQ = [dT | dR] [K ; TK]
-        // structured path: the packed dT of keys >= 112 sits in the spare columns (see bwd_row_af)
-        const bool hi_part = p.af_grid != 0 && k >= kAfSplitCols / 16 && k < Npad / 16;
-        const uint32_t a_col = hi_part ? kDtHiCol + 8 * (k - kAfSplitCols / 16) : 8 * k;
-        umma_ts(tmem + 192, tmem + a_col, umma_smem_desc_sw128(aK + k * 2048, 8192, 1024), id_o, k > 0);
+      const int nk = Npad / 16;
+      if (p.af_mma) {
+        const uint32_t id_abs = umma_idesc_bf16(128, kFeat, 0, 0);
+        for (int k = 0; k < nk; ++k) {            // dQ = dT . K  (the table part follows the un-shifted dR)
+          const uint32_t a_col = k >= kAfSplitCols / 16 ? kDtHiCol + 8 * (k - kAfSplitCols / 16) : 8 * k;
+          umma_ts(tmem + 192, tmem + a_col, umma_smem_desc_sw128(aK + k * 2048, 8192, 1024), id_o, k > 0);
+        }
+        for (int k = 0; k < nk; ++k) {            // PBabs = P . Ind^T,  dRabs = dT . Ind^T
+          const uint32_t d_col = k >= kAfSplitCols / 16 ? kDtHiCol + 8 * (k - kAfSplitCols / 16) : 8 * k;
+          const uint32_t p_col = k >= kAfSplitCols / 16 ? kPHiCol + 8 * (k - kAfSplitCols / 16) : 256 + 8 * k;
+          const uint64_t bd = umma_smem_desc_sw128(aInd + (k >> 2) * kIndChunk + (k & 3) * 32, 16, 1024);
+          umma_ts(tmem + kAbsPB, tmem + p_col, bd, id_abs, k > 0);
+          umma_ts(tmem + kAbsDR, tmem + d_col, bd, id_abs, k > 0);
+        }
+        umma_commit(bar_abs);
+        mbar_wait(bar_p2, 0);
+        tc_fence_after();
+        for (int k = nk; k < ksteps; ++k)         // dQ += dR . TK
+          umma_ts(tmem + 192, tmem + kDrPackCol + 8 * (k - nk), umma_smem_desc_sw128(aK + k * 2048, 8192, 1024), id_o, 1u);
+      } else {
+        for (int k = 0; k < ksteps; ++k) {  // dQ = [dT | dR] [K ; TK]
+          // structured paths: the packed dT of keys >= 112 sits in the spare columns (see bwd_row_af / bwd_row_gridprod)
+          const bool hi_part = (p.af_grid != 0 || p.gp_grid != 0) && k >= kAfSplitCols / 16 && k < nk;
+          const uint32_t a_col = hi_part ? kDtHiCol + 8 * (k - kAfSplitCols / 16) : 8 * k;
+          umma_ts(tmem + 192, tmem + a_col, umma_smem_desc_sw128(aK + k * 2048, 8192, 1024), id_o, k > 0);
+        }
       }
       umma_commit(bar_o);
     }
@@ -596,7 +703,9 @@ attn_bwd_rows_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
           tmem_ld32(x.trow + c * 32, raw);
           tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < 32; ++i) sts_f32(x.s_r + 4 * (c * 32 + i), p.scale * __uint_as_float(raw[i]));
+          const float rs = p.af_mma ? 1.0f : p.scale;   // tensor-core mode adds the UNSCALED term into T
+#pragma unroll
+          for (int i = 0; i < 32; ++i) sts_f32(x.s_r + 4 * (c * 32 + i), rs * __uint_as_float(raw[i]));
         }
         if (p.ctx_v) {
           tmem_ld32(x.trow + 64 + c * 32, raw);
@@ -605,9 +714,43 @@ attn_bwd_rows_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
           for (int i = 0; i < 32; ++i) sts_f32(x.s_dpb + 4 * (c * 32 + i), __uint_as_float(raw[i]));
         }
       }
-      tc_fence_before();
-      mbar_arrive(bar_rfree);
-      rows_barrier();                            // both halves of R / dPB staged before anyone gathers
+      if (p.af_mma) {
+        // A vectors (absolute key features, see attention_fwd.cu): the first thread of a row builds the
+        // logit-side vector from R, its partner the dP-side vector from dPB; bf16 hi + lo parts
+        rows_barrier();                          // both halves of R / dPB staged
+        constexpr int G = 14;
+        const int M1 = p.af_max_rel + 1;
+        const bool patch = row >= 1 && row < p.N;
+        const int qi = patch ? row - 1 : 0;
+        const int ri = qi / G, ci = qi - ri * G;
+        const uint32_t src = half ? x.s_dpb : x.s_r;
+        const float v0 = lds_f32(src), h0 = lds_f32(src + 4 * 32);
+        float a[kFeat];
+#pragma unroll
+        for (int t = 0; t < G; ++t) {
+          a[t] = patch ? lds_f32(src + 4 * (M1 - ri + t)) : v0;
+          a[G + t] = patch ? lds_f32(src + 4 * (32 + M1 - ci + t)) : h0;
+        }
+        a[2 * G] = v0 + h0;
+#pragma unroll
+        for (int t = 2 * G + 1; t < kFeat; ++t) a[t] = 0.f;
+        uint32_t hiw[16], low[16];
+#pragma unroll
+        for (int t = 0; t < 16; ++t) {
+          const __nv_bfloat16 b0 = __float2bfloat16_rn(a[2 * t]), b1 = __float2bfloat16_rn(a[2 * t + 1]);
+          hiw[t] = pack_bf16x2(__bfloat162float(b0), __bfloat162float(b1));
+          low[t] = pack_bf16x2(a[2 * t] - __bfloat162float(b0), a[2 * t + 1] - __bfloat162float(b1));
+        }
+        tmem_st16(x.trow + (half ? kAvecDPB : kAvecR), hiw);
+        tmem_st16(x.trow + (half ? kAvecDPBlo : kAvecR + 16), low);
+        tmem_st_wait();
+        tc_fence_before();
+        mbar_arrive(bar_rfree);
+      } else {
+        tc_fence_before();
+        mbar_arrive(bar_rfree);
+        rows_barrier();                          // both halves of R / dPB staged before anyone gathers
+      }
     }
     RT(2);
 
@@ -619,7 +762,44 @@ attn_bwd_rows_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
     tc_fence_after();
     RT(4);
 
-    if (p.af_grid == 14) bwd_row_af<14>(p, x);
+    if (p.af_mma) {
+      bwd_row_plain(p, x);
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(bar_p);                        // packed P / dT in place: dQ = dT K, PBabs, dRabs may start
+      // un-shift the absolute bucket sums into this row's 64 packed buckets: the first thread of the row
+      // takes PBabs -> PB (rotated shared row), its partner dRabs -> dR
+      constexpr int G = 14;
+      const int M1 = p.af_max_rel + 1;
+      const bool patch = row >= 1 && row < p.N;
+      const int qi = patch ? row - 1 : 0;
+      const int ri = qi / G, ci = qi - ri * G;
+      auto put = [&](int bucket, float v) {
+        sts_f32(half ? x.s_dr + 4 * bucket : x.s_pb + 4 * ((bucket + x.sw) & 63), v);
+      };
+      for (int k = 0; k < kNB; ++k) put(k, 0.f);
+      mbar_wait(bar_abs, 0);
+      tc_fence_after();
+      uint32_t ab[32];
+      tmem_ld32(x.trow + (half ? kAbsDR : kAbsPB), ab);
+      tmem_ld_wait();
+      if (patch) {
+#pragma unroll
+        for (int t = 0; t < G; ++t) {
+          put(M1 - ri + t, __uint_as_float(ab[t]));
+          put(32 + M1 - ci + t, __uint_as_float(ab[G + t]));
+        }
+        put(0, __uint_as_float(ab[2 * G]));
+        put(32, __uint_as_float(ab[2 * G]));
+      } else {
+        float tot = __uint_as_float(ab[2 * G]);
+#pragma unroll
+        for (int t = 0; t < G; ++t) tot += __uint_as_float(ab[t]);
+        put(0, tot);
+        put(32, tot);
+      }
+      rows_barrier();
+    } else if (p.af_grid == 14) bwd_row_af<14>(p, x);
     else if (p.gp_grid == 14) bwd_row_gridprod<14>(p, x);
     else bwd_row_generic(p, x);
     RT(5);
@@ -641,7 +821,7 @@ attn_bwd_rows_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
           dk[k] = pack_bf16x2(r0, r1);
         }
       }
-      if (p.ctx_k) tmem_st16(x.trow + Npad / 2 + c * 16, dk);
+      if (p.ctx_k) tmem_st16(x.trow + (p.af_mma ? kDrPackCol : Npad / 2) + c * 16, dk);
       if (row < p.N) {
         uint4* wp = reinterpret_cast<uint4*>(p.ws_p + x.wrow + Npad + c * 32);
         uint4* wd = reinterpret_cast<uint4*>(p.ws_dt + x.wrow + Npad + c * 32);
@@ -657,7 +837,7 @@ attn_bwd_rows_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
     }
     tmem_st_wait();
     tc_fence_before();
-    mbar_arrive(bar_p);
+    mbar_arrive(p.af_mma ? bar_p2 : bar_p);
     RT(6);
 
     const uint32_t trow = x.trow;
@@ -912,6 +1092,10 @@ extern "C" int cream_attn_bwd(const cream_attn_desc* d, void* stream_) {
   p.dense = d->dense_bias; p.dense_sb = d->dense_stride_b; p.dense_sh = d->dense_stride_h; p.dense_si = d->dense_stride_i;
   p.ddense = d->ddense;
   if (p.dense != nullptr || p.ddense != nullptr) p.af_grid = 0;   // generic gather path only
+  if (p.af_grid != 0) {
+    static const bool use_mma = []() { const char* e = getenv("CREAM_AF_MMA"); return e == nullptr || e[0] != '0'; }();
+    p.af_mma = use_mma ? 1 : 0;     // CREAM_AF_MMA=0: the register-arithmetic structured path (round 1)
+  }
   if (d->gp_grid == 14 && d->gp_grid * d->gp_grid + 1 == d->N && ctx_k && !ctx_v && d->idx_b == nullptr && !d->bias_pack &&
       p.dense == nullptr && p.ddense == nullptr && p.af_grid == 0 && d->gp_w >= 1 && d->gp_skip_id >= 0 && d->gp_skip_id < kNB) {
     bool ok = true;
@@ -954,7 +1138,7 @@ extern "C" int cream_attn_bwd(const cream_attn_desc* d, void* stream_) {
     attr_set = true;
   }
   const size_t smem_rows = 2 * 16384 + static_cast<size_t>(Npad) * 128 + 8192 +
-                           std::max<size_t>(Npad * 128, 26 * 1024) + 8192 + 2 * 128 * kStride * 4 + 2 * 64 * 4 + 64 + 128;
+                           std::max<size_t>(Npad * 128, 26 * 1024) + 8192 + 2 * 128 * kStride * 4 + 4 * kIndChunk + 2 * 64 * 4 + 64 + 128;
   CB_REQUIRE(smem_rows <= 227 * 1024, "shared memory budget");
   dim3 grid(ceil_div(d->N, 128), d->H, d->B);
 #ifdef CREAM_TRACE

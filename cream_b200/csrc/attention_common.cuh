@@ -59,6 +59,35 @@ __device__ __forceinline__ uint32_t byte_of(const uint32_t (&w)[4], int k) {
   return (w[k >> 2] >> (8 * (k & 3))) & 0xFF;
 }
 
+// ---- AutoFormer relative position through the tensor cores (see attention_fwd.cu, softmax_plain) ----
+constexpr int kFeat = 32;            // 14 rows + 14 columns + cls, padded to two K = 16 steps
+constexpr int kIndChunk = kFeat * 128;   // bytes of one 64-key chunk of Ind (32 feature rows x 128 B)
+
+// Ind[t][j] (bf16 0/1) for a 14 x 14 grid + cls; 128B-swizzled [feature rows][64-key chunks], written
+// cooperatively by `nthreads` threads (tid in [0, nthreads)).
+__device__ __forceinline__ void write_ind_matrix(uint32_t base, int tid, int nthreads, int G, int N) {
+  for (int U = tid; U < 4 * kFeat * 8; U += nthreads) {
+    const int c = U >> 8, t = (U >> 3) & 31, u = U & 7;
+    uint32_t w[4];
+#pragma unroll
+    for (int e2 = 0; e2 < 4; ++e2) {
+      uint32_t word = 0;
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int j = c * 64 + u * 8 + e2 * 2 + e;
+        bool one;
+        if (j == 0) one = t == 2 * G;
+        else if (j < N) one = (t == (j - 1) / G) || (t == G + (j - 1) % G);
+        else one = false;
+        if (one) word |= 0x3F80u << (16 * e);     // bf16 1.0
+      }
+      w[e2] = word;
+    }
+    const uint32_t a = base + c * kIndChunk + t * 128 + ((u ^ (t & 7)) << 4);
+    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]) : "memory");
+  }
+}
+
 // Dynamic shared memory base, required to be 1024-byte aligned (128B-swizzle atoms).
 __device__ __forceinline__ void require_smem_alignment(const void* smem) {
   if (threadIdx.x == 0 && (smem_u32(smem) & 1023u) != 0) {

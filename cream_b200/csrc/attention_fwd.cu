@@ -19,6 +19,7 @@
 //   warps 1..4       : one thread per query row: R copy-out, softmax, epilogue
 // TMEM columns: S fp32 [0,Npad) -> P bf16x2 in place [0,Npad/2) | PB [Npad/2,Npad/2+32);
 //               R fp32 [192,256) (dead before S cols >= 192 are produced); O fp32 [192,256).
+#include <cstdlib>
 #include <cstring>
 
 #include "attention_common.cuh"
@@ -39,6 +40,7 @@ struct AttnFwdParams {
   int ctx_k, ctx_v;                    // contextual tables on K / V present
   int shared_tables;                   // 1: one table pack for all heads
   int af_grid, af_max_rel;             // AutoFormer structured mode (0 = generic index tables)
+  int af_mma;                          // structured mode through the tensor cores (see softmax_plain)
   int gp_grid, gp_w, gp_skip;          // iRPE grid-product structured mode (0 = off)
   uint8_t lut_a[32], lut_b[32];        // bucket row / column components by (delta + grid - 1)
   const uint8_t* idx_a; const uint8_t* idx_b;   // K-side gather indices (N, ldi), values < 64
@@ -315,6 +317,60 @@ __device__ __forceinline__ void softmax_gridprod(const AttnFwdParams& p, uint32_
   sum_out = sum;
 }
 
+// ---------------------------------------------------------------------------------------
+// AutoFormer relative position THROUGH THE TENSOR CORES ("absolute-coordinate" formulation).
+// For a query at grid position (ri, ci) the K-side term of key (rj, cj) is
+//     Rv[rj - ri + M1] + Rh[cj - ci + M1]      (Rv | Rh = the two halves of R = Q . TKpack^T)
+// i.e. a per-query vector a_i over 29 ABSOLUTE key features (14 grid rows, 14 grid columns, the cls
+// key) times a 0/1 matrix Ind (features x keys) that does not depend on the query:
+//     S += A . Ind,     A[i] = [ Rv[M1 - ri + t] (t < 14) | Rh[M1 - ci + t] (t < 14) | Rv[0] + Rh[0] | 0 0 0 ].
+// A is built once per row (a shifted copy of 28 of its 64 R values), split into bf16 hi + lo parts
+// (exact for the fp16-staged R) and added into the S accumulator by two K = 32 MMAs; the softmax is
+// then a PLAIN softmax - no gather adds, no compile-time (rj, cj) - and the value-side bucket sums are
+// the same matrix used the other way round:  PBabs = P . Ind^T  (one N = 32 MMA), un-shifted per row.
+// ---------------------------------------------------------------------------------------
+template <int NPAD>
+__device__ __forceinline__ void softmax_plain(float scale, int N, uint32_t trow, float& mx_out, float& sum_out) {
+  constexpr int NCH = NPAD / 16;
+  float mx = -INFINITY;
+  uint32_t rb[2][16];
+  tmem_ld16(trow, rb[0]);
+#pragma unroll
+  for (int c = 0; c < NCH; ++c) {
+    uint32_t (&raw)[16] = rb[c & 1];
+    tmem_ld_wait();
+    if (c + 1 < NCH) tmem_ld16(trow + (c + 1) * 16, rb[(c + 1) & 1]);
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      const int j = c * 16 + k;
+      if (j < N) mx = fmaxf(mx, __uint_as_float(raw[k]));
+    }
+  }
+  mx *= scale;                                  // scale > 0
+  const float sl = scale * kLog2e, mxl = mx * kLog2e;
+  float sum = 0.f;
+  tmem_ld16(trow, rb[0]);
+#pragma unroll
+  for (int c = 0; c < NCH; ++c) {
+    uint32_t (&raw)[16] = rb[c & 1];
+    tmem_ld_wait();
+    if (c + 1 < NCH) tmem_ld16(trow + (c + 1) * 16, rb[(c + 1) & 1]);
+    float pv[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      const int j = c * 16 + k;
+      pv[k] = j < N ? fast_exp2(fmaf(__uint_as_float(raw[k]), sl, -mxl)) : 0.f;
+      sum += pv[k];
+    }
+    uint32_t pk[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) pk[k] = pack_bf16x2(pv[2 * k], pv[2 * k + 1]);
+    tmem_st8(trow + c * 8, pk);
+  }
+  mx_out = mx;
+  sum_out = sum;
+}
+
 __global__ void __launch_bounds__(kThreads, 2)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_kv,
                 const __grid_constant__ CUtensorMap map_tk, const __grid_constant__ CUtensorMap map_tv,
@@ -339,7 +395,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
   uint64_t* bar_s = bars + 4;
   uint64_t* bar_p = bars + 5;
   uint64_t* bar_o = bars + 6;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+  uint64_t* bar_pb = bars + 7;       // MMA -> rows: PBabs = P . Ind^T ready (tensor-core structured mode)
+  uint64_t* bar_p2 = bars + 8;       // rows -> MMA: packed bucket sums written
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.x * 128, head = blockIdx.y, b = blockIdx.z;
@@ -357,6 +415,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
     mbar_init(bar_s, 1);
     mbar_init(bar_p, 128);
     mbar_init(bar_o, 1);
+    mbar_init(bar_pb, 1);
+    mbar_init(bar_p2, 128);
     fence_mbar_init();
   }
   if (warp == 0) tmem_alloc<256>(tmem_slot);
@@ -414,6 +474,16 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
           umma_ss(tmem + 192, umma_smem_desc_sw128(aQ + k * 32, 16, 1024),
                   umma_smem_desc_sw128(aK + 192 * 128 + k * 32, 16, 1024), id_s, k > 0);
       }
+      const uint32_t aInd = smem_u32(sR);      // the 0/1 feature matrix replaces the staged R (tensor-core mode)
+      if (p.af_mma) {
+        // S += A_hi . Ind + A_lo . Ind   (A in TMEM columns [224, 240) / [240, 256), two K = 16 steps each)
+        const uint32_t id_g = umma_idesc_bf16(128, Npad, 0, 1);
+#pragma unroll
+        for (int part = 0; part < 2; ++part)
+#pragma unroll
+          for (int k = 0; k < kFeat / 16; ++k)
+            umma_ts(tmem, tmem + 224 + 16 * part + 8 * k, umma_smem_desc_sw128(aInd + k * 2048, kIndChunk, 1024), id_g, 1u);
+      }
       umma_commit(bar_s);
 
       // ---------------- O = [P | PB] [V ; TV] ----------------
@@ -423,8 +493,22 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
       const uint32_t aV = smem_u32(sV);
       const uint32_t id_o = umma_idesc_bf16(128, kD, 0, 1);
       const int ksteps = (Npad + (p.ctx_v ? kNB : 0)) / 16;
-      for (int k = 0; k < ksteps; ++k)
-        umma_ts(tmem + 192, tmem + 8 * k, umma_smem_desc_sw128(aV + k * 2048, 8192, 1024), id_o, k > 0);
+      if (p.af_mma) {
+        // bucket sums in absolute coordinates: PBabs[128 x 32] = P . Ind^T -> columns [112, 144)
+        const uint32_t id_pb = umma_idesc_bf16(128, kFeat, 0, 0);
+        for (int k = 0; k < Npad / 16; ++k)
+          umma_ts(tmem + 112, tmem + 8 * k, umma_smem_desc_sw128(aInd + (k >> 2) * kIndChunk + (k & 3) * 32, 16, 1024), id_pb, k > 0);
+        umma_commit(bar_pb);
+        for (int k = 0; k < Npad / 16; ++k)      // O = P . V while the rows un-shift their bucket sums
+          umma_ts(tmem + 192, tmem + 8 * k, umma_smem_desc_sw128(aV + k * 2048, 8192, 1024), id_o, k > 0);
+        mbar_wait(bar_p2, 0);
+        tc_fence_after();
+        for (int k = Npad / 16; k < ksteps; ++k)  // O += PB . TV
+          umma_ts(tmem + 192, tmem + 8 * k, umma_smem_desc_sw128(aV + k * 2048, 8192, 1024), id_o, 1u);
+      } else {
+        for (int k = 0; k < ksteps; ++k)
+          umma_ts(tmem + 192, tmem + 8 * k, umma_smem_desc_sw128(aV + k * 2048, 8192, 1024), id_o, k > 0);
+      }
       umma_commit(bar_o);
     }
   } else {
@@ -444,12 +528,43 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         uint32_t raw[32];
         tmem_ld32(trow + 192 + c * 32, raw);
         tmem_ld_wait();
+        const float rs = p.af_mma ? 1.0f : p.scale;   // tensor-core mode adds the UNSCALED term into S
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
-          const __half2 h2 = __floats2half2_rn(p.scale * __uint_as_float(raw[2 * i]),
-                                               p.scale * __uint_as_float(raw[2 * i + 1]));
+          const __half2 h2 = __floats2half2_rn(rs * __uint_as_float(raw[2 * i]), rs * __uint_as_float(raw[2 * i + 1]));
           sts_u32(sr_row + 4 * (c * 16 + i), *reinterpret_cast<const uint32_t*>(&h2));
         }
+      }
+      if (p.af_mma) {
+        // A[i]: this row's 29 absolute features, a shifted copy of its staged R values; bf16 hi + lo
+        constexpr int G = 14;
+        const int M1 = p.af_max_rel + 1;
+        const bool patch = row >= 1 && row < p.N;
+        const int qi = patch ? row - 1 : 0;
+        const int ri = qi / G, ci = qi - ri * G;
+        const float r0v = lds_f16(sr_row), r0h = lds_f16(sr_row + 2 * 32);
+        float a[kFeat];
+#pragma unroll
+        for (int t = 0; t < G; ++t) {
+          a[t] = patch ? lds_f16(sr_row + 2 * (M1 - ri + t)) : r0v;
+          a[G + t] = patch ? lds_f16(sr_row + 2 * (32 + M1 - ci + t)) : r0h;
+        }
+        a[2 * G] = r0v + r0h;
+#pragma unroll
+        for (int t = 2 * G + 1; t < kFeat; ++t) a[t] = 0.f;
+        uint32_t hi[16], lo[16];
+#pragma unroll
+        for (int t = 0; t < 16; ++t) {
+          const __nv_bfloat16 h0 = __float2bfloat16_rn(a[2 * t]), h1 = __float2bfloat16_rn(a[2 * t + 1]);
+          hi[t] = pack_bf16x2(__bfloat162float(h0), __bfloat162float(h1));
+          lo[t] = pack_bf16x2(a[2 * t] - __bfloat162float(h0), a[2 * t + 1] - __bfloat162float(h1));
+        }
+        tmem_st16(trow + 224, hi);
+        tmem_st16(trow + 240, lo);
+        tmem_st_wait();
+        asm volatile("bar.sync 1, 128;" ::: "memory");          // every row has read its staged R
+        write_ind_matrix(smem_u32(sR), threadIdx.x - 32, 128, G, p.N);
+        fence_proxy_async_smem();
       }
       tc_fence_before();
       mbar_arrive(bar_rfree);
@@ -458,7 +573,52 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
     tc_fence_after();
 
     float mx, sum;
-    if (p.af_grid == 14) {
+    if (p.af_mma) {
+      constexpr int G = 14;
+      softmax_plain<208>(p.scale, p.N, trow, mx, sum);
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(bar_p);
+      // un-shift the absolute bucket sums into this row's 64 packed buckets
+      const uint32_t spb_row = smem_u32(smem) + r_local * kPBStrideAF * 4;
+      const int M1 = p.af_max_rel + 1;
+      const bool patch = row >= 1 && row < p.N;
+      const int qi = patch ? row - 1 : 0;
+      const int ri = qi / G, ci = qi - ri * G;
+#pragma unroll
+      for (int q = 0; q < 16; ++q) sts_f32x4(spb_row + 16 * q, make_float4(0.f, 0.f, 0.f, 0.f));
+      mbar_wait(bar_pb, 0);
+      tc_fence_after();
+      uint32_t pb[32];
+      tmem_ld32(trow + 112, pb);
+      tmem_ld_wait();
+      if (patch) {
+#pragma unroll
+        for (int t = 0; t < G; ++t) {
+          sts_f32(spb_row + 4 * (M1 - ri + t), __uint_as_float(pb[t]));
+          sts_f32(spb_row + 4 * (32 + M1 - ci + t), __uint_as_float(pb[G + t]));
+        }
+        sts_f32(spb_row, __uint_as_float(pb[2 * G]));
+        sts_f32(spb_row + 4 * 32, __uint_as_float(pb[2 * G]));
+      } else {
+        sts_f32(spb_row, sum);
+        sts_f32(spb_row + 4 * 32, sum);
+      }
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        uint32_t pk[16];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const float4 v = lds_f32x4(spb_row + 4 * (c * 32 + 4 * q));
+          pk[2 * q] = pack_bf16x2(v.x, v.y);
+          pk[2 * q + 1] = pack_bf16x2(v.z, v.w);
+        }
+        tmem_st16(trow + 208 / 2 + c * 16, pk);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(bar_p2);
+    } else if (p.af_grid == 14) {
       softmax_af<14>(p, trow, sr_row, smem_u32(smem) + r_local * kPBStrideAF * 4, row, mx, sum);
     } else if (p.gp_grid == 14) {
       softmax_gridprod<14>(p, trow, sr_row, smem_u32(sLut), row, mx, sum);
@@ -466,9 +626,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
       const float* drow = p.dense ? p.dense + b * p.dense_sb + head * p.dense_sh + row_c * p.dense_si : nullptr;
       softmax_generic(p, trow, sr_row, smem_u32(smem) + r_local * kPBStride * 4, smem_u32(sBias), row_c, drow, mx, sum);
     }
-    tmem_st_wait();
-    tc_fence_before();
-    mbar_arrive(bar_p);
+    if (!p.af_mma) {
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(bar_p);
+    }
 
     // ---- epilogue: O / sum -> bf16 -> global ; log-sum-exp ----
     mbar_wait(bar_o, 0);
@@ -542,6 +704,8 @@ extern "C" int cream_attn_fwd(const cream_attn_desc* d, void* stream_) {
     if (d->af_grid == 14 && d->af_max_rel >= d->af_grid - 1) {
       p.af_grid = d->af_grid;
       p.af_max_rel = d->af_max_rel;
+      static const bool use_mma = []() { const char* e = getenv("CREAM_AF_MMA"); return e == nullptr || e[0] != '0'; }();
+      p.af_mma = use_mma ? 1 : 0;     // CREAM_AF_MMA=0: the register-arithmetic structured path (round 1)
     }
   }
 
@@ -581,7 +745,7 @@ extern "C" int cream_attn_fwd(const cream_attn_desc* d, void* stream_) {
   if (!mq || !mkv || !mtk || !mtv) return CREAM_ERR_CUDA;
 
   const size_t smem_bytes = 16384 + std::max<size_t>(Npad * 128, 11 * 1024) +
-                            static_cast<size_t>(Npad) * 128 + 2 * 8192 + 128 * kRStride * 2 + 64 * 4 + 64 + 128;
+                            static_cast<size_t>(Npad) * 128 + 2 * 8192 + 128 * kRStride * 2 + 64 * 4 + 64 + 192;
   static bool attr_set = false;
   if (!attr_set) {
     CB_CUDA_OK(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,

@@ -308,7 +308,7 @@ class FlatAdamW:
         self.index = {n: i for i, n in enumerate(self.names)}
         self.lr, self.betas, self.eps = lr, betas, eps
         dev = next(iter(named_params.values())).device
-        total = sum(p.numel() for p in named_params.values())
+        total = sum((p.numel() + 3) // 4 * 4 for p in named_params.values())      # every state slice 16-byte aligned
         self.state = torch.zeros(2 * total, dtype=torch.float32, device=dev)      # exp_avg | exp_avg_sq
         segs = (AdamwSeg * len(self.names))()
         off = 0
@@ -329,10 +329,14 @@ class FlatAdamW:
                 s.qkv_group_rows = p.shape[0] // 3 if (qkv_interleaved_names and n in qkv_interleaved_names) else 0
             else:
                 s.shadow, s.rows, s.cols, s.shadow_ld, s.qkv_group_rows = None, 1, max(p.numel(), 1), 0, 0
-            off += p.numel()
+            off += (p.numel() + 3) // 4 * 4
             self.max_numel = max(self.max_numel, p.numel())
         raw = np.frombuffer(bytes(segs), dtype=np.uint8).copy()
         self.segs_dev = torch.from_numpy(raw).to(dev)
+        chunk = self.lib.cream_adamw_chunk()
+        blocks = [(i, first) for i, n in enumerate(self.names) for first in range(0, named_params[n].numel(), chunk)]
+        self.n_blocks = len(blocks)
+        self.blocks_dev = torch.tensor(blocks, dtype=torch.int32).to(dev)
         self._masks: Dict[object, torch.Tensor] = {}
         self._plists: Dict[object, list] = {}
         self._params = named_params
@@ -348,7 +352,7 @@ class FlatAdamW:
             mask = torch.from_numpy(a).to(self.segs_dev.device)
             self._masks[key] = mask
         b1, b2 = self.betas
-        check(self.lib.cream_adamw_step(_p(self.segs_dev), _p(mask), len(self.names), self.max_numel,
+        check(self.lib.cream_adamw_step(_p(self.segs_dev), _p(mask), len(self.names), _p(self.blocks_dev), self.n_blocks,
                                         self.lr, b1, b2, self.eps, _stream()), "cream_adamw_step", kernels=2)
         # the kernel wrote the parameters through raw pointers: tell autograd / the shadow caches
         plist = self._plists.get(key)

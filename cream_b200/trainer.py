@@ -294,6 +294,10 @@ class SupernetTrainer:
             self.native.mark_shadows_fresh()
         else:
             self.optimizer.step()
+            # torch's fused AdamW updates the parameters WITHOUT bumping their version counters, so the
+            # version-tagged shadow cache cannot see the update (round 1 trained on stale bf16 weights
+            # because of exactly this): drop the tags explicitly
+            ops.SHADOWS.invalidate()
         return loss
 
     def sync_grads_to_params(self) -> None:

@@ -357,7 +357,7 @@ int cream_xent_fwd_bwd(const float* logits, int64_t ld, const int64_t* targets, 
  * this step, the step counter is advanced by the kernel).
  * ------------------------------------------------------------------------- */
 typedef struct cream_adamw_seg {
-  float* p; const float* g; float* m; float* v;   /* fp32, `numel` contiguous elements          */
+  float* p; const float* g; float* m; float* v;   /* fp32, `numel` (< 2^31) contiguous elements, 16-byte aligned */
   void* shadow;                                   /* bf16 shadow or NULL                        */
   int64_t numel;
   int32_t rows, cols;                             /* 2-D view (rows, cols) of p for the shadow  */
@@ -366,8 +366,11 @@ typedef struct cream_adamw_seg {
   float weight_decay;
   int32_t step;                                   /* updated in place by the kernel             */
 } cream_adamw_seg;
-int cream_adamw_step(cream_adamw_seg* segs_dev, const int32_t* active_dev, int n_segs, int64_t max_numel,
-                     float lr, float beta1, float beta2, float eps, void* stream);
+/* `blocks_dev`: n_blocks (segment, first element) int32 pairs, one per cream_adamw_chunk()-element chunk
+ * of every segment, in any order (built once by the caller). */
+int cream_adamw_step(cream_adamw_seg* segs_dev, const int32_t* active_dev, int n_segs, const int32_t* blocks_dev,
+                     int n_blocks, float lr, float beta1, float beta2, float eps, void* stream);
+int cream_adamw_chunk(void);
 
 #ifdef __cplusplus
 }

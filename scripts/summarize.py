@@ -4,7 +4,7 @@ import sys
 from pathlib import Path
 
 KEYS = ["value", "ms_per_step", "e2e", "gpu_launches", "host_enqueue_ms_per_step", "clocks", "roofline", "attention",
-        "attention_bwd", "byte_movers", "gpu_time_share", "model_tflops_per_gpu", "gpu_reference", "speedup_vs_gpu_reference",
+        "attention_bwd", "byte_movers", "gpu_time_share", "kernel_table_cupti", "model_tflops_per_gpu", "gpu_reference", "speedup_vs_gpu_reference",
         "cpu_baseline"]
 for f in sys.argv[1:]:
     try:
