@@ -1093,8 +1093,8 @@ extern "C" int cream_attn_bwd(const cream_attn_desc* d, void* stream_) {
   p.ddense = d->ddense;
   if (p.dense != nullptr || p.ddense != nullptr) p.af_grid = 0;   // generic gather path only
   if (p.af_grid != 0) {
-    static const bool use_mma = []() { const char* e = getenv("CREAM_AF_MMA"); return e == nullptr || e[0] != '0'; }();
-    p.af_mma = use_mma ? 1 : 0;     // CREAM_AF_MMA=0: the register-arithmetic structured path (round 1)
+    static const bool use_mma = []() { const char* e = getenv("CREAM_AF_MMA"); return e != nullptr && e[0] == '1'; }();
+    p.af_mma = use_mma ? 1 : 0;     // CREAM_AF_MMA=1 selects it; default: the register-arithmetic structured path
   }
   if (d->gp_grid == 14 && d->gp_grid * d->gp_grid + 1 == d->N && ctx_k && !ctx_v && d->idx_b == nullptr && !d->bias_pack &&
       p.dense == nullptr && p.ddense == nullptr && p.af_grid == 0 && d->gp_w >= 1 && d->gp_skip_id >= 0 && d->gp_skip_id < kNB) {

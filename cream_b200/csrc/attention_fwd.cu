@@ -704,8 +704,8 @@ extern "C" int cream_attn_fwd(const cream_attn_desc* d, void* stream_) {
     if (d->af_grid == 14 && d->af_max_rel >= d->af_grid - 1) {
       p.af_grid = d->af_grid;
       p.af_max_rel = d->af_max_rel;
-      static const bool use_mma = []() { const char* e = getenv("CREAM_AF_MMA"); return e == nullptr || e[0] != '0'; }();
-      p.af_mma = use_mma ? 1 : 0;     // CREAM_AF_MMA=0: the register-arithmetic structured path (round 1)
+      static const bool use_mma = []() { const char* e = getenv("CREAM_AF_MMA"); return e != nullptr && e[0] == '1'; }();
+      p.af_mma = use_mma ? 1 : 0;     // CREAM_AF_MMA=1 selects it; default: the register-arithmetic structured path
     }
   }
 

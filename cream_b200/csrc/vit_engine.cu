@@ -401,16 +401,31 @@ extern "C" int cream_vit_bwd(const cream_vit_desc* d, int first_stage, int last_
     ++t_launches;
     VIT_TRY(cream_layernorm_bwd(b.dln.p, b.dln.ld, 0, l.x.p, l.x.ld, p.ln1_g, l.mu1, l.rs1, g1.p, g1.ld, g.p, g.ld, p.g_ln1_g,
                                 p.g_ln1_b, M, E, s));
-    // table gradients of this layer: packed (64, 64) fp32 -> the reference's table tensors
-    for (int side = 0; side < 2; ++side) {
-      float* dp = side ? b.dtv_packs : b.dtk_packs;
-      if (dp == nullptr || p.g_tab[2 * side] == nullptr) continue;
-      float* g0[1] = {p.g_tab[2 * side]};
-      float* g1p[1] = {p.g_tab[2 * side + 1]};
-      ++t_launches;
-      VIT_TRY(cream_unpack_table_grads_batch(dp + static_cast<int64_t>(i) * 64 * 64, 1, 64, g0, g1p[0] ? g1p : nullptr, d->tab_nb,
-                                             d->tab_row_off1, side ? d->tabv_stride_b : d->tab_stride_b,
-                                             side ? d->tabv_stride_d : d->tab_stride_d, s));
+  }
+  // table gradients of the layers this call covered: packed (64, 64) fp32 -> the reference's table tensors,
+  // ONE launch per side for all of them (a single-block launch per layer costs ~12 us of latency each)
+  {
+    const int lo_stage = std::max(first_stage, 1), hi_stage = std::min(last_stage, d->depth);
+    const int n_layers = hi_stage - lo_stage + 1;                 // layers depth-hi_stage .. depth-lo_stage
+    if (n_layers > 0) {
+      const int first_layer = d->depth - hi_stage;
+      for (int side = 0; side < 2; ++side) {
+        float* dp = side ? b.dtv_packs : b.dtk_packs;
+        if (dp == nullptr || d->layers[first_layer].g_tab[2 * side] == nullptr) continue;
+        float* g0[CREAM_VIT_MAX_DEPTH];
+        float* g1[CREAM_VIT_MAX_DEPTH];
+        bool second = false;
+        for (int j = 0; j < n_layers; ++j) {
+          g0[j] = d->layers[first_layer + j].g_tab[2 * side];
+          g1[j] = d->layers[first_layer + j].g_tab[2 * side + 1];
+          second = second || g1[j] != nullptr;
+        }
+        ++t_launches;
+        VIT_TRY(cream_unpack_table_grads_batch(dp + static_cast<int64_t>(first_layer) * 64 * 64, n_layers, 64, g0,
+                                               second ? g1 : nullptr, d->tab_nb, d->tab_row_off1,
+                                               side ? d->tabv_stride_b : d->tab_stride_b,
+                                               side ? d->tabv_stride_d : d->tab_stride_d, s));
+      }
     }
   }
   return CREAM_OK;

@@ -164,7 +164,9 @@ def test_trainer_native_step_equals_python_sequencing_with_torch_adamw():
             for (n, p), (_, q) in zip(a.named_parameters(), b.named_parameters()):
                 assert (p.grad is None) == (q.grad is None), n
                 if p.grad is not None:
-                    assert rel_err(p.grad, q.grad) < 2e-5, f"gradient {n}"
+                    # the two trainers derive dlogits from different kernels (fused xent vs torch autograd): a
+                    # last-bit difference there moves a few bf16 roundings downstream
+                    assert rel_err(p.grad, q.grad) < 5e-3, f"gradient {n}"
     for (n, p), (_, q) in zip(a.named_parameters(), b.named_parameters()):
         # Adam's normalised step turns a re-association-level difference of a near-zero gradient element
         # into a +-lr difference of that element: compare in L2 over the tensor
