@@ -304,10 +304,11 @@ __device__ __forceinline__ void bwd_row_af(const BwdRowsParams& p, const RowCtx&
       put(x.s_dr + 4 * (32 + M1 - ci + G - 1), df);
     }
   } else {
+    // cls query row: every key gathers bucket 0 of both tables.  The bucket sums of P are genuine (= 1 each);
+    // those of dT are sum_j dT[0, j] = 0 exactly - only the rounding residual of delta would land there.
     put(x.s_pb + 4 * ((0 + x.sw) & 63), psum);
     put(x.s_pb + 4 * ((32 + x.sw) & 63), psum);
-    put(x.s_dr, dsum);
-    put(x.s_dr + 4 * 32, dsum);
+    (void)dsum;
   }
   if (hi == 0) rows_barrier();
   rows_barrier();
@@ -427,9 +428,13 @@ __device__ __forceinline__ void bwd_row_gridprod(const BwdRowsParams& p, const R
       wd[1] = make_uint4(dk[4], dk[5], dk[6], dk[7]);
     }
   }
-  flush(offa[LR - 1]);                                  // the last run (rows past the half's end repeat its offset)
-  {                                                     // local key 0 may share a bucket with a rectangle
-    const uint32_t a = bucket_addr(first4);
+  // The cls query row gathers ONE bucket for every key, i.e. adds a constant to its logits: its exact
+  // contribution to dR is sum_j dT[0, j] = 0.  What a flash-style backward would add instead is the
+  // rounding residual of delta = dO . O (bf16 O), scaled by the cls row's large gradient in DeiT - so
+  // non-patch rows are left out (their bucket row stays zero).
+  if (patch) {
+    flush(offa[LR - 1]);                                // the last run (rows past the half's end repeat its offset)
+    const uint32_t a = bucket_addr(first4);             // local key 0 may share a bucket with a rectangle
     sts_f32(a, lds_f32(a) + df);
   }
   rows_barrier();
@@ -791,7 +796,7 @@ attn_bwd_rows_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
         }
         put(0, __uint_as_float(ab[2 * G]));
         put(32, __uint_as_float(ab[2 * G]));
-      } else {
+      } else if (half == 0) {                  // cls query row: bucket sums of P are genuine, those of dT exactly 0
         float tot = __uint_as_float(ab[2 * G]);
 #pragma unroll
         for (int t = 0; t < G; ++t) tot += __uint_as_float(ab[t]);

@@ -81,21 +81,26 @@ class RPEAttention(nn.Module):
         self.rpe_k = make(head_dim, t_heads, self.mode, True, nb) if 'k' in rpe_on else None
         self.rpe_v = make(head_dim, t_heads, self.mode, False, nb) if 'v' in rpe_on else None
 
-    def bucket_ids(self, L):
-        side = int(math.sqrt(L))
-        skip = L - side * side
+    def bucket_ids(self, L, height=None, width=None):
+        """Bucket ids of an L-token sequence.  By default the grid is floor(sqrt(L)) square and the
+        remaining tokens are skipped (irpe.py:550-566); `height` / `width` give a non-square grid as the
+        DETR copy passes them (iRPE/DETR-with-iRPE/models/rpe_attention/rpe_attention_function.py:327-376)."""
+        if height is None:
+            height = width = int(math.sqrt(L))
+        skip = L - height * width
+        assert skip >= 0, "height * width exceeds the sequence length"
         if self.cross:
             out = []
             for m in (CROSS_ROWS, CROSS_COLS):
-                ids, nb = ops.irpe_bucket_ids(m, side, side, skip, 1 * self.ratio, 2 * self.ratio, 8 * self.ratio)
+                ids, nb = ops.irpe_bucket_ids(m, height, width, skip, 1 * self.ratio, 2 * self.ratio, 8 * self.ratio)
                 assert nb == self.num_buckets
                 out.append(ids)
             return tuple(out)
-        ids, nb = ops.irpe_bucket_ids(self.method, side, side, skip, 1 * self.ratio, 2 * self.ratio, 8 * self.ratio)
+        ids, nb = ops.irpe_bucket_ids(self.method, height, width, skip, 1 * self.ratio, 2 * self.ratio, 8 * self.ratio)
         assert nb == self.num_buckets
         return ids
 
-    def forward(self, x):
+    def forward(self, x, height=None, width=None):
         B, N, C = x.shape
         qkv = SlicedLinearFn.apply(x, self.qkv.weight, self.qkv.bias, C, 3 * C, False)   # (B, N, 3C) bf16
         pick = (lambda t: t.rp_rows.table) if self.cross else (lambda t: t.table)
@@ -104,7 +109,7 @@ class RPEAttention(nn.Module):
         second = [pick2(t) if t is not None else None for t in (self.rpe_k, self.rpe_v)]
         q1 = pick(self.rpe_q) if self.rpe_q is not None else None
         q2 = pick2(self.rpe_q) if self.rpe_q is not None else None
-        out = IrpeAttentionFn.apply(qkv, self.num_heads, float(self.scale), self.bucket_ids(N), self.mode,
+        out = IrpeAttentionFn.apply(qkv, self.num_heads, float(self.scale), self.bucket_ids(N, height, width), self.mode,
                                     *first, *second, q1, q2)
         out = SlicedLinearFn.apply(out, self.proj.weight, self.proj.bias, C, C, False)
         return self.proj_drop(out)
