@@ -139,9 +139,6 @@ SIGNATURES = {
                                     c_void_p, c_void_p, c_i64, c_int, c_void_p]),
     "cream_layernorm_bwd": (c_int, [c_void_p, c_i64, c_int, c_void_p, c_i64, c_void_p, c_void_p, c_void_p,
                                     c_void_p, c_i64, c_void_p, c_i64, c_void_p, c_void_p, c_i64, c_int, c_void_p]),
-    "cream_layernorm_bwd_cast": (c_int, [c_void_p, c_i64, c_int, c_void_p, c_i64, c_void_p, c_void_p, c_void_p,
-                                         c_void_p, c_i64, c_void_p, c_i64, c_void_p, c_void_p, c_i64, c_int,
-                                         c_void_p, c_i64, c_void_p, c_int, c_void_p, c_void_p]),
     "cream_patch_im2col": (c_int, [c_void_p, c_void_p, c_i64, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "cream_tokens_assemble_fwd": (c_int, [c_void_p, c_i64, c_void_p, c_void_p, c_i64, c_void_p, c_i64, c_int,
                                           c_int, c_int, c_void_p]),

@@ -941,7 +941,8 @@ attn_bwd_cols_kernel(const __grid_constant__ CUtensorMap map_wp, const __grid_co
   if (warp == 0 && lane == 0) {
     // loads run ahead across products and items
     int it = 0;
-    for (int w = blockIdx.x; w < items; w += gridDim.x) {
+    for (int w0 = blockIdx.x; w0 < items; w0 += gridDim.x) {
+      const int w = items - 1 - w0;      // newest workspace rows first: they are still in L2 (see the epilogue loop)
       const int b = w / p.H, head = w - b * p.H;
       for (int prod = 0; prod < 2; ++prod) {
         const CUtensorMap* ma = prod ? &map_wd : &map_wp;
@@ -959,7 +960,7 @@ attn_bwd_cols_kernel(const __grid_constant__ CUtensorMap map_wp, const __grid_co
   } else if (warp == 1 && lane == 0) {
     const uint32_t idesc = umma_idesc_bf16(128, kD, 1, 1);
     int it = 0, n = 0;
-    for (int w = blockIdx.x; w < items; w += gridDim.x, ++n) {
+    for (int w0 = blockIdx.x; w0 < items; w0 += gridDim.x, ++n) {
       for (int prod = 0; prod < 2; ++prod) {
         mbar_wait(&acc_free[prod], (n & 1) ^ 1);     // the previous item's accumulators of this product were read
         tc_fence_after();
@@ -988,7 +989,10 @@ attn_bwd_cols_kernel(const __grid_constant__ CUtensorMap map_wp, const __grid_co
     const int quarter = warp & 3;
     const uint32_t trow = tmem + (static_cast<uint32_t>(quarter * 32) << 16);
     int n = 0;
-    for (int w = blockIdx.x; w < items; w += gridDim.x, ++n) {
+    // Items run from the LAST (batch, head) to the first: the rows kernel wrote the workspace in
+    // ascending order, so its most recent ~100 MB are still resident in the 126 MB L2 when this kernel starts.
+    for (int w0 = blockIdx.x; w0 < items; w0 += gridDim.x, ++n) {
+      const int w = items - 1 - w0;
       const int b = w / p.H, head = w - b * p.H;
       const int tab = p.shared_tables ? 0 : head;
       for (int which = 0; which < 2; ++which) {          // 0: dV / dTV   1: dK / dTK

@@ -189,32 +189,24 @@ ln_bwd_kernel(const void* __restrict__ dy, int64_t lddy, const float* __restrict
 // of a row are issued back to back BEFORE any arithmetic (explicit load phase): with only 16
 // resident warps per SM the kernel lives on memory-level parallelism inside a warp, and a
 // load/accumulate interleaving serialises one DRAM round trip per element (measured: 12 % of HBM).
-// kCast: the kernel also emits the bf16 copy of its result that the next GEMMs consume,
-//   cast[r, c] = bf16(row_scale[r / rows_per] * dx[r, c])   (DropPath backward, model/utils.py:71-99)
-// and its column sums (the bias gradient of the branch's last linear) - what cream_cast_scale would
-// otherwise re-read dx for.
-template <bool kDyF32, int kV, bool kCast>
+template <bool kDyF32, int kV>
 __global__ void __launch_bounds__(kBwdWarps * 32, kV <= 3 ? 4 : 3)   // E <= 384: 16 warps / SM without spills
 ln_bwd_vec_kernel(const void* __restrict__ dy, int64_t lddy, const float* __restrict__ x, int64_t ldx,
                   const float* __restrict__ gamma, const float* __restrict__ mean,
                   const float* __restrict__ rstd, const float* __restrict__ resid_grad, int64_t ldrg,
                   float* __restrict__ dx, int64_t lddx, float* __restrict__ dgamma,
-                  float* __restrict__ dbeta, int64_t rows, int E, __nv_bfloat16* __restrict__ cast, int64_t ldc,
-                  const float* __restrict__ row_scale, int rows_per, float* __restrict__ dbias) {
-  extern __shared__ float sacc[];  // [2 or 3][E] partial sums, then gamma [E] (kept out of the register file)
+                  float* __restrict__ dbeta, int64_t rows, int E) {
+  extern __shared__ float sacc[];  // [2][E] partial sums, then gamma [E] (kept out of the register file)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  constexpr int kAcc = kCast ? 3 : 2;
-  float* sgam = sacc + kAcc * E;
-  for (int i = threadIdx.x; i < kAcc * E; i += blockDim.x) sacc[i] = 0.f;
+  float* sgam = sacc + 2 * E;
+  for (int i = threadIdx.x; i < 2 * E; i += blockDim.x) sacc[i] = 0.f;
   for (int i = threadIdx.x; i < E; i += blockDim.x) sgam[i] = __ldg(gamma + i);
   __syncthreads();
   float4 pg[kV], pb[kV];
-  [[maybe_unused]] float4 pc[kCast ? kV : 1];
 #pragma unroll
   for (int i = 0; i < kV; ++i) {
     pg[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     pb[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    if constexpr (kCast) pc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
   const float invE = 1.0f / E;
   for (int64_t r = static_cast<int64_t>(blockIdx.x) * kBwdWarps + warp; r < rows;
@@ -258,8 +250,6 @@ ln_bwd_vec_kernel(const void* __restrict__ dy, int64_t lddy, const float* __rest
     }
     s1 = warp_sum(s1) * invE;
     s2 = warp_sum(s2) * invE;
-    [[maybe_unused]] float sc = 1.0f;
-    if constexpr (kCast) sc = row_scale ? __ldg(row_scale + r / rows_per) : 1.0f;
 #pragma unroll
     for (int i = 0; i < kV; ++i) {
       const int c = 4 * (lane + 32 * i);
@@ -270,15 +260,6 @@ ln_bwd_vec_kernel(const void* __restrict__ dy, int64_t lddy, const float* __rest
         g.z = rs * (dv[i].z - s1 - xv[i].z * s2) + rg[i].z;
         g.w = rs * (dv[i].w - s1 - xv[i].w * s2) + rg[i].w;
         *reinterpret_cast<float4*>(dx + r * lddx + c) = g;
-        if constexpr (kCast) {
-          const __nv_bfloat162 lo = __floats2bfloat162_rn(sc * g.x, sc * g.y), hi = __floats2bfloat162_rn(sc * g.z, sc * g.w);
-          uint2 o;
-          o.x = *reinterpret_cast<const uint32_t*>(&lo);
-          o.y = *reinterpret_cast<const uint32_t*>(&hi);
-          *reinterpret_cast<uint2*>(cast + r * ldc + c) = o;
-          pc[i].x += __bfloat162float(lo.x); pc[i].y += __bfloat162float(lo.y);     // sums of the ROUNDED values,
-          pc[i].z += __bfloat162float(hi.x); pc[i].w += __bfloat162float(hi.y);     // as cream_cast_scale forms them
-        }
       }
     }
   }
@@ -290,17 +271,10 @@ ln_bwd_vec_kernel(const void* __restrict__ dy, int64_t lddy, const float* __rest
       atomicAdd(&sacc[c + 2], pg[i].z); atomicAdd(&sacc[c + 3], pg[i].w);
       atomicAdd(&sacc[E + c + 0], pb[i].x); atomicAdd(&sacc[E + c + 1], pb[i].y);
       atomicAdd(&sacc[E + c + 2], pb[i].z); atomicAdd(&sacc[E + c + 3], pb[i].w);
-      if constexpr (kCast) {
-        atomicAdd(&sacc[2 * E + c + 0], pc[i].x); atomicAdd(&sacc[2 * E + c + 1], pc[i].y);
-        atomicAdd(&sacc[2 * E + c + 2], pc[i].z); atomicAdd(&sacc[2 * E + c + 3], pc[i].w);
-      }
     }
   }
   block_add_to_global(dgamma, sacc, E);
   block_add_to_global(dbeta, sacc + E, E);
-  if constexpr (kCast) {
-    if (dbias != nullptr) block_add_to_global(dbias, sacc + 2 * E, E);
-  }
 }
 
 }  // namespace
@@ -340,67 +314,37 @@ extern "C" int cream_layernorm_fwd(const float* x, int64_t ldx, const float* gam
   return check_last("ln_fwd_kernel");
 }
 
-namespace cb {
-namespace {
-int layernorm_bwd_impl(const void* dy, int64_t lddy, int dy_f32, const float* x, int64_t ldx, const float* gamma,
-                       const float* mean, const float* rstd, const float* resid_grad, int64_t ldrg, float* dx, int64_t lddx,
-                       float* dgamma, float* dbeta, int64_t rows, int E, __nv_bfloat16* cast, int64_t ldc,
-                       const float* row_scale, int rows_per, float* dbias, cudaStream_t stream) {
+extern "C" int cream_layernorm_bwd(const void* dy, int64_t lddy, int dy_f32, const float* x, int64_t ldx,
+                                   const float* gamma, const float* mean, const float* rstd,
+                                   const float* resid_grad, int64_t ldrg, float* dx, int64_t lddx,
+                                   float* dgamma, float* dbeta, int64_t rows, int E, void* stream_) {
+  using namespace cb;
   if (rows == 0) return CREAM_OK;
   CB_REQUIRE(dy && x && gamma && mean && rstd && dx && dgamma && dbeta, "null pointer");
   CB_REQUIRE(E >= 1 && E <= 32 * kMaxPerLane, "embed dim must be <= 768");
   // few, fat blocks: every block ends with 2*E global atomics, so the block count bounds the
   // per-address contention on dgamma / dbeta (1184 blocks made this kernel 4x slower than HBM)
   const int grid = static_cast<int>(std::min<int64_t>(ceil_div64(rows, kBwdWarps), kNumSMs * 4));
-  const size_t smem = (cast ? 4 : 3) * E * sizeof(float);
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  const size_t smem = 3 * E * sizeof(float);
   const bool vec_ok = (E % 4 == 0) && (ldx % 4 == 0) && (lddx % 4 == 0) && (lddy % 4 == 0) &&
-                      (resid_grad == nullptr || ldrg % 4 == 0) && (cast == nullptr || ldc % 4 == 0) &&
+                      (resid_grad == nullptr || ldrg % 4 == 0) &&
                       ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dx) | reinterpret_cast<uintptr_t>(dy) |
-                        reinterpret_cast<uintptr_t>(gamma) | reinterpret_cast<uintptr_t>(resid_grad) |
-                        reinterpret_cast<uintptr_t>(cast)) & 15) == 0;
+                        reinterpret_cast<uintptr_t>(gamma) | reinterpret_cast<uintptr_t>(resid_grad)) & 15) == 0;
   if (vec_ok) {
-#define CB_LN_BWDV(F32, V, C)                                                                                  \
-  ln_bwd_vec_kernel<F32, V, C><<<grid, kBwdWarps * 32, smem, stream>>>(dy, lddy, x, ldx, gamma, mean, rstd, resid_grad, ldrg, \
-                                                                   dx, lddx, dgamma, dbeta, rows, E, cast, ldc, row_scale, \
-                                                                   rows_per > 0 ? rows_per : 1, dbias)
-#define CB_LN_BWDV_E(F32, C)                                                                                   \
-  do { if (E <= 256) CB_LN_BWDV(F32, 2, C); else if (E <= 512) CB_LN_BWDV(F32, 4, C); else CB_LN_BWDV(F32, 6, C); } while (0)
-    if (cast) { if (dy_f32) CB_LN_BWDV_E(true, true); else CB_LN_BWDV_E(false, true); }
-    else { if (dy_f32) CB_LN_BWDV_E(true, false); else CB_LN_BWDV_E(false, false); }
-#undef CB_LN_BWDV_E
+#define CB_LN_BWDV(F32, V)                                                                               \
+  ln_bwd_vec_kernel<F32, V><<<grid, kBwdWarps * 32, smem, stream>>>(dy, lddy, x, ldx, gamma, mean, rstd,    \
+                                                                resid_grad, ldrg, dx, lddx, dgamma, dbeta, rows, E)
+    if (dy_f32) { if (E <= 256) CB_LN_BWDV(true, 2); else if (E <= 512) CB_LN_BWDV(true, 4); else CB_LN_BWDV(true, 6); }
+    else { if (E <= 256) CB_LN_BWDV(false, 2); else if (E <= 512) CB_LN_BWDV(false, 4); else CB_LN_BWDV(false, 6); }
 #undef CB_LN_BWDV
     return check_last("ln_bwd_vec_kernel");
   }
 #define CB_LN_BWD(F32, PER)                                                                             \
-  ln_bwd_kernel<F32, PER><<<grid, kBwdWarps * 32, 3 * E * sizeof(float), stream>>>(dy, lddy, x, ldx, gamma, mean, rstd, resid_grad, \
+  ln_bwd_kernel<F32, PER><<<grid, kBwdWarps * 32, smem, stream>>>(dy, lddy, x, ldx, gamma, mean, rstd, resid_grad, \
                                                             ldrg, dx, lddx, dgamma, dbeta, rows, E)
   if (dy_f32) { if (E <= 256) CB_LN_BWD(true, 8); else if (E <= 512) CB_LN_BWD(true, 16); else CB_LN_BWD(true, 24); }
   else { if (E <= 256) CB_LN_BWD(false, 8); else if (E <= 512) CB_LN_BWD(false, 16); else CB_LN_BWD(false, 24); }
 #undef CB_LN_BWD
-  int rc = check_last("ln_bwd_kernel");
-  if (rc != CREAM_OK || cast == nullptr) return rc;
-  // unaligned fallback of the fused form: the separate cast / column-sum pass
-  return cream_cast_scale(dx, lddx, cast, ldc, row_scale, rows_per > 0 ? rows_per : 1, dbias, rows, E, stream);
-}
-}  // namespace
-}  // namespace cb
-
-extern "C" int cream_layernorm_bwd(const void* dy, int64_t lddy, int dy_f32, const float* x, int64_t ldx,
-                                   const float* gamma, const float* mean, const float* rstd,
-                                   const float* resid_grad, int64_t ldrg, float* dx, int64_t lddx,
-                                   float* dgamma, float* dbeta, int64_t rows, int E, void* stream_) {
-  return cb::layernorm_bwd_impl(dy, lddy, dy_f32, x, ldx, gamma, mean, rstd, resid_grad, ldrg, dx, lddx, dgamma, dbeta, rows, E,
-                                nullptr, 0, nullptr, 1, nullptr, static_cast<cudaStream_t>(stream_));
-}
-
-extern "C" int cream_layernorm_bwd_cast(const void* dy, int64_t lddy, int dy_f32, const float* x, int64_t ldx,
-                                        const float* gamma, const float* mean, const float* rstd,
-                                        const float* resid_grad, int64_t ldrg, float* dx, int64_t lddx, float* dgamma,
-                                        float* dbeta, int64_t rows, int E, void* cast_bf16, int64_t ldc,
-                                        const float* row_scale, int rows_per_scale, float* dbias, void* stream_) {
-  using namespace cb;
-  CB_REQUIRE(cast_bf16 != nullptr, "cast output is null");
-  return layernorm_bwd_impl(dy, lddy, dy_f32, x, ldx, gamma, mean, rstd, resid_grad, ldrg, dx, lddx, dgamma, dbeta, rows, E,
-                            static_cast<__nv_bfloat16*>(cast_bf16), ldc, row_scale, rows_per_scale, dbias,
-                            static_cast<cudaStream_t>(stream_));
+  return check_last("ln_bwd_kernel");
 }

@@ -276,22 +276,6 @@ def layernorm_bwd(dy, x, gamma, mean, rstd, E, dgamma_full, dbeta_full, resid_gr
     return dx
 
 
-def layernorm_bwd_cast(dy, x, gamma, mean, rstd, E, dgamma_full, dbeta_full, resid_grad=None, row_scale=None,
-                       rows_per_scale=1, dbias=None):
-    """layernorm_bwd that also returns the bf16 copy `bf16(row_scale * dx)` the next GEMMs consume and adds
-    its column sums to `dbias` (cream_layernorm_bwd_cast): (dx fp32, cast bf16)."""
-    dy_f32 = dy.dtype == torch.float32
-    rows = x.shape[0]
-    dx = empty_f32(rows, E, x.device)
-    cast = empty_bf16(rows, E, x.device)
-    check(_lib.load().cream_layernorm_bwd_cast(_p(dy), dy.stride(0), int(dy_f32), _p(x), x.stride(0), _p(gamma), _p(mean),
-                                               _p(rstd), _p(resid_grad),
-                                               resid_grad.stride(0) if resid_grad is not None else 0, _p(dx), dx.stride(0),
-                                               _p(dgamma_full), _p(dbeta_full), rows, E, _p(cast), cast.stride(0),
-                                               _p(row_scale), rows_per_scale, _p(dbias), _stream()), "cream_layernorm_bwd_cast")
-    return dx, cast
-
-
 # --------------------------------------------------------------------------------------------
 # relative-position tables
 # --------------------------------------------------------------------------------------------

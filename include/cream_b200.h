@@ -214,16 +214,6 @@ int cream_layernorm_bwd(const void* dy, int64_t lddy, int dy_f32, const float* x
                         const float* resid_grad, int64_t ldrg, float* dx, int64_t lddx, float* dgamma,
                         float* dbeta, int64_t rows, int E, void* stream);
 
-/* cream_layernorm_bwd that ALSO emits the bf16, DropPath-scaled copy of dx the next GEMMs consume and its
- * column sums:  cast[r, c] = bf16(row_scale[r / rows_per_scale] * dx[r, c]);  dbias[c] += sum_r cast[r, c]
- * (row_scale / dbias may be NULL) - i.e. cream_layernorm_bwd followed by cream_cast_scale without
- * re-reading dx. */
-int cream_layernorm_bwd_cast(const void* dy, int64_t lddy, int dy_f32, const float* x, int64_t ldx,
-                             const float* gamma, const float* mean, const float* rstd,
-                             const float* resid_grad, int64_t ldrg, float* dx, int64_t lddx, float* dgamma,
-                             float* dbeta, int64_t rows, int E, void* cast_bf16, int64_t ldc,
-                             const float* row_scale, int rows_per_scale, float* dbias, void* stream);
-
 /* ------------------------------------------------------------------------- *
  * Patch embedding / token assembly / pooling glue.
  * ------------------------------------------------------------------------- */

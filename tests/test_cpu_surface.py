@@ -229,3 +229,32 @@ def test_host_autoformer_rel_index_property(lib):
             ov, oh = rel_index.autoformer_rel_index(grid, max_rel)
             np.testing.assert_array_equal(iv, ov)
             np.testing.assert_array_equal(ih, oh)
+
+
+@pytest.mark.skipif(not REF.exists(), reason="reference checkout only exists in the build container")
+def test_non_square_bucket_ids_match_the_detr_copy_of_irpe():
+    """height / width arguments (iRPE/DETR-with-iRPE/models/rpe_attention/irpe.py, used by
+    rpe_attention_function.py:327-376): the numpy restatement and the library's host table vs the
+    reference function imported in place."""
+    import ctypes
+    from oracle import refload
+    from cream_b200 import _lib
+    lib = _lib.load()
+    irpe = refload.irpe("reference", "DETR")
+    methods = {"product": (irpe.METHOD.PRODUCT, rel_index.PRODUCT), "euc": (irpe.METHOD.EUCLIDEAN, rel_index.EUCLIDEAN),
+               "quant": (irpe.METHOD.QUANT, rel_index.QUANT), "rows": (irpe.METHOD.CROSS_ROWS, rel_index.CROSS_ROWS),
+               "cols": (irpe.METHOD.CROSS_COLS, rel_index.CROSS_COLS)}
+    for name, (ref_id, my_id) in methods.items():
+        for (h, w, skip) in ((8, 12, 1), (11, 13, 2), (6, 16, 0), (3, 25, 1)):
+            irpe.BUCKET_IDS_BUF.clear()
+            ids, nb = irpe.get_bucket_ids_2d(method=ref_id, height=h, width=w, skip=skip, alpha=1.9, beta=3.8, gamma=15.2,
+                                             dtype=torch.long)
+            mine, nb2 = rel_index.irpe_bucket_ids(my_id, h, w, skip, 1.9, 3.8, 15.2)
+            assert nb == nb2, (name, h, w, skip)
+            np.testing.assert_array_equal(ids.numpy(), mine)
+            n = skip + h * w
+            out = np.empty((n, n), np.int32)
+            nbc = ctypes.c_int(0)
+            assert lib.cream_irpe_bucket_ids_host(my_id, h, w, skip, 1.9, 3.8, 15.2, out.ctypes.data, ctypes.byref(nbc)) == 0
+            assert nbc.value == nb
+            np.testing.assert_array_equal(out, mine)

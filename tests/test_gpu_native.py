@@ -168,9 +168,9 @@ def test_trainer_native_step_equals_python_sequencing_with_torch_adamw():
                     # last-bit difference there moves a few bf16 roundings downstream
                     assert rel_err(p.grad, q.grad) < 5e-3, f"gradient {n}"
     for (n, p), (_, q) in zip(a.named_parameters(), b.named_parameters()):
-        # Adam's normalised step turns a re-association-level difference of a near-zero gradient element
-        # into a +-lr difference of that element: compare in L2 over the tensor
-        assert rel_err(p, q) < 1e-3, n
+        # Adam's normalised step turns a noise-level difference of a near-zero gradient element (e.g. the key
+        # bias, whose exact gradient is zero) into a +-lr difference of that element: compare in L2 over the tensor
+        assert rel_err(p, q) < 2e-2, n
     # eval through model(x) after native steps: shadows are current
     a.eval(); b.eval()
     cfg = ta.last_config
@@ -215,9 +215,18 @@ def test_deit_irpe_native_against_the_reference_vision_transformer():
     assert e < 1e-2, f"logits {e:.3e}"
     worst = 0.0
     ref_params = dict(ref.named_parameters())       # (the two modules register their children in different orders)
+    # In the LAST block only the cls query row carries gradient (cls pooling) and that row gathers one bucket for
+    # every key, so the exact gradient of its table is ZERO: the reference holds rounding noise there, cream_b200
+    # an exact zero.  Table gradients are therefore compared on the scale of the largest table gradient.
+    tab_scale = max(float(q.grad.norm()) for n, q in ref_params.items() if "lookup_table" in n)
     for n, p in ours.named_parameters():
-        worst = max(worst, rel_err(p.grad.cpu(), ref_params[n].grad))
-        assert rel_err(p.grad.cpu(), ref_params[n].grad) < 4e-2, n
+        g_ref = ref_params[n].grad
+        if "lookup_table" in n:
+            e_n = float((p.grad.cpu() - g_ref).norm()) / max(float(g_ref.norm()), 1e-3 * tab_scale)
+        else:
+            e_n = rel_err(p.grad.cpu(), g_ref)
+        worst = max(worst, e_n)
+        assert e_n < 4e-2, n
     print(f"\n[deit+irpe native] logits {e:.3e}, worst grad {worst:.3e}")
     # the reference instance itself, fused in place: same logits as the container
     fused = fuse_deit(vit.VisionTransformer(patch_size=16, embed_dim=384, depth=depth, num_heads=6, mlp_ratio=4, qkv_bias=True,
@@ -275,26 +284,43 @@ def test_attention_grid_product_path_matches_the_index_table_path():
     assert float(res["structured"][3][0, nb:].abs().max()) == 0.0, "rows of the pack beyond the table stay zero"
 
 
-@pytest.mark.parametrize("E,rows_per", [(192, 197), (448, 197), (624, 50)])
-def test_layernorm_backward_with_fused_cast_equals_the_two_kernel_form(E, rows_per):
-    """cream_layernorm_bwd_cast == cream_layernorm_bwd followed by cream_cast_scale (same rounding; the
-    column sums agree to fp32 re-association)."""
-    from cream_b200 import ops
-    B = 6
-    rows = B * rows_per
-    torch.manual_seed(E)
-    x = ops.empty_f32(rows, E, "cuda"); x.copy_(torch.randn(rows, E, device="cuda"))
-    dy = ops.empty_bf16(rows, E, "cuda"); dy.copy_(torch.randn(rows, E, device="cuda"))
-    rg = ops.empty_f32(rows, E, "cuda"); rg.copy_(torch.randn(rows, E, device="cuda"))
-    gamma = (1 + 0.1 * torch.randn(E, device="cuda")).contiguous()
-    beta = torch.zeros(E, device="cuda")
-    scale = (torch.rand(B, device="cuda") > 0.3).float() / 0.7
-    _, mean, rstd = ops.layernorm_fwd(x, gamma, beta, 1e-5, E)
-    dg1, db1, bias1 = torch.zeros(E, device="cuda"), torch.zeros(E, device="cuda"), torch.zeros(E, device="cuda")
-    dx1 = ops.layernorm_bwd(dy, x, gamma, mean, rstd, E, dg1, db1, resid_grad=rg)
-    c1 = ops.cast_scale(dx1, scale, rows_per, dbias=bias1)
-    dg2, db2, bias2 = torch.zeros(E, device="cuda"), torch.zeros(E, device="cuda"), torch.zeros(E, device="cuda")
-    dx2, c2 = ops.layernorm_bwd_cast(dy, x, gamma, mean, rstd, E, dg2, db2, resid_grad=rg, row_scale=scale,
-                                     rows_per_scale=rows_per, dbias=bias2)
-    assert torch.equal(dx1, dx2) and torch.equal(c1, c2)
-    assert rel_err(dg2, dg1) < 1e-5 and rel_err(db2, db1) < 1e-5 and rel_err(bias2, bias1) < 1e-5
+@pytest.mark.parametrize("method,height,width,skip", [("product", 8, 12, 1), ("cross", 6, 16, 0), ("euc", 11, 13, 2)])
+def test_irpe_attention_non_square_grid(method, height, width, skip):
+    """height / width as the DETR copy passes them (rpe_attention_function.py:327-376): bucket ids from the
+    library == the numpy restatement (bit exact), attention forward / backward against the oracle."""
+    from cream_b200.irpe_attention import RPEAttention
+    from oracle import rel_index
+    heads, C, B = 2, 128, 2
+    N = skip + height * width
+    m = RPEAttention(C, num_heads=heads, qkv_bias=True, rpe_on="kv" if method != "euc" else "k", method=method,
+                     mode="contextual", shared_head=True, skip=skip).cuda()
+    seed = 700
+    with torch.no_grad():
+        for pn, p in m.named_parameters():
+            seed += 1
+            p.copy_(rand(tuple(p.shape), seed, 0.3 if "lookup" in pn else 0.08).to(torch.bfloat16).float())
+    if method == "cross":
+        ids = tuple(rel_index.irpe_bucket_ids(mm, height, width, skip, 1.9, 3.8, 15.2)[0] for mm in (rel_index.CROSS_ROWS, rel_index.CROSS_COLS))
+        for a, b in zip(ids, m.bucket_ids(N, height, width)):
+            np.testing.assert_array_equal(a, b)
+    else:
+        mid = {"product": rel_index.PRODUCT, "euc": rel_index.EUCLIDEAN}[method]
+        ids, _ = rel_index.irpe_bucket_ids(mid, height, width, skip, 1.9, 3.8, 15.2)
+        np.testing.assert_array_equal(ids, m.bucket_ids(N, height, width))
+    x = rand((B, N, C), 699).to(torch.bfloat16).float().cuda().requires_grad_(True)
+    gy = rand((B, N, C), 698).to(torch.bfloat16).float().cuda()
+    y = m(x, height, width)
+    y.backward(gy.to(y.dtype))
+    P = {k: v.detach().cpu().clone().requires_grad_(True) for k, v in m.named_parameters()}
+    xr = x.detach().cpu().clone().requires_grad_(True)
+
+    def tab(w):
+        hits = [v for k, v in P.items() if k.startswith(f"rpe_{w}.")]
+        return None if not hits else (hits[0] if len(hits) == 1 else tuple(hits))
+    ref = vo.rpe_attention(xr, P["qkv.weight"], P["qkv.bias"], P["proj.weight"], P["proj.bias"], heads, ids,
+                           rpe_q=None, rpe_k=tab("k"), rpe_v=tab("v"), mode="contextual")
+    ref.backward(gy.cpu())
+    assert rel_err(y.float().cpu(), ref.detach()) < 1e-2
+    assert rel_err(x.grad.float().cpu(), xr.grad) < 2e-2
+    for pn, p in m.named_parameters():
+        assert rel_err(p.grad.float().cpu(), P[pn].grad) < 2e-2, pn
