@@ -373,7 +373,9 @@ def main():
     ap.add_argument("--config", default="c3", choices=sorted(CONFIGS), help="BASELINE.json configuration")
     ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (default = the configuration's own)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--overlap", action="store_true", help="per-layer all-reduce overlapped with backward (N > 1)")
+    ap.add_argument("--overlap", type=int, default=2,
+                    help="gradient all-reduce collectives per step at N > 1: 1 = one after the backward, k = k-1 "
+                         "overlapped + one after (default 2), 0 = one per layer (round-1 schedule)")
     ap.add_argument("--python-engine", action="store_true", help="sequence the kernels from Python (cross-check)")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -410,7 +412,7 @@ def main():
                                     num_heads=spec["num_heads"], mlp_ratio=spec["mlp_ratio"], qkv_bias=True, drop_rate=0.0,
                                     drop_path_rate=0.1, gp=True, num_classes=1000, max_relative_position=14,
                                     relative_position=True, change_qkv=True, abs_pos=True).to(dev).train()
-    trainer = SupernetTrainer(model, ss, native=not args.python_engine, overlap=args.overlap)
+    trainer = SupernetTrainer(model, ss, native=not args.python_engine, overlap=(True if args.overlap == 0 else args.overlap))
     g = torch.Generator().manual_seed(1234 + rank)
     n_host = 4
     host_imgs = [torch.randn(B, 3, 224, 224, generator=g).pin_memory() for _ in range(n_host)]
@@ -589,7 +591,8 @@ def main():
         "config": {"workload": conf["workload"], "baseline_config": args.config, "global_batch": B * world,
                    "per_gpu_batch": B, "parallelism": f"dp{world}",
                    "runtime": "python sequencing" if args.python_engine else "native (cream_vit_fwd/bwd, cream_adamw_step)",
-                   "grad_allreduce": ("per-layer, overlapped" if args.overlap else "one fp32 all-reduce after backward") if world > 1 else "none",
+                   "grad_allreduce": ("one fp32 all-reduce per layer, overlapped" if args.overlap == 0 else
+                                      f"{args.overlap} fp32 all-reduce(s) per step, all but the last under the backward") if world > 1 else "none",
                    "config_stream": "sample_configs with random.Random(0), identical on all ranks; the SAME K "
                                     "configurations are used for value, e2e and the roofline pass",
                    "l2": "inputs + activations per step (> 5 GB) far exceed the 126 MB L2; 4 rotating batches"},

@@ -62,11 +62,13 @@ class GradBuckets:
         dev = next(iter(named.values())).device
         self.master = torch.zeros(sum(sizes.values()), dtype=torch.float32, device=dev)
         base = 0
-        self.end_of: Dict[str, int] = {}       # group -> end offset of its span in the master buffer
+        self.end_of: Dict[str, int] = {}       # group -> end / start offset of its span in the master buffer
+        self.start_of: Dict[str, int] = {}
         for gname, names in self.groups.items():
             buf = self.master[base:base + sizes[gname]]
             base += sizes[gname]
             self.end_of[gname] = base
+            self.start_of[gname] = base - sizes[gname]
             off = 0
             for n in names:
                 p = named[n]
@@ -88,7 +90,7 @@ class StagedBatch:
 
 class SupernetTrainer:
     def __init__(self, model: Vision_TransformerSuper, choices: dict, lr: float = 5e-4, weight_decay: float = 0.05,
-                 process_group=None, native: bool = True, overlap: bool = False):
+                 process_group=None, native: bool = True, overlap=2):
         """native=True (default): the step is a handful of C calls - cream_vit_fwd, cream_xent_fwd_bwd,
         cream_vit_bwd (one call per all-reduce group when world > 1), cream_adamw_step (AdamW fused with
         the bf16 shadow refresh).  native=False: the same kernels sequenced from Python with torch's
@@ -187,12 +189,13 @@ class SupernetTrainer:
         groups (embed | head | block 0 .. L-1 sit at the front of the master buffer; un-sampled layers
         behind them are neither zero-filled by kernels nor reduced).
 
-        overlap=True instead reduces each group as soon as its stage is enqueued (NCCL on a side
-        stream).  Measured in round 1: NCCL's resident CTAs take SMs away from the persistent,
-        statically scheduled GEMM / attention kernels (+8 % on every GEMM while a collective is in
-        flight, 0.94 weak-scaling efficiency); the whole exchange is 0.1-0.14 GB over NVLink 5 /
-        NVSwitch (a few hundred microseconds), so one collective after the backward costs less than
-        the contention it removes."""
+        `overlap` = number of collectives per step.  1: the single all-reduce above.  k > 1 (default 2):
+        k - 1 collectives over the upper blocks run on a side stream under the remaining backward and
+        the last one - the prefix of the buffer - follows it.  True: one collective per group as in round 1.
+        Measured at N = 2 (profiles/r02_scaling.md): NCCL's resident CTAs take SMs away from the
+        persistent, statically scheduled GEMM / attention kernels (+8 % on every kernel that runs
+        beside a collective), so 16 small collectives cost more (0.93) than one exposed 0.56 ms
+        exchange (0.956); a few large ones hide most of the exchange and disturb few kernels."""
         self.buckets.master.zero_()
         if self.native.G is not self.buckets.views:      # an autograd call through model(x) re-bound them
             self.native.bind_grads(self.buckets.views)
@@ -200,20 +203,39 @@ class SupernetTrainer:
         if self.world == 1:
             self.native.backward(dlogits)
             return
-        if not self.overlap:
+        chunks = max(1, int(self.overlap) if self.overlap is not True else L + 2)
+        if chunks == 1:
             self.native.backward(dlogits)
             span = self.buckets.master[:self.buckets.end_of["block%d" % (L - 1)]]
             dist.all_reduce(span, op=dist.ReduceOp.AVG, group=self.pg)
             return
-        self.native.backward(dlogits, 0, 0)
-        self._allreduce("head")
-        for stage in range(1, L + 1):
-            self.native.backward(dlogits, stage, stage)
-            self._allreduce("block%d" % (L - stage))
-        self.native.backward(dlogits, L + 1, L + 1)
-        self._allreduce("embed")
-        if self.comm_stream is not None:
+        if chunks >= L + 2:          # one collective per group (round 1's schedule)
+            self.native.backward(dlogits, 0, 0)
+            self._allreduce("head")
+            for stage in range(1, L + 1):
+                self.native.backward(dlogits, stage, stage)
+                self._allreduce("block%d" % (L - stage))
+            self.native.backward(dlogits, L + 1, L + 1)
+            self._allreduce("embed")
             torch.cuda.current_stream().wait_stream(self.comm_stream)
+            return
+        # `chunks` collectives: chunks - 1 of them cover the upper blocks in equal shares and run on the side
+        # stream under the rest of the backward; the last one (embed | head | lowest blocks: a prefix of the
+        # master buffer) follows the backward on the compute stream.
+        per = max(1, L // chunks)
+        bounds = [L - per * c for c in range(chunks)]           # block index where each overlapped chunk starts
+        hi, stage_done = L, 0
+        for lo in bounds[1:]:
+            self.native.backward(dlogits, stage_done, L - lo)   # stages up to and including layer `lo`
+            stage_done = L - lo + 1
+            span = self.buckets.master[self.buckets.start_of["block%d" % lo]:self.buckets.end_of["block%d" % (hi - 1)]]
+            self.comm_stream.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(self.comm_stream):
+                dist.all_reduce(span, op=dist.ReduceOp.AVG, group=self.pg)
+            hi = lo
+        self.native.backward(dlogits, stage_done, L + 1)
+        dist.all_reduce(self.buckets.master[:self.buckets.end_of["block%d" % (hi - 1)]], op=dist.ReduceOp.AVG, group=self.pg)
+        torch.cuda.current_stream().wait_stream(self.comm_stream)
 
     def stage(self, images: torch.Tensor, targets: torch.Tensor) -> StagedBatch:
         """Start the host->device copy of the NEXT batch on a side stream and return a handle for

@@ -319,3 +319,46 @@ def rpe_vision_transformer(over: str = "reference"):
     mod.irpe = mod_irpe
     _CACHE[key] = mod
     return mod
+
+
+# ---------------------------------------------------------------------------------------------
+# TinyCLIP
+# ---------------------------------------------------------------------------------------------
+def open_clip_model():
+    """The reference's TinyCLIP/src/open_clip/model.py as a module, without running the package
+    __init__ (which pulls ftfy / regex through the tokenizer): its sibling imports (.timm_model, .utils,
+    .resnet, .l0module) resolve to name-only stubs - the attention path needs none of them."""
+    key = ("open_clip_model",)
+    if key in _CACHE:
+        return _CACHE[key]
+    ref = reference_root()
+    assert ref is not None
+    path = ref / "TinyCLIP" / "src" / "open_clip" / "model.py"
+    pkg = types.ModuleType("cream_ref_open_clip")
+    pkg.__path__ = []
+
+    class _Stub(nn.Module):
+        def __init__(self, *a, **k):
+            super().__init__()
+
+    def sub(name, **attrs):
+        m = types.ModuleType("cream_ref_open_clip." + name)
+        for k, v in attrs.items():
+            setattr(m, k, v)
+        return m
+    mapping = {"cream_ref_open_clip": pkg,
+               "cream_ref_open_clip.timm_model": sub("timm_model", TimmModel=_Stub),
+               "cream_ref_open_clip.utils": sub("utils", freeze_batch_norm_2d=lambda *a, **k: None,
+                                                to_2tuple=lambda x: x if isinstance(x, tuple) else (x, x)),
+               "cream_ref_open_clip.resnet": sub("resnet", ModifiedResNet=_Stub),
+               "cream_ref_open_clip.l0module": sub("l0module", L0Module=_Stub)}
+    with _module_overrides(mapping):
+        spec = importlib.util.spec_from_file_location("cream_ref_open_clip.model", path)
+        mod = importlib.util.module_from_spec(spec)
+        sys.modules["cream_ref_open_clip.model"] = mod
+        try:
+            spec.loader.exec_module(mod)
+        finally:
+            sys.modules.pop("cream_ref_open_clip.model", None)
+    _CACHE[key] = mod
+    return mod

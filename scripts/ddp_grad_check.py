@@ -44,6 +44,7 @@ def main():
     targets = torch.randint(0, 1000, (per * world,), generator=g)
     cfg = {"layer_num": 13, "embed_dim": [216] * 13, "num_heads": [3, 4] * 6 + [3], "mlp_ratio": [3.5, 4.0] * 6 + [4.0]}
     tr.forward_backward(images[rank * per:(rank + 1) * per].to(dev), targets[rank * per:(rank + 1) * per].to(dev), config=cfg)
+    tr.sync_grads_to_params()
     torch.cuda.synchronize()
     ddp = {n: (None if p.grad is None else p.grad.detach().clone()) for n, p in net.named_parameters()}
     # one rank, the whole batch, plain autograd over the same engine (no buckets, no collectives)

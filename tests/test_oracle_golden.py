@@ -381,3 +381,27 @@ def test_supernet_t_oracle_against_the_reference_model():
         for k in [k for k in sys.modules if k == "model" or k.startswith("model.")]:
             del sys.modules[k]
         sys.modules.update({k: v for k, v in saved.items() if v is not None})
+
+
+def test_clip_attention_oracle_is_pinned_against_the_reference_block():
+    """vo.clip_attention vs the reference's OWN `ResidualAttentionBlock.attention`
+    (TinyCLIP/src/open_clip/model.py:238-283, loaded unmodified through oracle/refload.py): the
+    nn.MultiheadAttention branch (with and without the causal mask of the text tower, model.py:756-762) and the
+    naive branch with the pruning multipliers head_z / hidden_z."""
+    from oracle import refload
+    if not refload.available():
+        pytest.skip("reference not available (build container / staged baseline/_ref only)")
+    m = refload.open_clip_model()
+    torch.manual_seed(0)
+    for d_model, heads, length, batch in ((128, 2, 50, 3), (512, 8, 77, 2)):
+        blk = m.ResidualAttentionBlock(d_model=d_model, n_head=heads)
+        a = blk.attn
+        x = torch.randn(length, batch, d_model)
+        causal = torch.full((length, length), float("-inf")).triu_(1)
+        cases = [(None, None, None), (causal, None, None), (None, torch.rand(heads), torch.rand(d_model))]
+        for mask, hz, hd in cases:
+            with torch.no_grad():
+                want = blk.attention(x, attn_mask=mask, head_z=hz, hidden_z=hd)
+                got = vo.clip_attention(x, a.in_proj_weight, a.in_proj_bias, a.out_proj.weight, a.out_proj.bias, heads,
+                                        attn_mask=mask, head_z=hz, hidden_z=hd)
+            assert float((want - got).abs().max()) < 2e-6
