@@ -373,9 +373,9 @@ def main():
     ap.add_argument("--config", default="c3", choices=sorted(CONFIGS), help="BASELINE.json configuration")
     ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (default = the configuration's own)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--overlap", type=int, default=2,
+    ap.add_argument("--overlap", type=int, default=1,
                     help="gradient all-reduce collectives per step at N > 1: 1 = one after the backward, k = k-1 "
-                         "overlapped + one after (default 2), 0 = one per layer (round-1 schedule)")
+                         "overlapped + one after, 0 = one per layer (round-1 schedule)")
     ap.add_argument("--python-engine", action="store_true", help="sequence the kernels from Python (cross-check)")
     args = ap.parse_args()
     if args.impl == "reference":
