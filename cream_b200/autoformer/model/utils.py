@@ -3,7 +3,6 @@
 from __future__ import annotations
 
 import collections.abc
-from itertools import repeat
 
 import torch
 import torch.nn as nn
@@ -14,16 +13,13 @@ def trunc_normal_(tensor, mean=0., std=1., a=-2., b=2.):
     return nn.init.trunc_normal_(tensor, mean=mean, std=std, a=a, b=b)
 
 
-def _ntuple(n):
-    def parse(x):
-        if isinstance(x, collections.abc.Iterable):
-            return x
-        return tuple(repeat(x, n))
-    return parse
+def _tuple_of(n: int):
+    """x -> (x,) * n unless x is already iterable (the reference's to_2tuple family, model/utils.py:8-17)."""
+    return lambda x: x if isinstance(x, collections.abc.Iterable) else (x,) * n
 
 
-to_1tuple, to_2tuple, to_3tuple, to_4tuple = _ntuple(1), _ntuple(2), _ntuple(3), _ntuple(4)
-to_ntuple = _ntuple
+to_1tuple, to_2tuple, to_3tuple, to_4tuple = (_tuple_of(k) for k in (1, 2, 3, 4))
+to_ntuple = _tuple_of
 
 
 def drop_path_scale(batch: int, drop_prob: float, training: bool, device) -> torch.Tensor | None:

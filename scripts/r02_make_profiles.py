@@ -16,7 +16,7 @@ import subprocess
 import sys
 from pathlib import Path
 
-OUT = Path("profiles")
+OUT = Path(sys.argv[1]) if len(sys.argv) > 1 else Path("profiles")
 SRC = Path("gpurun_out")
 WANT = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
         "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
@@ -129,6 +129,7 @@ def launch_shares(path: Path) -> str:
 
 
 def main():
+    OUT.mkdir(parents=True, exist_ok=True)
     traffic = {}
     for rep in sorted(SRC.glob("prof_r02_*.ncu-rep")):
         (OUT / ("r02_ncu_" + rep.stem.replace("prof_r02_", "") + ".txt")).write_text(summarize(rep, traffic))
