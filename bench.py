@@ -38,6 +38,10 @@ CONFIGS = {
                workload=("DeiT-S + iRPE (product method, contextual mode on keys, 50 buckets, shared head) training step, "
                          "224^2, bs256, 12 blocks, DropPath 0.1, AdamW; 1 GPU")),
     "c3": dict(size="S", batch=128, metric=METRIC, workload=WORKLOAD),
+    "c4": dict(size="clip_b32", batch=128, metric="TinyCLIP ViT-B/32 contrastive training image-text pairs/sec (bs128/GPU)",
+               workload=("CLIP ViT-B/32 (image tower 12 x 768, 32x32 patches, 50 tokens; text tower 12 x 512, 77 tokens, "
+                         "causal mask) contrastive training step, 224^2, bs128/GPU (1024 on 8 GPUs), local loss + feature "
+                         "all_gather with gradient, AdamW")),
     "c5": dict(size="B", batch=64, metric="supernet images/sec (224^2, bs64/GPU)",
                workload=("AutoFormer-B supernet random-sample training step (embed 528-624, heads 9-10, depth 14-16, "
                          "mlp 3-4), 224^2, bs64/GPU, relative position on K and V, DropPath 0.1, AdamW")),
@@ -101,6 +105,8 @@ def cpu_baseline(steps: int, warmup: int, batch: int = 4, config: str = "c3"):
     size = CONFIGS[config]["size"]
     if size == "deit_s":
         return cpu_baseline_deit(steps, warmup, batch)
+    if size == "clip_b32":
+        return cpu_baseline_clip(steps, warmup, max(batch, 8))
     spec = {"S": vo.SUPERNET_S, "B": vo.SUPERNET_B, "T": vo.SUPERNET_T}[size]
     space = vo.SEARCH_SPACE[size]
     sd0 = vo.init_params(spec, seed=0)
@@ -160,6 +166,54 @@ def cpu_baseline(steps: int, warmup: int, batch: int = 4, config: str = "c3"):
     return {"value": batch * len(times) / total, "unit": UNIT, "cores": torch.get_num_threads(), "kind": kind,
             "sample": f"{len(times)} training steps of batch {batch} (same supernet-{size} config stream), fp32, "
                       f"{what} on {torch.get_num_threads()} host threads"}, total / len(times)
+
+
+def gpu_reference_supernet(spec, cfg_warm, cfg_timed, dev_imgs, dev_tgts, B):
+    """The reference's own Vision_TransformerSuper (unmodified files, stock PyTorch ops) training on the SAME
+    GPU, batch and subnet stream: fp16 autocast + loss scaling (supernet_engine.py:65-84) + fused AdamW."""
+    import torch
+    import torch.nn.functional as F
+    from oracle import refload
+    if not refload.available():
+        return None
+    try:
+        dev = dev_imgs[0].device
+        torch.manual_seed(0)
+        net = refload.autoformer("reference").Vision_TransformerSuper(
+            img_size=224, patch_size=16, embed_dim=spec["embed_dim"], depth=spec["depth"], num_heads=spec["num_heads"],
+            mlp_ratio=spec["mlp_ratio"], qkv_bias=True, drop_rate=0.0, drop_path_rate=0.1, gp=True, num_classes=1000,
+            max_relative_position=14, relative_position=True, change_qkv=True, abs_pos=True).to(dev).train()
+        opt = torch.optim.AdamW(net.parameters(), lr=5e-4, weight_decay=0.05, fused=True)
+        scaler = torch.amp.GradScaler("cuda")
+
+        def step(cfg, x, y):
+            opt.zero_grad(set_to_none=True)
+            net.set_sample_config(cfg)
+            with torch.autocast("cuda", dtype=torch.float16):
+                loss = F.cross_entropy(net(x), y)
+            scaler.scale(loss).backward()
+            scaler.step(opt)
+            scaler.update()
+        n = len(dev_imgs)
+        for s, cfg in enumerate(cfg_warm):
+            step(cfg, dev_imgs[s % n], dev_tgts[s % n])
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for s, cfg in enumerate(cfg_timed):
+            step(cfg, dev_imgs[s % n], dev_tgts[s % n])
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        out = {"value": B * len(cfg_timed) / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms / len(cfg_timed),
+               "what": "reference Vision_TransformerSuper (AutoFormer/model/supernet_transformer.py + module/*, unmodified; cuBLAS / "
+                       "stock PyTorch attention with the relative-position einsums) under fp16 autocast + GradScaler + fused AdamW, "
+                       f"same GPU, same batch, the first {len(cfg_timed)} subnets of the timed stream"}
+        del net, opt
+        torch.cuda.empty_cache()
+        return out
+    except Exception as e:   # noqa: BLE001
+        return {"unavailable": repr(e)[:300]}
 
 
 def _reference_deit(device):
@@ -273,19 +327,20 @@ def bench_deit(args):
     from cream_b200 import ops as _o
     ids, nb = _o.irpe_bucket_ids(3, 14, 14, 1, 1.9, 3.8, 15.2)
     it = _o.irpe_index_table_u8(ids, dev)
+    gp = (14,) + tuple(_o.irpe_grid_product_structure(ids, 14, 1))     # the structured gather the model runs
     dout = ops.empty_bf16(B * N, 64 * H)
     dout.copy_(torch.randn(B * N, 64 * H, device=dev))
     def attn_times(reps=10):
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
-        out, lse = ops.attention_fwd(qkv, B, H, N, 0.125, tk=tk, idx=(it, None, None, None))
-        ops.attention_bwd(qkv, out, lse, dout, B, H, N, 0.125, tk=tk, idx=(it, None, None, None))
+        out, lse = ops.attention_fwd(qkv, B, H, N, 0.125, tk=tk, idx=(it, None, None, None), gp=gp)
+        ops.attention_bwd(qkv, out, lse, dout, B, H, N, 0.125, tk=tk, idx=(it, None, None, None), gp=gp)
         torch.cuda.synchronize()
         ev[0].record()
         for _ in range(reps):
-            out, lse = ops.attention_fwd(qkv, B, H, N, 0.125, tk=tk, idx=(it, None, None, None))
+            out, lse = ops.attention_fwd(qkv, B, H, N, 0.125, tk=tk, idx=(it, None, None, None), gp=gp)
         ev[1].record()
         for _ in range(reps):
-            ops.attention_bwd(qkv, out, lse, dout, B, H, N, 0.125, tk=tk, idx=(it, None, None, None))
+            ops.attention_bwd(qkv, out, lse, dout, B, H, N, 0.125, tk=tk, idx=(it, None, None, None), gp=gp)
         ev[2].record()
         torch.cuda.synchronize()
         return ev[0].elapsed_time(ev[1]) / reps * 1e-3, ev[1].elapsed_time(ev[2]) / reps * 1e-3
@@ -294,7 +349,7 @@ def bench_deit(args):
     by_fwd = 4.0 * B * H * N * 64 * 2
     peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text()) if (ROOT / "MEASURED_PEAKS.json").exists() else {}
     hbm, peak_tf = peaks.get("hbm_gbs", 6650.0), peaks.get("bf16_tflops_sustained", 1400.0)
-    roofline = {"kernel": "attn_fwd_kernel, iRPE contextual product gather on keys (the fused attention+iRPE kernel)",
+    roofline = {"kernel": "attn_fwd_kernel, iRPE contextual product gather on keys, grid-product structured path (the fused attention+iRPE kernel as the model runs it)",
                 "bound": "hbm", "achieved": by_fwd / t_fwd / 1e9, "peak": hbm, "unit": "GB/s", "frac": by_fwd / t_fwd / 1e9 / hbm,
                 "tflops": fl_fwd / t_fwd / 1e12, "tflops_frac_of_peak": fl_fwd / t_fwd / 1e12 / peak_tf, "avg_launch_us": t_fwd * 1e6,
                 "bwd_avg_us": t_bwd * 1e6, "bwd_tflops": 2.5 * fl_fwd / t_bwd / 1e12, "traffic": None,
@@ -349,6 +404,202 @@ def bench_deit(args):
     print(json.dumps(line))
 
 
+def _clip_batches(B, n, seed, pin=True):
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    pinned = (lambda t: t.pin_memory()) if pin else (lambda t: t)
+    imgs = [pinned(torch.randn(B, 3, 224, 224, generator=g)) for _ in range(n)]
+    txts = []
+    for _ in range(n):
+        t = torch.randint(1, 49406, (B, 77), generator=g)
+        eot = torch.randint(4, 77, (B,), generator=g)
+        for b in range(B):
+            t[b, eot[b]] = 49407
+            t[b, eot[b] + 1:] = 0
+        txts.append(pinned(t))
+    return imgs, txts
+
+
+def _reference_clip(device):
+    """The reference's own CLIP ViT-B/32 (TinyCLIP/src/open_clip/model.py + loss.py, unmodified)."""
+    import torch
+    from cream_b200.clip import VIT_B_32 as C4
+    from oracle import refload
+    m = refload.open_clip_model()
+    torch.manual_seed(0)
+    net = m.CLIP(C4["embed_dim"], dict(C4["vision_cfg"]), dict(C4["text_cfg"])).to(device).train()
+    named = list(net.named_parameters())
+    skip = lambda n, p: p.ndim < 2 or "bn" in n or "ln" in n or "bias" in n or "logit_scale" in n
+    opt = torch.optim.AdamW([dict(params=[p for n, p in named if skip(n, p)], weight_decay=0.0),
+                             dict(params=[p for n, p in named if not skip(n, p)], weight_decay=0.2)],
+                            lr=5e-4, betas=(0.9, 0.98), eps=1e-6, fused=(device != "cpu"))
+    return net, opt, refload.open_clip_loss().ClipLoss()
+
+
+def cpu_baseline_clip(steps: int, warmup: int, batch: int = 8):
+    import torch
+    from oracle import refload
+    assert refload.available(), "config c4's CPU arm needs the staged reference (scripts/stage_reference.py)"
+    net, opt, loss_fn = _reference_clip("cpu")
+    imgs, txts = _clip_batches(batch, 1, 7, pin=False)
+    torch.set_num_threads(min(os.cpu_count() or 1, 16))
+    times = []
+    for s in range(warmup + steps):
+        t0 = time.perf_counter()
+        opt.zero_grad(set_to_none=True)
+        fi, ft, sc = net(imgs[0], txts[0])
+        loss = loss_fn(fi, ft, sc)
+        loss.backward()
+        opt.step()
+        loss.item()
+        if s >= warmup:
+            times.append(time.perf_counter() - t0)
+    total = sum(times)
+    return {"value": batch * len(times) / total, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "reference",
+            "sample": f"{len(times)} contrastive training steps of batch {batch}, fp32, TinyCLIP/src/open_clip model.py + "
+                      f"loss.py (unmodified) on {torch.get_num_threads()} host threads"}, total / len(times)
+
+
+def bench_clip(args):
+    """BASELINE config 4: CLIP ViT-B/32 contrastive training, bs128/GPU, one process per GPU; the features
+    are exchanged with all_gather (the path's one real collective besides the gradient average)."""
+    import torch
+    import torch.distributed as dist
+    from cream_b200 import _lib, clip
+    from oracle import refload
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a B200 (no CPU fallback)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    _lib.load()
+    conf = CONFIGS["c4"]
+    W, K, B = max(3, args.warmup), args.steps, args.batch or conf["batch"]
+    torch.manual_seed(0)
+    net = clip.CLIP(clip.VIT_B_32["embed_dim"], clip.VIT_B_32["vision_cfg"], clip.VIT_B_32["text_cfg"]).to(dev).train()
+    tr = clip.ClipTrainer(net)
+    n_host = 4
+    host_imgs, host_txts = _clip_batches(B, n_host, 1234 + rank)
+    dev_imgs, dev_txts = [t.to(dev) for t in host_imgs], [t.to(dev) for t in host_txts]
+    pin_loss = torch.zeros((), dtype=torch.float32).pin_memory()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(n, from_host):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = _lib.LAUNCHES[0]
+        host = []
+        e0.record()
+        for s in range(n):
+            t0 = time.perf_counter()
+            i = s % n_host
+            if from_host:
+                loss = tr.step(host_imgs[i].to(dev, non_blocking=True), host_txts[i].to(dev, non_blocking=True))
+                pin_loss.copy_(loss, non_blocking=True)
+                if s + 1 == n:
+                    torch.cuda.current_stream().synchronize()
+            else:
+                loss = tr.step(dev_imgs[i], dev_txts[i])
+            host.append((time.perf_counter() - t0) * 1e3)
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms), _lib.LAUNCHES[0] - l0, host, float(pin_loss)
+
+    timed(W, False)
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    ms, launches, host, _ = timed(K, False)
+    timed(2, True)
+    ms_e2e, _, _, last_loss = timed(K, True)
+    clocks = sampler.stop() if sampler else None
+
+    # per-kernel-class times of one step (python sequencing -> ops.PROFILE brackets every launch)
+    from cream_b200 import ops
+    ops.PROFILE = []
+    tr.step(dev_imgs[0], dev_txts[0])
+    torch.cuda.synchronize()
+    by_kind = {}
+    for kind, a, b, fl, by in ops.PROFILE:
+        d = by_kind.setdefault(kind, [0.0, 0, 0.0, 0.0])
+        d[0] += a.elapsed_time(b)
+        d[1] += 1
+        d[2] += fl
+        d[3] += by
+    ops.PROFILE = None
+    peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text()) if (ROOT / "MEASURED_PEAKS.json").exists() else {}
+    hbm, peak_tf = peaks.get("hbm_gbs", 6650.0), peaks.get("bf16_tflops_sustained", 1400.0)
+    gm = by_kind.get("gemm", [1.0, 0, 0.0, 0.0])
+    roofline = {"kernel": "gemm_bf16_kernel (tcgen05; all GEMMs of one step, event-bracketed per launch)", "bound": "tensor",
+                "achieved": gm[2] / (gm[0] * 1e-3) / 1e12, "peak": peak_tf, "unit": "TFLOP/s",
+                "frac": gm[2] / (gm[0] * 1e-3) / 1e12 / peak_tf, "traffic": None,
+                "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md)",
+                "per_kind_ms": {k: {"ms": round(v[0], 3), "launches": v[1]} for k, v in sorted(by_kind.items())}}
+
+    gpu_ref = None
+    if world == 1 and refload.available():
+        try:
+            ref, opt, loss_fn = _reference_clip(dev)
+            def ref_step(x, t):
+                opt.zero_grad(set_to_none=True)
+                with torch.autocast("cuda", dtype=torch.bfloat16):      # --precision amp_bfloat16
+                    fi, ft, sc = ref(x, t)
+                    loss = loss_fn(fi, ft, sc)
+                loss.backward()
+                opt.step()
+                return loss
+            for s in range(3):
+                ref_step(dev_imgs[s % n_host], dev_txts[s % n_host])
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            kk = max(3, K // 2)
+            for s in range(kk):
+                ref_step(dev_imgs[s % n_host], dev_txts[s % n_host])
+            e1.record()
+            torch.cuda.synchronize()
+            rms = e0.elapsed_time(e1)
+            gpu_ref = {"value": B * kk / (rms * 1e-3), "unit": UNIT, "ms_per_step": rms / kk,
+                       "what": "reference CLIP (open_clip/model.py + loss.py, unmodified: nn.MultiheadAttention, cuDNN conv, "
+                               "cuBLAS) under bf16 autocast + fused AdamW, same GPU, same batch"}
+            del ref, opt
+        except Exception as e:   # noqa: BLE001
+            gpu_ref = {"unavailable": repr(e)[:300]}
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    pairs = B * K * world
+    line = {"metric": conf["metric"], "value": pairs / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+            "data": "synthetic",
+            "config": {"workload": conf["workload"], "baseline_config": "c4", "global_batch": B * world, "per_gpu_batch": B,
+                       "parallelism": f"dp{world}", "l2": "activations per step (> 3 GB) exceed the 126 MB L2; 4 rotating batches",
+                       "engine": "python sequencing of the C-ABI launches (one autograd node per tower)"},
+            "e2e": {"value": pairs / (ms_e2e * 1e-3), "unit": UNIT,
+                    "h2d_bytes_per_step": world * (B * 3 * 224 * 224 * 4 + B * 77 * 8), "d2h_bytes_per_step": 4 * world,
+                    "ms_per_step": ms_e2e / K, "last_loss": last_loss},
+            "gpu_launches": launches, "host_enqueue_ms_per_step": {"mean": sum(host) / len(host), "min": min(host)},
+            "clocks": clocks, "roofline": roofline, "gpu_reference": gpu_ref}
+    if gpu_ref and "value" in gpu_ref:
+        line["speedup_vs_gpu_reference"] = line["value"] / gpu_ref["value"]
+    if not args.no_cpu_baseline and world == 1 and refload.available():
+        line["cpu_baseline"], _ = cpu_baseline_clip(1, 1)
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -382,6 +633,8 @@ def main():
         return run_reference(args)
     if args.config == "c2":
         return bench_deit(args)
+    if args.config == "c4":
+        return bench_clip(args)
 
     import torch
     import torch.distributed as dist
@@ -615,6 +868,10 @@ def main():
         "model_flops_frac_of_peak": flops / (ms * 1e-3) / 1e12 / peak_tf,
         "attn_core_share_of_flops": attn_flops / max(flops, 1.0),
     }
+    if world == 1:
+        line["gpu_reference"] = gpu_reference_supernet(spec, cfg_warm[:3], cfg_timed[:max(4, K // 2)], dev_imgs, dev_tgts, B)
+        if line["gpu_reference"] and "value" in line["gpu_reference"]:
+            line["speedup_vs_gpu_reference"] = line["value"] / line["gpu_reference"]["value"]
     if not args.no_cpu_baseline and world == 1:
         line["cpu_baseline"], _ = cpu_baseline(2, 1, config=args.config)
     print(json.dumps(line))

@@ -362,3 +362,18 @@ def open_clip_model():
             sys.modules.pop("cream_ref_open_clip.model", None)
     _CACHE[key] = mod
     return mod
+
+
+def open_clip_loss():
+    """The reference's TinyCLIP/src/open_clip/loss.py as a module (it imports only torch)."""
+    key = ("open_clip_loss",)
+    if key in _CACHE:
+        return _CACHE[key]
+    ref = reference_root()
+    assert ref is not None
+    path = ref / "TinyCLIP" / "src" / "open_clip" / "loss.py"
+    spec = importlib.util.spec_from_file_location("cream_ref_open_clip_loss", path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    _CACHE[key] = mod
+    return mod
