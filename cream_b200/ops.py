@@ -146,7 +146,7 @@ SHADOWS = ShadowCache()
 # --------------------------------------------------------------------------------------------
 def gemm(M, N, K, a, lda, b, ldb, out, ldo, epi, *, groups=1, a_mn=0, b_mn=0, a_group_off=0,
          b_group_rows=0, k_groups=1, k_group_len=0, out_row_mul=1, out_g_row=0, out_g_col=0, aux=None,
-         ldaux=0, bias=None, resid=None, ldr=0, row_scale=None, rows_per_scale=1, alpha=1.0, split_k=0):
+         ldaux=0, bias=None, resid=None, ldr=0, row_scale=None, rows_per_scale=1, alpha=1.0, split_k=0, cta_pair=0):
     d = GemmDesc()
     d.M, d.N, d.K, d.groups = M, N, K, groups
     d.a, d.lda, d.a_mn, d.a_group_off = _p(a), lda, a_mn, a_group_off
@@ -159,7 +159,7 @@ def gemm(M, N, K, a, lda, b, ldb, out, ldo, epi, *, groups=1, a_mn=0, b_mn=0, a_
     d.bias = _p(bias)
     d.resid, d.ldr = _p(resid), ldr
     d.row_scale, d.rows_per_scale = _p(row_scale), rows_per_scale
-    d.alpha, d.split_k = alpha, split_k
+    d.alpha, d.split_k, d.cta_pair = alpha, split_k, cta_pair
     _profiled("gemm", 2.0 * M * N * K * groups, 0.0,
               lambda: check(_lib.load().cream_gemm_bf16(C.byref(d), _stream()), "cream_gemm_bf16"))
 
