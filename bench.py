@@ -168,6 +168,34 @@ def cpu_baseline(steps: int, warmup: int, batch: int = 4, config: str = "c3"):
                       f"{what} on {torch.get_num_threads()} host threads"}, total / len(times)
 
 
+def _e2e_steps(tr, host_a, host_b, n):
+    """n end-to-end steps through trainer.stage / trainer.step: every step's batch is copied from pinned host memory
+    inside the timed region (side stream, one step ahead) and every step's loss is copied to pinned host memory and
+    read on the host one step behind the enqueue front.  Returns (host ms per step list, last loss)."""
+    import torch
+    pins = [torch.zeros((), dtype=torch.float32).pin_memory() for _ in range(2)]
+    host, pending, last = [], None, 0.0
+    staged = tr.stage(host_a[0], host_b[0])
+    for s in range(n):
+        t0 = time.perf_counter()
+        loss = tr.step(staged)
+        buf = pins[s & 1]
+        buf.copy_(loss, non_blocking=True)
+        done = torch.cuda.Event()
+        done.record()
+        if s + 1 < n:
+            staged = tr.stage(host_a[(s + 1) % len(host_a)], host_b[(s + 1) % len(host_b)])
+        if pending is not None:
+            pending[1].synchronize()
+            last = float(pending[0])
+        pending = (buf, done)
+        if s + 1 == n:
+            done.synchronize()
+            last = float(buf)
+        host.append((time.perf_counter() - t0) * 1e3)
+    return host, last
+
+
 def gpu_reference_supernet(spec, cfg_warm, cfg_timed, dev_imgs, dev_tgts, B):
     """The reference's own Vision_TransformerSuper (unmodified files, stock PyTorch ops) training on the SAME
     GPU, batch and subnet stream: fp16 autocast + loss scaling (supernet_engine.py:65-84) + fused AdamW."""
@@ -293,18 +321,17 @@ def bench_deit(args):
         host = []
         e0.record()
         last = 0.0
-        for s in range(n):
-            t0 = time.perf_counter()
-            if from_host:
-                loss = tr.step(host_imgs[s % n_host], host_tgts[s % n_host])       # pinned host -> device inside the step
-                pin_loss.copy_(loss, non_blocking=True)
-                torch.cuda.current_stream().synchronize() if s + 1 == n else None
-            else:
-                loss = tr.step(dev_imgs[s % n_host], dev_tgts[s % n_host])
-            host.append((time.perf_counter() - t0) * 1e3)
+        last = 0.0
+        if from_host:
+            host, last = _e2e_steps(tr, host_imgs, host_tgts, n)
+        else:
+            for s in range(n):
+                t0 = time.perf_counter()
+                tr.step(dev_imgs[s % n_host], dev_tgts[s % n_host])
+                host.append((time.perf_counter() - t0) * 1e3)
         e1.record()
         torch.cuda.synchronize()
-        return e0.elapsed_time(e1), _lib.LAUNCHES[0] - l0, host, float(pin_loss)
+        return e0.elapsed_time(e1), _lib.LAUNCHES[0] - l0, host, last
 
     timed(W, False)
     sampler = ClockSampler(0)
@@ -497,23 +524,20 @@ def bench_clip(args):
         l0 = _lib.LAUNCHES[0]
         host = []
         e0.record()
-        for s in range(n):
-            t0 = time.perf_counter()
-            i = s % n_host
-            if from_host:
-                loss = tr.step(host_imgs[i].to(dev, non_blocking=True), host_txts[i].to(dev, non_blocking=True))
-                pin_loss.copy_(loss, non_blocking=True)
-                if s + 1 == n:
-                    torch.cuda.current_stream().synchronize()
-            else:
-                loss = tr.step(dev_imgs[i], dev_txts[i])
-            host.append((time.perf_counter() - t0) * 1e3)
+        last = 0.0
+        if from_host:
+            host, last = _e2e_steps(tr, host_imgs, host_txts, n)
+        else:
+            for s in range(n):
+                t0 = time.perf_counter()
+                tr.step(dev_imgs[s % n_host], dev_txts[s % n_host])
+                host.append((time.perf_counter() - t0) * 1e3)
         e1.record()
         barrier()
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return float(ms), _lib.LAUNCHES[0] - l0, host, float(pin_loss)
+        return float(ms), _lib.LAUNCHES[0] - l0, host, last
 
     timed(W, False)
     sampler = ClockSampler(local) if rank == 0 else None

@@ -57,6 +57,7 @@ class AttnDesc(C.Structure):
         ("ddense", c_void_p),
         ("gp_grid", c_int), ("gp_w", c_int), ("gp_skip_id", c_int),
         ("gp_lut_a", C.c_uint8 * 32), ("gp_lut_b", C.c_uint8 * 32),
+        ("causal", c_int),
     ]
 
 
@@ -139,6 +140,9 @@ SIGNATURES = {
                                     c_void_p, c_void_p, c_i64, c_int, c_void_p]),
     "cream_layernorm_bwd": (c_int, [c_void_p, c_i64, c_int, c_void_p, c_i64, c_void_p, c_void_p, c_void_p,
                                     c_void_p, c_i64, c_void_p, c_i64, c_void_p, c_void_p, c_i64, c_int, c_void_p]),
+    "cream_layernorm_bwd_cast": (c_int, [c_void_p, c_i64, c_int, c_void_p, c_i64, c_void_p, c_void_p, c_void_p,
+                                         c_void_p, c_i64, c_void_p, c_i64, c_void_p, c_void_p, c_i64, c_int,
+                                         c_void_p, c_i64, c_void_p, c_int, c_void_p, c_void_p]),
     "cream_patch_im2col": (c_int, [c_void_p, c_void_p, c_i64, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "cream_tokens_assemble_fwd": (c_int, [c_void_p, c_i64, c_void_p, c_void_p, c_i64, c_void_p, c_i64, c_int,
                                           c_int, c_int, c_void_p]),

@@ -10,7 +10,7 @@ text_projection, causal mask), `CLIP` (model.py:874-1001,1073-1112: `_image_enco
 
 Each tower is ONE autograd node: its forward and backward are sequences of cream_b200 launches
 (im2col + GEMM for the 32x32 stride-32 convolution, LayerNorm, QKV GEMM, the fused attention kernel
-with the causal mask as its dense logit term, projection / MLP GEMMs with fused bias, GELU and fp32
+with the text tower's causal mask computed from the token coordinates, projection / MLP GEMMs with fused bias, GELU and fp32
 residual epilogues).  The residual stream, LayerNorm statistics and weight gradients are fp32, GEMM
 operands bf16 - the arithmetic of the reference under `--precision amp`.  torch carries the token
 embedding lookup, the eot-row selection and the (B x B) contrastive logits.
@@ -47,7 +47,7 @@ def block_names(prefix: str, i: int) -> List[str]:
 # ------------------------------------------------------------------------------------------------
 # transformer blocks (model.py:286-328: x += attn(ln_1(x)); x += mlp(ln_2(x)))
 # ------------------------------------------------------------------------------------------------
-def blocks_forward(P, prefix, layers, heads, x, B, N, dense, save):
+def blocks_forward(P, prefix, layers, heads, x, B, N, causal, save):
     """x: (B*N, E) fp32 residual stream.  Returns (x_out, saved-per-block list)."""
     M, E = x.shape
     sh = ops.SHADOWS
@@ -59,7 +59,7 @@ def blocks_forward(P, prefix, layers, heads, x, B, N, dense, save):
         p = f"{prefix}resblocks.{i}."
         ln1, mu1, rs1 = ops.layernorm_fwd(x, P[p + "ln_1.weight"], P[p + "ln_1.bias"], eps, E, save_stats=save)
         qkv = ops.linear_fwd(ln1, sh.get(P[p + "attn.in_proj_weight"]), 3 * E, E, P[p + "attn.in_proj_bias"])
-        att, lse = ops.attention_fwd(qkv, B, heads, N, scale, dense=dense, need_lse=save)
+        att, lse = ops.attention_fwd(qkv, B, heads, N, scale, causal=causal, need_lse=save)
         x1 = ops.linear_fwd(att, sh.get(P[p + "attn.out_proj.weight"]), E, E, P[p + "attn.out_proj.bias"],
                             epi=EPI_F32_RESID, resid=x)
         ln2, mu2, rs2 = ops.layernorm_fwd(x1, P[p + "ln_2.weight"], P[p + "ln_2.bias"], eps, E, save_stats=save)
@@ -75,32 +75,38 @@ def blocks_forward(P, prefix, layers, heads, x, B, N, dense, save):
     return x, saved
 
 
-def blocks_backward(P, G, prefix, layers, heads, saved, g, B, N, dense):
+def blocks_backward(P, G, prefix, layers, heads, saved, g, B, N, causal):
     """g: (B*N, E) fp32 gradient of the block stack's output; returns the gradient of its input."""
     M, E = g.shape
     sh = ops.SHADOWS
     ffn = P[f"{prefix}resblocks.0.mlp.c_fc.weight"].shape[0]
     scale = HD ** -0.5
+    dy2 = None
     for i in reversed(range(layers)):
         p = f"{prefix}resblocks.{i}."
         s = saved[i]
-        dy2 = ops.cast_scale(g, dbias=G[p + "mlp.c_proj.bias"])
+        if dy2 is None:     # top block; below it the bf16 copy comes out of the LayerNorm backward of the block above
+            dy2 = ops.cast_scale(g, dbias=G[p + "mlp.c_proj.bias"])
         ops.linear_wgrad(dy2, s["act"], E, ffn, G[p + "mlp.c_proj.weight"])
         dh = ops.linear_dgrad(dy2, sh.get(P[p + "mlp.c_proj.weight"]), E, ffn, epi=EPI_BF16_DGELU, aux=s["hpre"])
         ops.bias_grad(dh, G[p + "mlp.c_fc.bias"])
         ops.linear_wgrad(dh, s["ln2"], ffn, E, G[p + "mlp.c_fc.weight"])
         dln2 = ops.linear_dgrad(dh, sh.get(P[p + "mlp.c_fc.weight"]), ffn, E)
-        g1 = ops.layernorm_bwd(dln2, s["x1"], P[p + "ln_2.weight"], s["mu2"], s["rs2"], E, G[p + "ln_2.weight"],
-                               G[p + "ln_2.bias"], resid_grad=g)
-        dy1 = ops.cast_scale(g1, dbias=G[p + "attn.out_proj.bias"])
+        g1, dy1 = ops.layernorm_bwd_cast(dln2, s["x1"], P[p + "ln_2.weight"], s["mu2"], s["rs2"], E, G[p + "ln_2.weight"],
+                                         G[p + "ln_2.bias"], resid_grad=g, dbias=G[p + "attn.out_proj.bias"])
         ops.linear_wgrad(dy1, s["att"], E, E, G[p + "attn.out_proj.weight"])
         datt = ops.linear_dgrad(dy1, sh.get(P[p + "attn.out_proj.weight"]), E, E)
-        dqkv = ops.attention_bwd(s["qkv"], s["att"], s["lse"], datt, B, heads, N, scale, dense=dense)[0]
+        dqkv = ops.attention_bwd(s["qkv"], s["att"], s["lse"], datt, B, heads, N, scale, causal=causal)[0]
         ops.bias_grad(dqkv, G[p + "attn.in_proj_bias"])
         ops.linear_wgrad(dqkv, s["ln1"], 3 * E, E, G[p + "attn.in_proj_weight"])
         dln1 = ops.linear_dgrad(dqkv, sh.get(P[p + "attn.in_proj_weight"]), 3 * E, E)
-        g = ops.layernorm_bwd(dln1, s["x"], P[p + "ln_1.weight"], s["mu1"], s["rs1"], E, G[p + "ln_1.weight"],
-                              G[p + "ln_1.bias"], resid_grad=g1)
+        if i > 0:
+            g, dy2 = ops.layernorm_bwd_cast(dln1, s["x"], P[p + "ln_1.weight"], s["mu1"], s["rs1"], E, G[p + "ln_1.weight"],
+                                            G[p + "ln_1.bias"], resid_grad=g1,
+                                            dbias=G[f"{prefix}resblocks.{i - 1}.mlp.c_proj.bias"])
+        else:
+            g = ops.layernorm_bwd(dln1, s["x"], P[p + "ln_1.weight"], s["mu1"], s["rs1"], E, G[p + "ln_1.weight"],
+                                  G[p + "ln_1.bias"], resid_grad=g1)
         saved[i] = None
     return g
 
@@ -118,6 +124,18 @@ def _project_backward(dfeat, pooled_bf16, proj, g_proj):
     width, out_dim = proj.shape
     ops.linear_wgrad(pooled_bf16, df, width, out_dim, g_proj)          # d proj = pooled^T dfeat
     return ops.linear_fwd(df, ops.SHADOWS.get(proj), width, out_dim)     # d pooled = dfeat proj^T
+
+
+def _grad_views(P: Dict[str, torch.Tensor], names) -> Dict[str, torch.Tensor]:
+    """Zeroed fp32 gradients for `names`, carved out of ONE flat buffer (one memset instead of one per parameter);
+    every view starts 16-byte aligned (the weight-gradient GEMMs reduce into them with bulk adds)."""
+    sizes = [(P[n].numel() + 3) // 4 * 4 for n in names]
+    flat = torch.zeros(sum(sizes), dtype=torch.float32, device=P[names[0]].device)
+    out, off = {}, 0
+    for n, sz in zip(names, sizes):
+        out[n] = flat[off:off + P[n].numel()].view(P[n].shape)
+        off += sz
+    return out
 
 
 class _VisionTowerFn(torch.autograd.Function):
@@ -142,7 +160,7 @@ class _VisionTowerFn(torch.autograd.Function):
         check(lib.cream_tokens_assemble_fwd(_p(tok), tok.stride(0), _p(P["class_embedding"]), _p(P["positional_embedding"]),
                                             E, _p(x0), x0.stride(0), B, N, E, _stream()), "cream_tokens_assemble_fwd")
         x, mu0, rs0 = ops.layernorm_fwd(x0, P["ln_pre.weight"], P["ln_pre.bias"], 1e-5, E, out_f32=True, save_stats=save)
-        x, blocks = blocks_forward(P, "transformer.", layers, heads, x, B, N, None, save)
+        x, blocks = blocks_forward(P, "transformer.", layers, heads, x, B, N, False, save)
         cls_rows = x.view(B, N, E)[:, 0]                                  # (B, E) view, pitch N*E
         pooled, mu_p, rs_p = ops.layernorm_fwd(cls_rows, P["ln_post.weight"], P["ln_post.bias"], 1e-5, E, save_stats=save)
         feat = _project(pooled, P["proj"], spec["out"])
@@ -156,7 +174,7 @@ class _VisionTowerFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dfeat):
         P = dict(zip(ctx.names, ctx.saved_tensors))
-        G = {n: torch.zeros_like(P[n], dtype=torch.float32) for n in ctx.names}
+        G = _grad_views(P, ctx.names)
         lib = _lib.load()
         spec, B, s = ctx.spec, ctx.B, ctx.saved
         E, N, heads, layers, patch = spec["width"], spec["tokens"], spec["heads"], spec["layers"], spec["patch"]
@@ -167,7 +185,7 @@ class _VisionTowerFn(torch.autograd.Function):
                                  G["ln_post.bias"])
         g = ops.empty_f32(B * N, E, dev, zero=True)
         g.view(B, N, E)[:, 0].copy_(dcls)
-        g = blocks_backward(P, G, "transformer.", layers, heads, s["blocks"], g, B, N, None)
+        g = blocks_backward(P, G, "transformer.", layers, heads, s["blocks"], g, B, N, False)
         g0 = ops.layernorm_bwd(g, s["x0"], P["ln_pre.weight"], s["mu0"], s["rs0"], E, G["ln_pre.weight"], G["ln_pre.bias"])
         dtok = ops.empty_bf16(B * (N - 1), E, dev)
         check(lib.cream_tokens_assemble_bwd(_p(g0), g0.stride(0), _p(dtok), dtok.stride(0), _p(G["positional_embedding"]), E,
@@ -190,7 +208,7 @@ class _TextTowerFn(torch.autograd.Function):
         save = any(ctx.needs_input_grad)
         x = ops.empty_f32(B * N, E, dev)
         x.view(B, N, E).copy_(P["token_embedding.weight"][text] + P["positional_embedding"][:N])
-        x, blocks = blocks_forward(P, "transformer.", layers, heads, x, B, N, spec["mask"][:, :, :N, :N].contiguous(), save)
+        x, blocks = blocks_forward(P, "transformer.", layers, heads, x, B, N, True, save)   # causal mask, model.py:756-762
         eot = text.argmax(dim=-1)                                          # the eot token has the largest id
         rows = torch.arange(B, device=dev) * N + eot
         x_eot = ops.empty_f32(B, E, dev)
@@ -206,7 +224,7 @@ class _TextTowerFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dfeat):
         P = dict(zip(ctx.names, ctx.saved_tensors))
-        G = {n: torch.zeros_like(P[n], dtype=torch.float32) for n in ctx.names}
+        G = _grad_views(P, ctx.names)
         spec, s = ctx.spec, ctx.saved
         text = s["text"]
         B, N = text.shape
@@ -217,8 +235,7 @@ class _TextTowerFn(torch.autograd.Function):
                                  G["ln_final.bias"])
         g = ops.empty_f32(B * N, E, dev, zero=True)
         g[s["rows"]] = deot
-        g = blocks_backward(P, G, "transformer.", layers, heads, s["blocks"], g, B, N,
-                            spec["mask"][:, :, :N, :N].contiguous())
+        g = blocks_backward(P, G, "transformer.", layers, heads, s["blocks"], g, B, N, True)
         g3 = g.view(B, N, E)
         G["positional_embedding"][:N] = g3.sum(0)
         G["token_embedding.weight"].index_add_(0, text.reshape(-1), g)
@@ -348,8 +365,7 @@ class TextEncoder(nn.Module):
             raise RuntimeError("cream_b200 modules run on CUDA (sm_100a) tensors only")
         t = self.transformer
         L = self.context_length
-        spec = dict(width=t.width, heads=t.num_heads, layers=t.layers, out=self.text_projection.shape[1],
-                    mask=self.attn_mask.to(device=text.device, dtype=torch.float32).reshape(1, 1, L, L))
+        spec = dict(width=t.width, heads=t.num_heads, layers=t.layers, out=self.text_projection.shape[1])
         names = _tower_names(self)
         P = dict(self.named_parameters())
         f = _TextTowerFn.apply(spec, names, text, *[P[n] for n in names])
@@ -467,6 +483,15 @@ class ClipLoss(nn.Module):
         return (F.cross_entropy(logits_per_image, labels) + F.cross_entropy(logits_per_text, labels)) / 2
 
 
+def average_gradients(grads, world: int) -> None:
+    """One all-reduce over the concatenation of `grads`, averaged over the ranks, written back in place (what DDP's
+    bucketed reducer does for the reference, TinyCLIP/src/training/main.py)."""
+    flat = torch.cat([g.reshape(-1) for g in grads])
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+    flat.div_(world)
+    torch._foreach_copy_(grads, [piece.view_as(g) for piece, g in zip(flat.split([g.numel() for g in grads]), grads)])
+
+
 class ClipTrainer:
     """One contrastive training step (TinyCLIP/src/training/train.py train_one_epoch, the plain CLIP
     branch): forward both towers, ClipLoss over the gathered features, backward, gradient average over
@@ -491,17 +516,28 @@ class ClipTrainer:
         self.loss = ClipLoss(local_loss=local_loss, gather_with_grad=gather_with_grad, cache_labels=True,
                              rank=self.rank, world_size=self.world)
         self.params = [p for _, p in named]
+        self.stager = None
 
-    def step(self, images, texts):
+    def stage(self, images, texts):
+        """Start the host -> device copy of the next batch on the side stream (staging.BatchStager)."""
+        if self.stager is None:
+            from .staging import BatchStager
+            self.stager = BatchStager(self.params[0].device)
+        return self.stager.stage(images, texts)
+
+    def step(self, images, texts=None):
+        """images: a batch tensor with `texts`, or the handle `stage` returned."""
+        staged = images if texts is None else None
+        if staged is not None:
+            images, texts = staged.acquire()
         self.opt.zero_grad(set_to_none=True)
         fi, ft, scale = self.model(images, texts)
         loss = self.loss(fi, ft, scale)
         loss.backward()
+        if staged is not None:
+            staged.release()            # the text tower's backward reads the token ids once more
         if self.world > 1:
-            grads = [p.grad for p in self.params if p.grad is not None]
-            flat = torch.cat([g.reshape(-1) for g in grads])
-            dist.all_reduce(flat, op=dist.ReduceOp.AVG)
-            torch._foreach_copy_(grads, list(flat.split([g.numel() for g in grads])))
+            average_gradients([p.grad for p in self.params if p.grad is not None], self.world)
         self.opt.step()
         ops.SHADOWS.invalidate()        # the fused optimiser writes parameters without a version bump
         with torch.no_grad():

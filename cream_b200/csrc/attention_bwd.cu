@@ -34,6 +34,7 @@ constexpr int kStride = 66;  // floats per row of the staged R / dPB / dR tiles 
 
 struct BwdRowsParams {
   int B, H, N, Npad, ldw;
+  int causal;                          // generic path: key j > query i masked
   float scale;
   int ctx_k, ctx_v, shared_tables;
   int af_grid, af_max_rel;
@@ -111,7 +112,7 @@ __device__ __forceinline__ void bwd_row_generic(const BwdRowsParams& p, const Ro
       if (use_bias) t += lds_f32(x.s_bias + 4 * a_id);
       if (x.drow != nullptr && c * 16 + k < p.N) t += __ldg(x.drow + c * 16 + k);
       float pr = fast_exp2(fmaf(t, kLog2e, -x.lsel));
-      if (c * 16 + k >= p.N || x.row >= p.N) pr = 0.f;
+      if (c * 16 + k >= p.N || x.row >= p.N || (p.causal && c * 16 + k > x.row)) pr = 0.f;
       float dp = __uint_as_float(rp[k]);
       if (p.ctx_v) {
         if (iva) dp += lds_f32(x.s_dpb + 4 * va_id);
@@ -506,15 +507,17 @@ __device__ __forceinline__ void bwd_row_plain(const BwdRowsParams& p, const RowC
 
 __global__ void __launch_bounds__(kRowsThreads, 1)
 attn_bwd_rows_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_kv,
-                     const __grid_constant__ CUtensorMap map_do, const __grid_constant__ CUtensorMap map_tk,
-                     const __grid_constant__ CUtensorMap map_tv, const BwdRowsParams p) {
+                     const __grid_constant__ CUtensorMap map_do, const __grid_constant__ CUtensorMap map_o,
+                     const __grid_constant__ CUtensorMap map_tk, const __grid_constant__ CUtensorMap map_tv,
+                     const BwdRowsParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   require_smem_alignment(smem);
   const int kv_bytes = p.Npad * 128;
   const int v_slot = max(kv_bytes, 26 * 1024);
   uint8_t* sQ = smem;                       // 16 KB
   uint8_t* sdO = sQ + 16384;                // 16 KB
-  uint8_t* sK = sdO + 16384;                // [K ; TK] contiguous rows
+  uint8_t* sO = sdO + 16384;                // 16 KB: forward output rows, only for delta_i = dO_i . O_i
+  uint8_t* sK = sO + 16384;                 // [K ; TK] contiguous rows
   uint8_t* sTK = sK + kv_bytes;
   uint8_t* sV = sTK + 8192;                 // [V ; TV]
   uint8_t* sTV = sV + v_slot;
@@ -546,6 +549,7 @@ attn_bwd_rows_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
     prefetch_tmap(&map_q);
     prefetch_tmap(&map_kv);
     prefetch_tmap(&map_do);
+    prefetch_tmap(&map_o);
     mbar_init(bar_ld, 1);
     mbar_init(bar_r, 1);
     mbar_init(bar_rfree, kRowThreads);
@@ -575,9 +579,10 @@ attn_bwd_rows_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
   if (warp == 0) {
     if (lane == 0) {
       const int qcol = head * kD, kcol = (p.H + head) * kD, vcol = (2 * p.H + head) * kD;
-      mbar_arrive_expect_tx(bar_ld, 2 * 16384 + 2 * kv_bytes + (p.ctx_k ? 8192 : 0) + (p.ctx_v ? 8192 : 0));
+      mbar_arrive_expect_tx(bar_ld, 3 * 16384 + 2 * kv_bytes + (p.ctx_k ? 8192 : 0) + (p.ctx_v ? 8192 : 0));
       tma_load_3d(sQ, &map_q, bar_ld, qcol, m0, b);
       tma_load_3d(sdO, &map_do, bar_ld, qcol, m0, b);
+      tma_load_3d(sO, &map_o, bar_ld, qcol, m0, b);
       tma_load_3d(sK, &map_kv, bar_ld, kcol, 0, b);
       tma_load_3d(sV, &map_kv, bar_ld, vcol, 0, b);
       if (p.ctx_k) tma_load_3d(sTK, &map_tk, bar_ld, 0, 0, tab);
@@ -680,21 +685,24 @@ attn_bwd_rows_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
 
     const int tslot = threadIdx.x == 32 ? 8 : (threadIdx.x == 160 ? 24 : -1);
 #define RT(k) do { if (tslot >= 0) ROWS_TRACE(tslot + (k)); } while (0)
-    // delta_i = dO_i . O_i and lse_i straight from global (256 B per row), requested FIRST: the
-    // row-strided loads take ~5k cycles and complete under the operand loads / first MMAs
+    // delta_i = dO_i . O_i from the TMA-staged tiles (same SWIZZLE_128B layout: 16-byte chunk c of row r sits at
+    // chunk c ^ (r & 7)).  Reading the 2 x 128 bytes of a row straight from global - one row per lane - costs 32
+    // L1 tag cycles per warp instruction and used to hold the row threads back for ~5 us per tile.
     float delta = 0.f, lse = 0.f;
-    if (row < p.N) {
-      const uint4* o4 = reinterpret_cast<const uint4*>(p.out + (static_cast<int64_t>(b) * p.N + row) * p.ldo + head * kD);
-      const uint4* g4 = reinterpret_cast<const uint4*>(p.dout + (static_cast<int64_t>(b) * p.N + row) * p.lddo + head * kD);
+    if (row < p.N) lse = p.lse[(static_cast<int64_t>(b) * p.H + head) * p.N + row];
+    mbar_wait(bar_ld, 0);
+    {
+      const uint32_t o_row = smem_u32(sO) + r_local * 128, g_row = smem_u32(sdO) + r_local * 128;
 #pragma unroll
       for (int q = 0; q < 8; ++q) {
-        const uint4 a = __ldg(o4 + q), g = __ldg(g4 + q);
+        const uint32_t off = static_cast<uint32_t>((q ^ (r_local & 7)) << 4);
+        const uint4 a = lds_u32x4(o_row + off), g = lds_u32x4(g_row + off);
         const float2 a0 = unpack_bf16x2(a.x), a1 = unpack_bf16x2(a.y), a2 = unpack_bf16x2(a.z), a3 = unpack_bf16x2(a.w);
         const float2 g0 = unpack_bf16x2(g.x), g1 = unpack_bf16x2(g.y), g2 = unpack_bf16x2(g.z), g3 = unpack_bf16x2(g.w);
         delta += a0.x * g0.x + a0.y * g0.y + a1.x * g1.x + a1.y * g1.y + a2.x * g2.x + a2.y * g2.y +
                  a3.x * g3.x + a3.y * g3.y;
       }
-      lse = p.lse[(static_cast<int64_t>(b) * p.H + head) * p.N + row];
+      if (row >= p.N) delta = 0.f;           // rows past N are zero-filled by TMA; keep them exactly inert
     }
     RT(0);
     if (any_r) {
@@ -1099,6 +1107,8 @@ extern "C" int cream_attn_bwd(const cream_attn_desc* d, void* stream_) {
   p.ws_p = ws_p; p.ws_dt = ws_dt;
   p.dbias = d->dbias_pack;
   p.dense = d->dense_bias; p.dense_sb = d->dense_stride_b; p.dense_sh = d->dense_stride_h; p.dense_si = d->dense_stride_i;
+  p.causal = d->causal;
+  CB_REQUIRE(!d->causal || (d->af_grid == 0 && d->gp_grid == 0), "the causal mask runs on the generic gather path (no af / gp hint)");
   p.ddense = d->ddense;
   if (p.dense != nullptr || p.ddense != nullptr) p.af_grid = 0;   // generic gather path only
   if (p.af_grid != 0) {
@@ -1129,6 +1139,8 @@ extern "C" int cream_attn_bwd(const cream_attn_desc* d, void* stream_) {
   const uint64_t dstrides[3] = {1, static_cast<uint64_t>(d->ld_dout), static_cast<uint64_t>(d->N) * d->ld_dout};
   const CUtensorMap* mdo = get_tensor_map(d->dout, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, ddims, dstrides, box_q, CU_TENSOR_MAP_SWIZZLE_128B);
   const CUtensorMap* mdo64 = get_tensor_map(d->dout, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, ddims, dstrides, box_64, CU_TENSOR_MAP_SWIZZLE_128B);
+  const uint64_t ostrides[3] = {1, static_cast<uint64_t>(d->ld_out), static_cast<uint64_t>(d->N) * d->ld_out};
+  const CUtensorMap* mo = get_tensor_map(d->out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, ddims, ostrides, box_q, CU_TENSOR_MAP_SWIZZLE_128B);
   const int ntab = d->tables_per_head ? d->H : 1;
   const uint64_t tdims[3] = {64, 64, static_cast<uint64_t>(ntab)};
   const uint64_t tstrides[3] = {1, 64, 64 * 64};
@@ -1138,7 +1150,7 @@ extern "C" int cream_attn_bwd(const cream_attn_desc* d, void* stream_) {
   const uint64_t wstrides[3] = {1, static_cast<uint64_t>(ldw), static_cast<uint64_t>(d->N) * ldw};
   const CUtensorMap* mwp = get_tensor_map(ws_p, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, wdims, wstrides, box_64, CU_TENSOR_MAP_SWIZZLE_128B);
   const CUtensorMap* mwd = get_tensor_map(ws_dt, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, wdims, wstrides, box_64, CU_TENSOR_MAP_SWIZZLE_128B);
-  if (!mq || !mkv || !mq64 || !mdo || !mdo64 || !mtk || !mtv || !mwp || !mwd) return CREAM_ERR_CUDA;
+  if (!mq || !mkv || !mq64 || !mdo || !mdo64 || !mo || !mtk || !mtv || !mwp || !mwd) return CREAM_ERR_CUDA;
 
   static bool attr_set = false;
   if (!attr_set) {
@@ -1146,7 +1158,7 @@ extern "C" int cream_attn_bwd(const cream_attn_desc* d, void* stream_) {
     CB_CUDA_OK(cudaFuncSetAttribute(attn_bwd_cols_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
-  const size_t smem_rows = 2 * 16384 + static_cast<size_t>(Npad) * 128 + 8192 +
+  const size_t smem_rows = 3 * 16384 + static_cast<size_t>(Npad) * 128 + 8192 +
                            std::max<size_t>(Npad * 128, 26 * 1024) + 8192 + 2 * 128 * kStride * 4 + 4 * kIndChunk + 2 * 64 * 4 + 64 + 128;
   CB_REQUIRE(smem_rows <= 227 * 1024, "shared memory budget");
   dim3 grid(ceil_div(d->N, 128), d->H, d->B);
@@ -1158,7 +1170,7 @@ extern "C" int cream_attn_bwd(const cream_attn_desc* d, void* stream_) {
     p.trace = trace_dev;
   }
 #endif
-  attn_bwd_rows_kernel<<<grid, kRowsThreads, smem_rows, stream>>>(*mq, *mkv, *mdo, *mtk, *mtv, p);
+  attn_bwd_rows_kernel<<<grid, kRowsThreads, smem_rows, stream>>>(*mq, *mkv, *mdo, *mo, *mtk, *mtv, p);
   int rc = check_last("attn_bwd_rows_kernel");
   if (rc) return rc;
 #ifdef CREAM_TRACE

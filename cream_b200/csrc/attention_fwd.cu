@@ -48,6 +48,7 @@ struct AttnFwdParams {
   int ldi;
   const float* bias;                   // (H or 1, 64) pre-packed bias table, gathered by idx_a
   const float* dense; int64_t dense_sb, dense_sh, dense_si;   // dense additive logit term (generic path)
+  int causal;                          // generic path: key j > query i masked
   __nv_bfloat16* out; int64_t ldo;     // (B*N, H*64)
   float* lse;                          // (B, H, N)
 };
@@ -85,7 +86,7 @@ __device__ __forceinline__ void softmax_generic(const AttnFwdParams& p, uint32_t
       }
       if (use_bias) t += lds_f32(sbias + 4 * a_id);
       if (drow != nullptr && c * 16 + k < p.N) t += __ldg(drow + c * 16 + k);
-      if (c * 16 + k >= p.N) t = -INFINITY;
+      if (c * 16 + k >= p.N || (p.causal && c * 16 + k > row_c)) t = -INFINITY;
       mx = fmaxf(mx, t);
       raw[k] = __float_as_uint(t);
     }
@@ -697,6 +698,8 @@ extern "C" int cream_attn_fwd(const cream_attn_desc* d, void* stream_) {
   p.out = static_cast<__nv_bfloat16*>(d->out); p.ldo = d->ld_out;
   p.lse = d->lse;
   p.dense = d->dense_bias; p.dense_sb = d->dense_stride_b; p.dense_sh = d->dense_stride_h; p.dense_si = d->dense_stride_i;
+  p.causal = d->causal;
+  CB_REQUIRE(!d->causal || (d->af_grid == 0 && d->gp_grid == 0), "the causal mask runs on the generic gather path (no af / gp hint)");
   // structured AutoFormer gather: square grid + cls, both tables, clamp never binding
   if (d->af_grid > 0 && d->dense_bias == nullptr) {
     CB_REQUIRE(d->af_grid * d->af_grid + 1 == d->N && ctx_k && ctx_v && !d->bias_pack, "af mode needs N = g*g+1 and both table packs");

@@ -7,6 +7,7 @@
 //   grad cast/scale     DropPath backward + fp32->bf16 (model/utils.py:71-99)
 //   bias gradient       column sums of dY
 //   RPE table packing   multihead_super.py:32-35 / irpe.py:483-496 tables -> 64x64 bf16 packs
+#include <cstdlib>
 #include "common.cuh"
 
 namespace cb {
@@ -114,6 +115,7 @@ pool_bwd_kernel(const __nv_bfloat16* __restrict__ dp, int64_t lddp, float* __res
 // out_bf16[r,c] = bf16(scale[r / rows_per] * in[r,c]); optional fused bias gradient
 // dbias[c] += sum_r out[r,c].  Block = 32 column threads (x4 columns) x 8 row lanes; the row lanes
 // are reduced through shared memory so that only gridDim.y atomics hit each dbias address.
+template <int U>
 __global__ void __launch_bounds__(256)
 cast_scale_kernel(const float* __restrict__ in, int64_t ldi, __nv_bfloat16* __restrict__ out, int64_t ldo,
                   const float* __restrict__ scale, int rows_per, float* __restrict__ dbias, int64_t rows,
@@ -124,11 +126,11 @@ cast_scale_kernel(const float* __restrict__ in, int64_t ldi, __nv_bfloat16* __re
   float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
   const int64_t stride = static_cast<int64_t>(gridDim.y) * 8;
   if (live) {
-    for (int64_t r0 = static_cast<int64_t>(blockIdx.y) * 8 + threadIdx.y; r0 < rows; r0 += 2 * stride) {
-      float4 v[2];
-      float s[2];
+    for (int64_t r0 = static_cast<int64_t>(blockIdx.y) * 8 + threadIdx.y; r0 < rows; r0 += U * stride) {
+      float4 v[U];
+      float s[U];
 #pragma unroll
-      for (int u = 0; u < 2; ++u) {
+      for (int u = 0; u < U; ++u) {
         const int64_t r = r0 + u * stride;
         if (r < rows) {
           v[u] = __ldg(reinterpret_cast<const float4*>(in + r * ldi + c));
@@ -136,7 +138,7 @@ cast_scale_kernel(const float* __restrict__ in, int64_t ldi, __nv_bfloat16* __re
         }
       }
 #pragma unroll
-      for (int u = 0; u < 2; ++u) {
+      for (int u = 0; u < U; ++u) {
         const int64_t r = r0 + u * stride;
         if (r < rows) {
           const __nv_bfloat162 lo = __floats2bfloat162_rn(s[u] * v[u].x, s[u] * v[u].y);
@@ -170,9 +172,11 @@ cast_scale_kernel(const float* __restrict__ in, int64_t ldi, __nv_bfloat16* __re
 }
 
 // dbias[c] += sum_r dy[r,c]  (bf16 input).  Block = 32 column threads (x8 columns) x 8 row lanes.
+template <int kU>
 __global__ void __launch_bounds__(256)
 colsum_kernel(const __nv_bfloat16* __restrict__ dy, int64_t ld, float* __restrict__ dbias, int64_t rows,
               int cols) {
+  constexpr int U = kU;
   __shared__ float red[8][32][8];
   const int c = (blockIdx.x * 32 + threadIdx.x) << 3;
   const bool live = c < cols;
@@ -180,10 +184,10 @@ colsum_kernel(const __nv_bfloat16* __restrict__ dy, int64_t ld, float* __restric
   const int64_t stride = static_cast<int64_t>(gridDim.y) * 8;
   const bool vec = (c + 8 <= cols) && ((ld & 7) == 0);
   if (live) {
-    for (int64_t r0 = static_cast<int64_t>(blockIdx.y) * 8 + threadIdx.y; r0 < rows; r0 += 2 * stride) {
-      uint4 v[2];
+    for (int64_t r0 = static_cast<int64_t>(blockIdx.y) * 8 + threadIdx.y; r0 < rows; r0 += U * stride) {
+      uint4 v[U];
 #pragma unroll
-      for (int u = 0; u < 2; ++u) {
+      for (int u = 0; u < U; ++u) {
         const int64_t r = r0 + u * stride;
         v[u] = make_uint4(0, 0, 0, 0);
         if (r < rows) {
@@ -196,7 +200,7 @@ colsum_kernel(const __nv_bfloat16* __restrict__ dy, int64_t ld, float* __restric
         }
       }
 #pragma unroll
-      for (int u = 0; u < 2; ++u) {
+      for (int u = 0; u < U; ++u) {
         const float2 f0 = unpack_bf16x2(v[u].x), f1 = unpack_bf16x2(v[u].y), f2 = unpack_bf16x2(v[u].z), f3 = unpack_bf16x2(v[u].w);
         acc[0] += f0.x; acc[1] += f0.y; acc[2] += f1.x; acc[3] += f1.y;
         acc[4] += f2.x; acc[5] += f2.y; acc[6] += f3.x; acc[7] += f3.y;
@@ -351,16 +355,17 @@ extern "C" int cream_pool_bwd(const void* dpooled_bf16, int64_t lddp, float* dy,
   return check_last("pool_bwd_kernel");
 }
 
+
 extern "C" int cream_cast_scale(const float* in, int64_t ldi, void* out_bf16, int64_t ldo,
                                 const float* row_scale, int rows_per_scale, float* dbias, int64_t rows,
                                 int cols, void* stream) {
   if (rows == 0 || cols == 0) return CREAM_OK;
   CB_REQUIRE(in && out_bf16, "null pointer");
   CB_REQUIRE(ldi % 4 == 0 && ldo % 4 == 0 && cols % 4 == 0, "cols and pitches must be multiples of 4");
+  // (unroll depth 2 / 4 / 8 and 2 - 8 blocks per SM were swept at the supernet shapes: within 5 % of each other)
   dim3 block(32, 8), grid(ceil_div(cols / 4, 32), static_cast<unsigned>(std::min<int64_t>(ceil_div64(rows, 16), kNumSMs * 2)));
-  cast_scale_kernel<<<grid, block, 0, static_cast<cudaStream_t>(stream)>>>(
-      in, ldi, static_cast<__nv_bfloat16*>(out_bf16), ldo, row_scale, rows_per_scale > 0 ? rows_per_scale : 1,
-      dbias, rows, cols);
+  cast_scale_kernel<2><<<grid, block, 0, static_cast<cudaStream_t>(stream)>>>(
+      in, ldi, static_cast<__nv_bfloat16*>(out_bf16), ldo, row_scale, rows_per_scale > 0 ? rows_per_scale : 1, dbias, rows, cols);
   return check_last("cast_scale_kernel");
 }
 
@@ -369,8 +374,7 @@ extern "C" int cream_bias_grad(const void* dy_bf16, int64_t ld, float* dbias, in
   if (rows == 0 || cols == 0) return CREAM_OK;
   CB_REQUIRE(dy_bf16 && dbias && ld % 2 == 0, "bad args");
   dim3 block(32, 8), grid(ceil_div(ceil_div(cols, 8), 32), static_cast<unsigned>(std::min<int64_t>(ceil_div64(rows, 16), kNumSMs * 2)));
-  colsum_kernel<<<grid, block, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const __nv_bfloat16*>(dy_bf16), ld, dbias, rows, cols);
+  colsum_kernel<2><<<grid, block, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const __nv_bfloat16*>(dy_bf16), ld, dbias, rows, cols);
   return check_last("colsum_kernel");
 }
 

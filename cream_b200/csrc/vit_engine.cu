@@ -10,6 +10,7 @@
 // (iRPE/DeiT-with-iRPE/rpe_vision_transformer.py:107-201, RPEBlock :100-104).
 #include <cstring>
 
+#include <cstdlib>
 #include "common.cuh"
 
 namespace cb {
@@ -191,6 +192,49 @@ int bias_grad(cudaStream_t s, Bf16Mat dy, int64_t rows, int cols, float* dbias) 
   return cream_bias_grad(dy.p, dy.ld, dbias, rows, cols, s);
 }
 
+// The per-layer bias gradients of fc1 and qkv are leaves: nothing downstream in the backward reads them.  Their
+// column-sum kernels (256 threads, 9 KB of shared memory) fit on an SM beside a resident GEMM CTA, and the GEMMs
+// leave most of the HBM bandwidth unused, so they run on a side stream UNDER the weight / data gradient GEMMs that
+// follow instead of in front of them.  fork: side waits for the producer on `s`; join (once per stage, before the
+// buffers are rewritten): `s` waits for the side stream.  CREAM_SIDE_BIAS=0 keeps everything on `s`.
+struct SideStream {
+  cudaStream_t st = nullptr;
+  cudaEvent_t fork = nullptr, join = nullptr;
+  bool pending = false;
+};
+thread_local SideStream t_side[16];
+
+bool side_enabled() {
+  static const bool on = []() { const char* e = getenv("CREAM_SIDE_BIAS"); return !(e != nullptr && e[0] == '0'); }();
+  return on;
+}
+
+int side_bias_grad(cudaStream_t s, Bf16Mat dy, int64_t rows, int cols, float* dbias) {
+  int dev = 0;
+  if (!side_enabled() || cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) return bias_grad(s, dy, rows, cols, dbias);
+  SideStream& ss = t_side[dev];
+  if (ss.st == nullptr) {
+    CB_CUDA_OK(cudaStreamCreateWithFlags(&ss.st, cudaStreamNonBlocking));
+    CB_CUDA_OK(cudaEventCreateWithFlags(&ss.fork, cudaEventDisableTiming));
+    CB_CUDA_OK(cudaEventCreateWithFlags(&ss.join, cudaEventDisableTiming));
+  }
+  CB_CUDA_OK(cudaEventRecord(ss.fork, s));
+  CB_CUDA_OK(cudaStreamWaitEvent(ss.st, ss.fork, 0));
+  ss.pending = true;
+  return bias_grad(ss.st, dy, rows, cols, dbias);
+}
+
+int side_join(cudaStream_t s) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) return CREAM_OK;
+  SideStream& ss = t_side[dev];
+  if (!ss.pending) return CREAM_OK;
+  CB_CUDA_OK(cudaEventRecord(ss.join, ss.st));
+  CB_CUDA_OK(cudaStreamWaitEvent(s, ss.join, 0));
+  ss.pending = false;
+  return CREAM_OK;
+}
+
 int pack_layer_tables(const cream_vit_desc& d, const Bufs& b, cudaStream_t s) {
   // K-side and V-side packs of every layer, one launch per side
   for (int side = 0; side < 2; ++side) {
@@ -331,9 +375,14 @@ extern "C" int cream_vit_bwd(const cream_vit_desc* d, int first_stage, int last_
       VIT_TRY(linear_dgrad(s, d->B, d->num_classes, E, b.dl, d->whead, d->ld_whead, CREAM_EPI_BF16, b.dpooled));
       ++t_launches;
       VIT_TRY(cream_pool_bwd(b.dpooled.p, b.dpooled.ld, b.dy.p, b.dy.ld, d->B, d->N, E, d->pool_first, d->pool_count, s));
-      ++t_launches;
-      VIT_TRY(cream_layernorm_bwd(b.dy.p, b.dy.ld, 1, b.x_last.p, b.x_last.ld, d->norm_g, b.mu_f, b.rs_f, nullptr, 0, g.p, g.ld,
-                                  d->g_norm_g, d->g_norm_b, M, E, s));
+      {   // final LayerNorm backward; it also emits the bf16 DropPath-scaled gradient + fc2 bias gradient
+          // that the last layer's FFN branch starts from
+        const cream_vit_layer& nx = d->layers[d->depth - 1];
+        ++t_launches;
+        VIT_TRY(cream_layernorm_bwd_cast(b.dy.p, b.dy.ld, 1, b.x_last.p, b.x_last.ld, d->norm_g, b.mu_f, b.rs_f, nullptr, 0, g.p,
+                                         g.ld, d->g_norm_g, d->g_norm_b, M, E, b.dy_bf.p, b.dy_bf.ld,
+                                         nx.dp_scale ? nx.dp_scale + d->B : nullptr, d->N, nx.g_bfc2, s));
+      }
       if (b.dtk_packs) { ++t_launches; CB_CUDA_OK(cudaMemsetAsync(b.dtk_packs, 0, static_cast<size_t>(d->depth) * 64 * 64 * 4, s)); }
       if (b.dtv_packs) { ++t_launches; CB_CUDA_OK(cudaMemsetAsync(b.dtv_packs, 0, static_cast<size_t>(d->depth) * 64 * 64 * 4, s)); }
       continue;
@@ -352,19 +401,17 @@ extern "C" int cream_vit_bwd(const cream_vit_desc* d, int first_stage, int last_
     const LayerBufs& l = b.L[i];
     const int h = p.heads, qd = 64 * h, ffn = p.ffn;
     // ---- FFN branch: x2 = x1 + s * fc2(gelu(fc1(ln2))) ----
-    ++t_launches;
-    VIT_TRY(cream_cast_scale(g.p, g.ld, b.dy_bf.p, b.dy_bf.ld, p.dp_scale ? p.dp_scale + d->B : nullptr, d->N, p.g_bfc2, M, E, s));
+    // (b.dy_bf = bf16(DropPath scale * g) and the fc2 bias gradient were produced by the LayerNorm
+    //  backward of the previous stage)
     VIT_TRY(linear_wgrad(s, M, E, ffn, b.dy_bf, l.act, p.g_wfc2, d->ld_gfc2));
     VIT_TRY(linear_dgrad(s, M, E, ffn, b.dy_bf, p.wfc2, d->ld_wfc2, CREAM_EPI_BF16_DGELU, b.dh, l.hpre.p, l.hpre.ld));
-    if (p.g_bfc1) VIT_TRY(bias_grad(s, b.dh, M, ffn, p.g_bfc1));
+    if (p.g_bfc1) VIT_TRY(side_bias_grad(s, b.dh, M, ffn, p.g_bfc1));
     VIT_TRY(linear_wgrad(s, M, ffn, E, b.dh, l.ln2, p.g_wfc1, d->ld_gfc1));
     VIT_TRY(linear_dgrad(s, M, ffn, E, b.dh, p.wfc1, d->ld_wfc1, CREAM_EPI_BF16, b.dln));
-    ++t_launches;
-    VIT_TRY(cream_layernorm_bwd(b.dln.p, b.dln.ld, 0, l.x1.p, l.x1.ld, p.ln2_g, l.mu2, l.rs2, g.p, g.ld, g1.p, g1.ld, p.g_ln2_g,
-                                p.g_ln2_b, M, E, s));
+    ++t_launches;   // ffn_layer_norm backward (+ residual gradient) -> g1, its bf16 DropPath-scaled copy, proj bias gradient
+    VIT_TRY(cream_layernorm_bwd_cast(b.dln.p, b.dln.ld, 0, l.x1.p, l.x1.ld, p.ln2_g, l.mu2, l.rs2, g.p, g.ld, g1.p, g1.ld,
+                                     p.g_ln2_g, p.g_ln2_b, M, E, b.dy_bf.p, b.dy_bf.ld, p.dp_scale, d->N, p.g_bproj, s));
     // ---- attention branch: x1 = x + s * proj(attn(qkv(ln1))) ----
-    ++t_launches;
-    VIT_TRY(cream_cast_scale(g1.p, g1.ld, b.dy_bf.p, b.dy_bf.ld, p.dp_scale, d->N, p.g_bproj, M, E, s));
     VIT_TRY(linear_wgrad(s, M, E, qd, b.dy_bf, l.att, p.g_wproj, d->ld_gproj));
     VIT_TRY(linear_dgrad(s, M, E, qd, b.dy_bf, p.wproj, d->ld_wproj, CREAM_EPI_BF16, b.datt));
     {
@@ -378,7 +425,7 @@ extern "C" int cream_vit_bwd(const cream_vit_desc* d, int first_stage, int last_
       t_launches += 2;
       VIT_TRY(cream_attn_bwd(&at, s));
     }
-    if (p.g_bqkv) VIT_TRY(bias_grad(s, b.dqkv, M, 3 * qd, p.g_bqkv));
+    if (p.g_bqkv) VIT_TRY(side_bias_grad(s, b.dqkv, M, 3 * qd, p.g_bqkv));
     {   // dWqkv: the reference's interleaved rows 3j+i (qkv_super.py:72-77) or plain [q;k;v] row blocks
       GemmArgs a;
       a.g.M = qd; a.g.N = E; a.g.K = static_cast<int>(M); a.g.groups = 3;
@@ -398,9 +445,17 @@ extern "C" int cream_vit_bwd(const cream_vit_desc* d, int first_stage, int last_
       a.g.epi = CREAM_EPI_BF16; a.g.out = b.dln.p; a.g.ldo = b.dln.ld;
       VIT_TRY(run_gemm(a.g, s));
     }
-    ++t_launches;
-    VIT_TRY(cream_layernorm_bwd(b.dln.p, b.dln.ld, 0, l.x.p, l.x.ld, p.ln1_g, l.mu1, l.rs1, g1.p, g1.ld, g.p, g.ld, p.g_ln1_g,
-                                p.g_ln1_b, M, E, s));
+    VIT_TRY(side_join(s));   // the side-stream column sums of this layer have read dh / dqkv
+    ++t_launches;   // attn_layer_norm backward -> g; for i > 0 also what layer i-1's FFN branch starts from
+    if (i > 0) {
+      const cream_vit_layer& nx = d->layers[i - 1];
+      VIT_TRY(cream_layernorm_bwd_cast(b.dln.p, b.dln.ld, 0, l.x.p, l.x.ld, p.ln1_g, l.mu1, l.rs1, g1.p, g1.ld, g.p, g.ld,
+                                       p.g_ln1_g, p.g_ln1_b, M, E, b.dy_bf.p, b.dy_bf.ld,
+                                       nx.dp_scale ? nx.dp_scale + d->B : nullptr, d->N, nx.g_bfc2, s));
+    } else {
+      VIT_TRY(cream_layernorm_bwd(b.dln.p, b.dln.ld, 0, l.x.p, l.x.ld, p.ln1_g, l.mu1, l.rs1, g1.p, g1.ld, g.p, g.ld, p.g_ln1_g,
+                                  p.g_ln1_b, M, E, s));
+    }
   }
   // table gradients of the layers this call covered: packed (64, 64) fp32 -> the reference's table tensors,
   // ONE launch per side for all of them (a single-block launch per layer costs ~12 us of latency each)

@@ -198,9 +198,21 @@ class DeitTrainer:
         self.optimizer = FlatAdamW(self.params, self.grads, decay, lr, weight_decay, shadows=self.native.shadows)
         self.config = _config(model)
         self.names = tuple(self.params)
+        self.stager = None
 
-    def step(self, images: torch.Tensor, targets: torch.Tensor) -> torch.Tensor:
+    def stage(self, images: torch.Tensor, targets: torch.Tensor):
+        """Start the host -> device copy of the next batch on the side stream (staging.BatchStager)."""
+        if self.stager is None:
+            from .staging import BatchStager
+            self.stager = BatchStager(self.native.device)
+        return self.stager.stage(images, targets)
+
+    def step(self, images, targets: torch.Tensor = None) -> torch.Tensor:
+        """images: a batch tensor (host or device) with `targets`, or the handle `stage` returned."""
         dev = self.native.device
+        staged = images if targets is None else None
+        if staged is not None:
+            images, targets = staged.acquire()
         images = images.to(dev, non_blocking=True).float().contiguous()
         targets = targets.to(dev, non_blocking=True)
         scales = drop_path_scales(self.model, images.shape[0], dev)
@@ -208,6 +220,8 @@ class DeitTrainer:
             self.native.bind_grads(self.grads)
         logits = self.native.forward(self.config, images, scales)
         loss, dlogits = self.native.xent(logits, targets)
+        if staged is not None:
+            staged.release()            # im2col and the loss have read the slot
         self.flat_grads.zero_()
         self.native.backward(dlogits)
         self.optimizer.step(self.names, cache_key="all")

@@ -276,6 +276,24 @@ def layernorm_bwd(dy, x, gamma, mean, rstd, E, dgamma_full, dbeta_full, resid_gr
     return dx
 
 
+def layernorm_bwd_cast(dy, x, gamma, mean, rstd, E, dgamma_full, dbeta_full, resid_grad=None, row_scale=None,
+                       rows_per_scale=1, dbias=None):
+    """layernorm_bwd that also returns bf16(row_scale * dx) and accumulates its column sums into `dbias`
+    (cream_layernorm_bwd_cast): one pass instead of layernorm_bwd + cast_scale.  Returns (dx fp32, dx bf16)."""
+    dy_f32 = dy.dtype == torch.float32
+    rows = x.shape[0]
+    dx = empty_f32(rows, E, x.device)
+    out = empty_bf16(rows, E, x.device)
+    nbytes = rows * E * ((4.0 if dy_f32 else 2.0) + 4.0 + 4.0 + 2.0 + (4.0 if resid_grad is not None else 0.0))
+    _profiled("ln_bwd", 0.0, nbytes,
+              lambda: check(_lib.load().cream_layernorm_bwd_cast(
+                  _p(dy), dy.stride(0), int(dy_f32), _p(x), x.stride(0), _p(gamma), _p(mean), _p(rstd), _p(resid_grad),
+                  resid_grad.stride(0) if resid_grad is not None else 0, _p(dx), dx.stride(0), _p(dgamma_full), _p(dbeta_full),
+                  rows, E, _p(out), out.stride(0), _p(row_scale), rows_per_scale, _p(dbias), _stream()),
+                  "cream_layernorm_bwd_cast"))
+    return dx, out
+
+
 # --------------------------------------------------------------------------------------------
 # relative-position tables
 # --------------------------------------------------------------------------------------------
@@ -419,8 +437,9 @@ def _set_dense(d, dense, B, H, N):
     d.dense_stride_i = dense.stride(2)
 
 
-def _attn_desc(B, H, N, scale, qkv, tk, tv, per_head, idx, bias, af=None, gp=None):
+def _attn_desc(B, H, N, scale, qkv, tk, tv, per_head, idx, bias, af=None, gp=None, causal=False):
     d = AttnDesc()
+    d.causal = int(bool(causal))
     if af is not None:
         d.af_grid, d.af_max_rel = af
     if gp is not None:          # (grid, W, skip_id, lut_a, lut_b) from irpe_grid_product_structure
@@ -440,13 +459,13 @@ def _attn_desc(B, H, N, scale, qkv, tk, tv, per_head, idx, bias, af=None, gp=Non
 
 
 def attention_fwd(qkv, B, H, N, scale, *, tk=None, tv=None, per_head=False, idx=(None, None, None, None),
-                  bias=None, need_lse=True, af=None, dense=None, gp=None):
+                  bias=None, need_lse=True, af=None, dense=None, gp=None, causal=False):
     """Fused attention forward.  qkv: (B*N, 3*H*64) bf16.  Returns (out (B*N, H*64) bf16, lse).
     dense: optional fp32 (B|1, H|1, N, N) term added to the logits (see cream_attn_desc.dense_bias)."""
     _check_2d(qkv, torch.bfloat16, "qkv", 8)
     out = empty_bf16(B * N, H * HEAD_DIM, qkv.device)
     lse = torch.empty((B, H, N), dtype=torch.float32, device=qkv.device) if need_lse else None
-    d = _attn_desc(B, H, N, scale, qkv, tk, tv, per_head, idx, bias, af, gp)
+    d = _attn_desc(B, H, N, scale, qkv, tk, tv, per_head, idx, bias, af, gp, causal)
     _set_dense(d, dense, B, H, N)
     d.out, d.ld_out, d.lse = _p(out), out.stride(0), _p(lse)
     nb = (NB_PACK if tk is not None else 0) + (NB_PACK if tv is not None else 0)
@@ -456,7 +475,8 @@ def attention_fwd(qkv, B, H, N, scale, *, tk=None, tv=None, per_head=False, idx=
 
 
 def attention_bwd(qkv, out, lse, dout, B, H, N, scale, *, tk=None, tv=None, per_head=False,
-                  idx=(None, None, None, None), bias=None, af=None, dtk=None, dtv=None, dense=None, ddense=None, gp=None):
+                  idx=(None, None, None, None), bias=None, af=None, dtk=None, dtv=None, dense=None, ddense=None, gp=None,
+                  causal=False):
     """Returns (dqkv bf16, dtk_pack fp32|None, dtv_pack fp32|None, dbias fp32|None).  dtk / dtv may
     be caller-provided zeroed (T, 64, 64) fp32 accumulators.  With `dense`, pass `ddense` = an fp32
     (B, H, N, N) tensor to receive the logit gradient dS."""
@@ -471,7 +491,7 @@ def attention_bwd(qkv, out, lse, dout, B, H, N, scale, *, tk=None, tv=None, per_
     dbias = torch.zeros((T, NB_PACK), dtype=torch.float32, device=dev) if bias is not None else None
     nbytes = _lib.load().cream_attn_bwd_workspace_bytes(B, H, N)
     ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
-    d = _attn_desc(B, H, N, scale, qkv, tk, tv, per_head, idx, bias, af, gp)
+    d = _attn_desc(B, H, N, scale, qkv, tk, tv, per_head, idx, bias, af, gp, causal)
     d.out, d.ld_out, d.lse = _p(out), out.stride(0), _p(lse)
     d.dout, d.ld_dout = _p(dout), dout.stride(0)
     d.dqkv, d.ld_dqkv = _p(dqkv), dqkv.stride(0)

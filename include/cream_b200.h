@@ -194,6 +194,10 @@ typedef struct cream_attn_desc {
    * idx_a must still be the matching table (it is what the caller verified the structure against). */
   int gp_grid, gp_w, gp_skip_id;
   uint8_t gp_lut_a[32], gp_lut_b[32];
+  /* 1: key j > query i is masked out (logit -inf) - the text tower's causal mask of
+   * open_clip/model.py:756-762 computed from the coordinates instead of read from a dense (N, N) term.
+   * Generic gather path only (no af / gp hint). */
+  int causal;
 } cream_attn_desc;
 
 int cream_attn_fwd(const cream_attn_desc* desc, void* stream);
@@ -213,6 +217,17 @@ int cream_layernorm_bwd(const void* dy, int64_t lddy, int dy_f32, const float* x
                         const float* gamma, const float* mean, const float* rstd,
                         const float* resid_grad, int64_t ldrg, float* dx, int64_t lddx, float* dgamma,
                         float* dbeta, int64_t rows, int E, void* stream);
+/* cream_layernorm_bwd that ALSO emits what the next two GEMMs of the backward consume - out_bf16 =
+ * bf16(row_scale[r / rows_per_scale] * dx) (the DropPath factor of the branch the gradient enters,
+ * model/utils.py:71-99; NULL = 1) - and that branch's bias gradient dbias[c] += sum_r out_bf16[r, c]
+ * (NULL = skip): the separate cream_cast_scale pass over dx disappears.  Same result as
+ * cream_layernorm_bwd followed by cream_cast_scale (which is what runs for shapes the pipelined
+ * kernel does not take). */
+int cream_layernorm_bwd_cast(const void* dy, int64_t lddy, int dy_f32, const float* x, int64_t ldx,
+                             const float* gamma, const float* mean, const float* rstd,
+                             const float* resid_grad, int64_t ldrg, float* dx, int64_t lddx, float* dgamma,
+                             float* dbeta, int64_t rows, int E, void* out_bf16, int64_t ldo,
+                             const float* row_scale, int rows_per_scale, float* dbias, void* stream);
 
 /* ------------------------------------------------------------------------- *
  * Patch embedding / token assembly / pooling glue.

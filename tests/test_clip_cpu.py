@@ -115,6 +115,13 @@ def _worker(rank, world, port, ret):
                     assert torch.allclose(fi.grad / world, a.grad[sl], atol=1e-12), (local_loss, "image grad")
                     assert torch.allclose(ft.grad / world, b.grad[sl], atol=1e-12), (local_loss, "text grad")
                 out[(local_loss, with_grad)] = float(loss)
+        # the trainer's gradient exchange: one flat all-reduce, averaged, written back with the original shapes
+        shapes = [(3, 5), (7,), (2, 2, 2), ()]
+        grads = [torch.full(sh, float(rank + 1) * (i + 1), dtype=torch.float64) for i, sh in enumerate(shapes)]
+        clip.average_gradients(grads, world)
+        mean_rank = sum(range(1, world + 1)) / world
+        for i, (gr, sh) in enumerate(zip(grads, shapes)):
+            assert gr.shape == torch.Size(sh) and torch.allclose(gr, torch.full(sh, mean_rank * (i + 1), dtype=torch.float64))
         ret[rank] = "ok"
     finally:
         dist.destroy_process_group()

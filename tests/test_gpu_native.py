@@ -249,6 +249,35 @@ def test_deit_trainer_step_runs_and_learns():
     assert all(np.isfinite(losses)) and losses[-1] < losses[0], losses
 
 
+def test_staged_host_batches_give_the_same_steps_as_resident_ones():
+    """BatchStager: batches copied from pinned host memory on the side stream, two slots reused over 5 steps,
+    must produce the same losses as the same batches resident on the device (DropPath off; the split-K weight
+    gradients reduce in a run-dependent order, hence a 2e-4 band instead of bit equality)."""
+    from cream_b200.deit import DeitIrpe, DeitTrainer
+    g = torch.Generator().manual_seed(3)
+    host = [(torch.randn(4, 3, 224, 224, generator=g).pin_memory(), torch.randint(0, 1000, (4,), generator=g).pin_memory())
+            for _ in range(3)]
+    losses = []
+    for staged in (False, True):
+        torch.manual_seed(0)
+        net = DeitIrpe(depth=2, drop_path_rate=0.0).cuda().train()
+        tr = DeitTrainer(net, lr=1e-3)
+        out = []
+        nxt = tr.stage(*host[0]) if staged else None
+        for s in range(5):
+            x, y = host[s % 3]
+            if staged:
+                cur = nxt
+                loss = tr.step(cur)
+                if s + 1 < 5:
+                    nxt = tr.stage(*host[(s + 1) % 3])
+            else:
+                loss = tr.step(x.cuda(), y.cuda())
+            out.append(float(loss))
+        losses.append(out)
+    assert np.allclose(losses[0], losses[1], rtol=2e-4, atol=0), losses
+
+
 # ------------------------------------------------------------------------------------------------
 # iRPE product structure: register-arithmetic gather vs the index-table gather
 # ------------------------------------------------------------------------------------------------

@@ -263,6 +263,41 @@ def test_layernorm_fwd_bwd(E, Es):
     assert float(dgw[E:].abs().sum()) == 0.0
 
 
+@pytest.mark.parametrize("E,rows,dy_bf16,scaled", [(192, 591, True, True), (448, 3 * 197, True, False), (448, 128 * 197, True, True),
+                                                   (624, 1001, False, True), (320, 37, True, True)])
+def test_layernorm_bwd_with_fused_cast(E, rows, dy_bf16, scaled):
+    """cream_layernorm_bwd_cast == cream_layernorm_bwd followed by cream_cast_scale: dx, the bf16 DropPath-scaled
+    copy, the bias-gradient column sums and dgamma / dbeta (pipelined kernel incl. ragged tail tiles; rows = 37 takes
+    the two-pass form); dx is also checked against torch autograd."""
+    from cream_b200 import ops
+    torch.manual_seed(8)
+    x = ops.empty_f32(rows, E); x.copy_(torch.randn(rows, E) * 1.5 - 0.3)
+    gw, gb = (1 + 0.1 * torch.randn(E)).cuda(), (0.1 * torch.randn(E)).cuda()
+    _, mean, rstd = ops.layernorm_fwd(x, gw, gb, 1e-5, E)
+    if dy_bf16:
+        dy = ops.empty_bf16(rows, E); dy.copy_(torch.randn(rows, E))
+    else:
+        dy = ops.empty_f32(rows, E); dy.copy_(torch.randn(rows, E))
+    rg = ops.empty_f32(rows, E); rg.copy_(torch.randn(rows, E))
+    per = 197 if rows % 197 == 0 else rows
+    scale = (torch.rand(rows // per, device="cuda") > 0.3).float() / 0.7 if scaled else None
+    a_g, a_b, a_bias = torch.zeros(E, device="cuda"), torch.zeros(E, device="cuda"), torch.zeros(E, device="cuda")
+    b_g, b_b, b_bias = torch.zeros(E, device="cuda"), torch.zeros(E, device="cuda"), torch.zeros(E, device="cuda")
+    dx_a = ops.layernorm_bwd(dy, x, gw, mean, rstd, E, a_g, a_b, resid_grad=rg)
+    bf_a = ops.cast_scale(dx_a, scale, per, dbias=a_bias)
+    dx_b, bf_b = ops.layernorm_bwd_cast(dy, x, gw, mean, rstd, E, b_g, b_b, resid_grad=rg, row_scale=scale, rows_per_scale=per,
+                                        dbias=b_bias)
+    xr = x.clone().contiguous().requires_grad_(True)
+    F.layer_norm(xr, (E,), gw, gb, 1e-5).backward(dy.float().contiguous())
+    assert rel_err(dx_b.cpu(), (xr.grad + rg).cpu()) < 1e-4
+    assert rel_err(dx_b.cpu(), dx_a.cpu()) < 1e-6
+    # the bf16 copies may differ by one rounding step where dx differs in its last bits
+    assert rel_err(bf_b.float().cpu(), bf_a.float().cpu()) < 1e-3
+    assert float((bf_b.float() - bf_a.float()).abs().max()) <= 2 ** -7 * float(bf_a.float().abs().max())
+    assert rel_err(b_bias.cpu(), a_bias.cpu()) < 1e-4
+    assert rel_err(b_g.cpu(), a_g.cpu()) < 1e-5 and rel_err(b_b.cpu(), a_b.cpu()) < 1e-5
+
+
 # ------------------------------------------------------------------------------------------
 # fused attention
 # ------------------------------------------------------------------------------------------
@@ -629,3 +664,21 @@ def test_tinyvit_attention_module(golden_dir, name):
     check_summary(g, f"{name}_gx", x.grad.float(), 3e-2)
     for pn, p in m.named_parameters():
         check_summary(g, f"{name}_grad_{pn}", p.grad.float(), 3e-2, what=pn)
+
+
+@pytest.mark.parametrize("B,N,h", [(3, 77, 2), (2, 16, 1), (2, 197, 3)])
+def test_attention_causal_flag_equals_the_dense_causal_mask(B, N, h):
+    """cream_attn_desc.causal computes the text tower's mask (open_clip/model.py:756-762) from the coordinates; it
+    must give exactly what the same mask passed as the dense additive term gives, forward and backward."""
+    from cream_b200 import ops
+    qkv = _qkv(B, N, h, 71)
+    dout = ops.empty_bf16(B * N, 64 * h)
+    dout.copy_(rand((B * N, 64 * h), 72))
+    mask = torch.full((N, N), float("-inf")).triu_(1).reshape(1, 1, N, N).cuda()
+    o1, l1 = ops.attention_fwd(qkv, B, h, N, 0.125, dense=mask)
+    o2, l2 = ops.attention_fwd(qkv, B, h, N, 0.125, causal=True)
+    assert torch.equal(o1, o2) and torch.equal(l1, l2)
+    d1 = ops.attention_bwd(qkv, o1, l1, dout, B, h, N, 0.125, dense=mask)[0]
+    d2 = ops.attention_bwd(qkv, o2, l2, dout, B, h, N, 0.125, causal=True)[0]
+    assert torch.isfinite(d2.float()).all()
+    assert rel_err(d2.float().cpu(), d1.float().cpu()) < 1e-5
