@@ -652,6 +652,8 @@ def main():
                     help="gradient all-reduce collectives per step at N > 1: 1 = one after the backward, k = k-1 "
                          "overlapped + one after, 0 = one per layer (round-1 schedule)")
     ap.add_argument("--python-engine", action="store_true", help="sequence the kernels from Python (cross-check)")
+    ap.add_argument("--quick", action="store_true",
+                    help="A/B runs (c3 / c5): the two timed regions only - no per-kernel pass, no reference legs")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -785,6 +787,15 @@ def main():
     timed(cfg_warm[:3], True)
     ms_e2e, _, _, _, last_loss = timed(cfg_timed, True)
     clocks = sampler.stop() if sampler else None
+    if args.quick:
+        if rank == 0:
+            print(json.dumps({"quick": True, "config": args.config, "n_gpus": world, "value": B * world * K / (ms * 1e-3),
+                              "ms_per_step": ms / K, "e2e_ms_per_step": ms_e2e / K, "gpu_launches": launches,
+                              "host_enqueue_ms_per_step": host_enqueue_ms, "pdl": os.environ.get("CREAM_PDL", "1"),
+                              "last_loss": last_loss, "clocks": clocks}))
+        if world > 1:
+            dist.destroy_process_group()
+        return
 
     # ---- per-kernel roofline pass (instrumented; separate from the timed regions, same configs) ----
     # Every launch is bracketed by CUDA events on its own stream.  So that the events time the kernel

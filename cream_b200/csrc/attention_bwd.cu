@@ -50,13 +50,16 @@ struct BwdRowsParams {
   __nv_bfloat16* dqkv; int64_t lddqkv;
   __nv_bfloat16* ws_p; __nv_bfloat16* ws_dt;  // (B*H*N, ldw)
   float* dbias;
+  int wide_out;                        // dqkv rows are 32-byte aligned: 256-bit stores
   const float* dense; int64_t dense_sb, dense_sh, dense_si;   // dense additive logit term (generic path)
   float* ddense;                                              // (B,H,N,N) fp32: dS, or NULL
   long long* trace;   // CREAM_TRACE builds only
 };
 
 #ifdef CREAM_TRACE
-#define ROWS_TRACE(slot) do { if (p.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) p.trace[slot] = clock64(); } while (0)
+// two traced CTAs: the first of the grid (first wave: every SM loads at once) and one from the middle of the grid
+#define ROWS_TRACE(slot) do { if (p.trace && blockIdx.x == 0 && blockIdx.y == 0 && (blockIdx.z == 0 || blockIdx.z == gridDim.z / 2)) \
+    p.trace[(blockIdx.z == 0 ? 0 : 64) + (slot)] = clock64(); } while (0)
 #else
 #define ROWS_TRACE(slot) do {} while (0)
 #endif
@@ -139,12 +142,8 @@ __device__ __forceinline__ void bwd_row_generic(const BwdRowsParams& p, const Ro
     }
     tmem_st8(x.trow + c * 8, dk);   // dT (bf16x2) in place over T, A operand of the dQ MMA
     if (x.row < p.N) {
-      uint4* wp = reinterpret_cast<uint4*>(p.ws_p + x.wrow + c * 16);
-      uint4* wd = reinterpret_cast<uint4*>(p.ws_dt + x.wrow + c * 16);
-      wp[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-      wp[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
-      wd[0] = make_uint4(dk[0], dk[1], dk[2], dk[3]);
-      wd[1] = make_uint4(dk[4], dk[5], dk[6], dk[7]);
+      stg_256(p.ws_p + x.wrow + c * 16, pk);     // 16 keys = 32 bytes of this row, one 256-bit store each
+      stg_256(p.ws_dt + x.wrow + c * 16, dk);
     }
   }
   rows_barrier();
@@ -160,6 +159,9 @@ __device__ __forceinline__ void bwd_row_generic(const BwdRowsParams& p, const Ro
 // unrolled code on "local" grid rows 0..7 with their own operand registers (the kernel is
 // instruction-fetch bound: one shared stream halves its footprint).  The only asymmetric element
 // is local key 0: the cls key for half 0, grid position (7, 13) for half 1.
+#ifndef CREAM_ABL
+#define CREAM_ABL 0      // timing ablations (debug builds only; results are wrong when non-zero)
+#endif
 constexpr int kAfSplitCols = 112;                 // keys owned by the first thread of a row
 constexpr int kAfSplitRows = 8;                   // = kAfSplitCols / 14 grid rows
 constexpr int kDtHiCol = 464;                     // TMEM columns [464, 512): packed dT of the second half
@@ -247,8 +249,10 @@ __device__ __forceinline__ void bwd_row_af(const BwdRowsParams& p, const RowCtx&
         const int rj = (j0 - 1) / G, cj = (j0 - 1) % G;
         pr = fast_exp2(fmaf(sl, __uint_as_float(rt[k]), rv[rj]) + rh[cj]);
         d = pr * (__uint_as_float(rp[k]) + gv[rj] + gh[cj]);
+        if (!(CREAM_ABL & 4)) {
         prow[rj] += pr; pcol[cj] += pr;
         drow[rj] += d;  dcol[cj] += d;
+        }
       }
       pv[k] = pr;
       dt[k] = d;
@@ -260,13 +264,9 @@ __device__ __forceinline__ void bwd_row_af(const BwdRowsParams& p, const RowCtx&
       dk[k] = pack_bf16x2(dt[2 * k], dt[2 * k + 1]);
     }
     tmem_st8(t_out + cc * 8, dk);     // half 0: over T columns it has already read; half 1: spare columns
-    if (live) {
-      uint4* wp = reinterpret_cast<uint4*>(p.ws_p + w0 + cc * 16);
-      uint4* wd = reinterpret_cast<uint4*>(p.ws_dt + w0 + cc * 16);
-      wp[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-      wp[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
-      wd[0] = make_uint4(dk[0], dk[1], dk[2], dk[3]);
-      wd[1] = make_uint4(dk[4], dk[5], dk[6], dk[7]);
+    if (live && !(CREAM_ABL & 1)) {
+      stg_256(p.ws_p + w0 + cc * 16, pk);     // 16 keys = 32 bytes of this row, one 256-bit store each
+      stg_256(p.ws_dt + w0 + cc * 16, dk);
     }
   }
   // this thread's share of the row totals (every key hits exactly one vertical bucket)
@@ -421,12 +421,8 @@ __device__ __forceinline__ void bwd_row_gridprod(const BwdRowsParams& p, const R
     }
     tmem_st8(t_out + cc * 8, dk);
     if (live) {
-      uint4* wp = reinterpret_cast<uint4*>(p.ws_p + w0 + cc * 16);
-      uint4* wd = reinterpret_cast<uint4*>(p.ws_dt + w0 + cc * 16);
-      wp[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-      wp[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
-      wd[0] = make_uint4(dk[0], dk[1], dk[2], dk[3]);
-      wd[1] = make_uint4(dk[4], dk[5], dk[6], dk[7]);
+      stg_256(p.ws_p + w0 + cc * 16, pk);     // 16 keys = 32 bytes of this row, one 256-bit store each
+      stg_256(p.ws_dt + w0 + cc * 16, dk);
     }
   }
   // The cls query row gathers ONE bucket for every key, i.e. adds a constant to its logits: its exact
@@ -495,12 +491,8 @@ __device__ __forceinline__ void bwd_row_plain(const BwdRowsParams& p, const RowC
     tmem_st8(dt_out + cc * 8, dk);
     tmem_st8(p_out + cc * 8, pk);
     if (live) {
-      uint4* wp = reinterpret_cast<uint4*>(p.ws_p + w0 + cc * 16);
-      uint4* wd = reinterpret_cast<uint4*>(p.ws_dt + w0 + cc * 16);
-      wp[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-      wp[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
-      wd[0] = make_uint4(dk[0], dk[1], dk[2], dk[3]);
-      wd[1] = make_uint4(dk[4], dk[5], dk[6], dk[7]);
+      stg_256(p.ws_p + w0 + cc * 16, pk);     // 16 keys = 32 bytes of this row, one 256-bit store each
+      stg_256(p.ws_dt + w0 + cc * 16, dk);
     }
   }
 }
@@ -512,6 +504,8 @@ attn_bwd_rows_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
                      const BwdRowsParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   require_smem_alignment(smem);
+  if (threadIdx.x == 0) ROWS_TRACE(40);
+  pdl_trigger();
   const int kv_bytes = p.Npad * 128;
   const int v_slot = max(kv_bytes, 26 * 1024);
   uint8_t* sQ = smem;                       // 16 KB
@@ -561,6 +555,7 @@ attn_bwd_rows_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
     fence_mbar_init();
   }
   if (warp == 0) tmem_alloc<512>(tmem_slot);
+  pdl_wait();      // barrier init / TMEM allocation above overlap the previous kernel's tail; global memory from here on
   if (p.af_mma && threadIdx.x >= 32) {
     write_ind_matrix(smem_u32(sInd), threadIdx.x - 32, kRowThreads, 14, p.N);
     fence_proxy_async_smem();
@@ -835,13 +830,13 @@ attn_bwd_rows_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
         }
       }
       if (p.ctx_k) tmem_st16(x.trow + (p.af_mma ? kDrPackCol : Npad / 2) + c * 16, dk);
-      if (row < p.N) {
-        uint4* wp = reinterpret_cast<uint4*>(p.ws_p + x.wrow + Npad + c * 32);
-        uint4* wd = reinterpret_cast<uint4*>(p.ws_dt + x.wrow + Npad + c * 32);
+      if (row < p.N && !(CREAM_ABL & 2)) {
+        __nv_bfloat16* wp = p.ws_p + x.wrow + Npad + c * 32;
+        __nv_bfloat16* wd = p.ws_dt + x.wrow + Npad + c * 32;
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          wp[q] = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
-          wd[q] = make_uint4(dk[4 * q], dk[4 * q + 1], dk[4 * q + 2], dk[4 * q + 3]);
+        for (int q = 0; q < 2; ++q) {
+          stg_256(wp + 16 * q, pk[8 * q], pk[8 * q + 1], pk[8 * q + 2], pk[8 * q + 3], pk[8 * q + 4], pk[8 * q + 5], pk[8 * q + 6], pk[8 * q + 7]);
+          stg_256(wd + 16 * q, dk[8 * q], dk[8 * q + 1], dk[8 * q + 2], dk[8 * q + 3], dk[8 * q + 4], dk[8 * q + 5], dk[8 * q + 6], dk[8 * q + 7]);
         }
       }
     }
@@ -863,18 +858,7 @@ attn_bwd_rows_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
       uint32_t raw[32];
       tmem_ld32(trow + 192 + c * 32, raw);
       tmem_ld_wait();
-      if (row < p.N) {
-        uint4* o4 = reinterpret_cast<uint4*>(qrow + c * 32);
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          uint4 u;
-          u.x = pack_bf16x2(p.scale * __uint_as_float(raw[8 * q + 0]), p.scale * __uint_as_float(raw[8 * q + 1]));
-          u.y = pack_bf16x2(p.scale * __uint_as_float(raw[8 * q + 2]), p.scale * __uint_as_float(raw[8 * q + 3]));
-          u.z = pack_bf16x2(p.scale * __uint_as_float(raw[8 * q + 4]), p.scale * __uint_as_float(raw[8 * q + 5]));
-          u.w = pack_bf16x2(p.scale * __uint_as_float(raw[8 * q + 6]), p.scale * __uint_as_float(raw[8 * q + 7]));
-          o4[q] = u;
-        }
-      }
+      if (row < p.N && !(CREAM_ABL & 2)) store_row32_bf16(qrow + c * 32, raw, p.scale, p.wide_out != 0);
     }
   }
 
@@ -885,6 +869,7 @@ attn_bwd_rows_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
   if (warp == 0) {
     tc_fence_after();
     tmem_dealloc<512>(tmem);
+    if (lane == 0) ROWS_TRACE(41);
   }
 }
 
@@ -908,6 +893,7 @@ struct BwdColsParams {
   int shared_tables;
   __nv_bfloat16* dqkv; int64_t lddqkv;
   float* dtk; float* dtv;
+  int wide_out;
 };
 
 __global__ void __launch_bounds__(kColsThreads, 1)
@@ -916,6 +902,7 @@ attn_bwd_cols_kernel(const __grid_constant__ CUtensorMap map_wp, const __grid_co
                      const BwdColsParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   require_smem_alignment(smem);
+  pdl_trigger();
   uint8_t* red_rows = smem + kColStages * kColStageBytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(red_rows + kRedBytes);
   uint64_t* full = bars;
@@ -945,6 +932,7 @@ attn_bwd_cols_kernel(const __grid_constant__ CUtensorMap map_wp, const __grid_co
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
+  pdl_wait();      // the rows kernel's workspace / dQ writes are complete and visible from here on
 
   if (warp == 0 && lane == 0) {
     // loads run ahead across products and items
@@ -1017,16 +1005,7 @@ attn_bwd_cols_kernel(const __grid_constant__ CUtensorMap map_wp, const __grid_co
             tmem_ld32(trow + which * 192 + mt * 64 + c * 32, raw);
             tmem_ld_wait();
             if (m < p.N) {
-              uint4* o4 = reinterpret_cast<uint4*>(p.dqkv + (static_cast<int64_t>(b) * p.N + m) * p.lddqkv + col0 + c * 32);
-#pragma unroll
-              for (int q = 0; q < 4; ++q) {
-                uint4 u;
-                u.x = pack_bf16x2(mul * __uint_as_float(raw[8 * q + 0]), mul * __uint_as_float(raw[8 * q + 1]));
-                u.y = pack_bf16x2(mul * __uint_as_float(raw[8 * q + 2]), mul * __uint_as_float(raw[8 * q + 3]));
-                u.z = pack_bf16x2(mul * __uint_as_float(raw[8 * q + 4]), mul * __uint_as_float(raw[8 * q + 5]));
-                u.w = pack_bf16x2(mul * __uint_as_float(raw[8 * q + 6]), mul * __uint_as_float(raw[8 * q + 7]));
-                o4[q] = u;
-              }
+              store_row32_bf16(p.dqkv + (static_cast<int64_t>(b) * p.N + m) * p.lddqkv + col0 + c * 32, raw, mul, p.wide_out != 0);
             } else if (m >= p.Npad && m < p.Npad + kNB && dtab != nullptr) {
               // table-gradient row (one bucket): staged in this thread's private shared row and
               // added to global memory by ONE 256-byte bulk reduce (the L2 does the fp32 adds on
@@ -1104,6 +1083,7 @@ extern "C" int cream_attn_bwd(const cream_attn_desc* d, void* stream_) {
   p.dout = static_cast<const __nv_bfloat16*>(d->dout); p.lddo = d->ld_dout;
   p.lse = d->lse;
   p.dqkv = static_cast<__nv_bfloat16*>(d->dqkv); p.lddqkv = d->ld_dqkv;
+  p.wide_out = aligned_for_256bit(d->dqkv, d->ld_dqkv) ? 1 : 0;
   p.ws_p = ws_p; p.ws_dt = ws_dt;
   p.dbias = d->dbias_pack;
   p.dense = d->dense_bias; p.dense_sb = d->dense_stride_b; p.dense_sh = d->dense_stride_h; p.dense_si = d->dense_stride_i;
@@ -1165,28 +1145,32 @@ extern "C" int cream_attn_bwd(const cream_attn_desc* d, void* stream_) {
 #ifdef CREAM_TRACE
   static long long* trace_dev = nullptr;
   if (getenv("CREAM_ATTN_TRACE") != nullptr) {
-    if (trace_dev == nullptr) CB_CUDA_OK(cudaMalloc(&trace_dev, 64 * sizeof(long long)));
-    CB_CUDA_OK(cudaMemsetAsync(trace_dev, 0, 64 * sizeof(long long), stream));
+    if (trace_dev == nullptr) CB_CUDA_OK(cudaMalloc(&trace_dev, 128 * sizeof(long long)));
+    CB_CUDA_OK(cudaMemsetAsync(trace_dev, 0, 128 * sizeof(long long), stream));
     p.trace = trace_dev;
   }
 #endif
-  attn_bwd_rows_kernel<<<grid, kRowsThreads, smem_rows, stream>>>(*mq, *mkv, *mdo, *mo, *mtk, *mtv, p);
+  CB_CUDA_OK(launch_chain(attn_bwd_rows_kernel, grid, dim3(kRowsThreads), smem_rows, stream, 1, *mq, *mkv, *mdo, *mo, *mtk, *mtv, p));
   int rc = check_last("attn_bwd_rows_kernel");
   if (rc) return rc;
 #ifdef CREAM_TRACE
   if (p.trace != nullptr) {
     static int dumps = 0;
-    if (p.af_grid != 0 && dumps++ < 4) {
-      long long h[64];
+    if ((p.af_grid != 0 || p.gp_grid != 0) && dumps++ < 6) {
+      long long hh[128];
       CB_CUDA_OK(cudaStreamSynchronize(stream));
-      CB_CUDA_OK(cudaMemcpy(h, trace_dev, sizeof(h), cudaMemcpyDeviceToHost));
-      const long long t0 = h[0];
-      fprintf(stderr, "ROWS TRACE (cycles from first TMA issue) B %d H %d N %d af %d\n", p.B, p.H, p.N, p.af_grid);
-      fprintf(stderr, "  mma thread: loads landed %lld | T,dP issued %lld | bar_p %lld\n", h[1] - t0, h[2] - t0, h[3] - t0);
-      for (int q = 0; q < 2; ++q) {
-        const long long* e = h + 8 + 16 * q;
-        fprintf(stderr, "  row thread half %d: start %lld | R ready %lld | staged %lld | delta loaded %lld | T ready %lld | columns done %lld | tail done %lld | dQ ready %lld\n",
-                q, e[0] - t0, e[1] - t0, e[2] - t0, e[3] - t0, e[4] - t0, e[5] - t0, e[6] - t0, e[7] - t0);
+      CB_CUDA_OK(cudaMemcpy(hh, trace_dev, sizeof(hh), cudaMemcpyDeviceToHost));
+      for (int cta = 0; cta < 2; ++cta) {
+        const long long* h = hh + 64 * cta;
+        const long long t0 = h[0];
+        fprintf(stderr, "ROWS TRACE cta %s (cycles from first TMA issue) B %d H %d N %d af %d gp %d\n", cta ? "mid-grid" : "first", p.B, p.H, p.N, p.af_grid, p.gp_grid);
+        fprintf(stderr, "  kernel entry %lld | exit %lld\n", h[40] - t0, h[41] - t0);
+        fprintf(stderr, "  mma thread: loads landed %lld | T,dP issued %lld | bar_p %lld\n", h[1] - t0, h[2] - t0, h[3] - t0);
+        for (int q = 0; q < 2; ++q) {
+          const long long* e = h + 8 + 16 * q;
+          fprintf(stderr, "  row thread half %d: delta done %lld | R ready %lld | staged %lld | - %lld | T ready %lld | columns done %lld | tail done %lld | dQ ready %lld\n",
+                  q, e[0] - t0, e[1] - t0, e[2] - t0, e[3] - t0, e[4] - t0, e[5] - t0, e[6] - t0, e[7] - t0);
+        }
       }
     }
   }
@@ -1197,10 +1181,11 @@ extern "C" int cream_attn_bwd(const cream_attn_desc* d, void* stream_) {
   c.scale = d->scale;
   c.shared_tables = d->tables_per_head ? 0 : 1;
   c.dqkv = static_cast<__nv_bfloat16*>(d->dqkv); c.lddqkv = d->ld_dqkv;
+  c.wide_out = p.wide_out;
   c.dtk = ctx_k ? d->dtk_pack : nullptr;
   c.dtv = ctx_v ? d->dtv_pack : nullptr;
   const size_t smem_cols = kColStages * kColStageBytes + kRedBytes + 256;
   const int grid2 = std::min(d->B * d->H, kNumSMs);
-  attn_bwd_cols_kernel<<<grid2, kColsThreads, smem_cols, stream>>>(*mwp, *mwd, *mdo64, *mq64, c);
+  CB_CUDA_OK(launch_chain(attn_bwd_cols_kernel, dim3(grid2), dim3(kColsThreads), smem_cols, stream, 1, *mwp, *mwd, *mdo64, *mq64, c));
   return check_last("attn_bwd_cols_kernel");
 }

@@ -60,6 +60,25 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8])
       : "memory");
 }
 
+// 32 fp32 accumulator values of one output row -> 32 bf16 (64 contiguous bytes): two 256-bit stores when the
+// destination is 32-byte aligned (`wide`, checked on the host: base pointer and leading dimension), else four 128-bit ones.
+__device__ __forceinline__ void store_row32_bf16(__nv_bfloat16* dst, const uint32_t (&raw)[32], float mul, bool wide) {
+  uint32_t u[16];
+#pragma unroll
+  for (int k = 0; k < 16; ++k) u[k] = pack_bf16x2(mul * __uint_as_float(raw[2 * k]), mul * __uint_as_float(raw[2 * k + 1]));
+  if (wide) {
+    stg_256(dst, u[0], u[1], u[2], u[3], u[4], u[5], u[6], u[7]);
+    stg_256(dst + 16, u[8], u[9], u[10], u[11], u[12], u[13], u[14], u[15]);
+  } else {
+    uint4* o4 = reinterpret_cast<uint4*>(dst);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) o4[q] = make_uint4(u[4 * q], u[4 * q + 1], u[4 * q + 2], u[4 * q + 3]);
+  }
+}
+__host__ inline bool aligned_for_256bit(const void* base, int64_t ld_elems_bf16) {
+  return (reinterpret_cast<uintptr_t>(base) & 31) == 0 && (ld_elems_bf16 % 16) == 0;
+}
+
 __device__ __forceinline__ uint32_t byte_of(const uint32_t (&w)[4], int k) {
   return (w[k >> 2] >> (8 * (k & 3))) & 0xFF;
 }

@@ -50,6 +50,7 @@ struct AttnFwdParams {
   const float* dense; int64_t dense_sb, dense_sh, dense_si;   // dense additive logit term (generic path)
   int causal;                          // generic path: key j > query i masked
   __nv_bfloat16* out; int64_t ldo;     // (B*N, H*64)
+  int wide_out;                        // out rows are 32-byte aligned: 256-bit stores
   float* lse;                          // (B, H, N)
 };
 
@@ -378,6 +379,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
                 const AttnFwdParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   require_smem_alignment(smem);
+  pdl_trigger();
   const int kv_bytes = p.Npad * 128;
   const int k_slot = max(kv_bytes, 11 * 1024);  // sQ + sTK + sK must hold the 128 x 68 fp32 PB overlay
   uint8_t* sQ = smem;
@@ -421,6 +423,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
     fence_mbar_init();
   }
   if (warp == 0) tmem_alloc<256>(tmem_slot);
+  pdl_wait();      // barrier init / TMEM allocation above overlap the previous kernel's tail; global memory from here on
   if (p.bias != nullptr && threadIdx.x >= 32 && threadIdx.x < 96)
     sts_f32(smem_u32(sBias) + 4 * (threadIdx.x - 32),
             p.bias[(p.shared_tables ? 0 : head) * 64 + threadIdx.x - 32]);
@@ -643,18 +646,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
       uint32_t raw[32];
       tmem_ld32(trow + 192 + c * 32, raw);
       tmem_ld_wait();
-      if (row < p.N) {
-        uint4* o4 = reinterpret_cast<uint4*>(orow + c * 32);
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          uint4 u;
-          u.x = pack_bf16x2(inv * __uint_as_float(raw[8 * q + 0]), inv * __uint_as_float(raw[8 * q + 1]));
-          u.y = pack_bf16x2(inv * __uint_as_float(raw[8 * q + 2]), inv * __uint_as_float(raw[8 * q + 3]));
-          u.z = pack_bf16x2(inv * __uint_as_float(raw[8 * q + 4]), inv * __uint_as_float(raw[8 * q + 5]));
-          u.w = pack_bf16x2(inv * __uint_as_float(raw[8 * q + 6]), inv * __uint_as_float(raw[8 * q + 7]));
-          o4[q] = u;
-        }
-      }
+      if (row < p.N) store_row32_bf16(orow + c * 32, raw, inv, p.wide_out != 0);
     }
     if (row < p.N && p.lse != nullptr)
       p.lse[(static_cast<int64_t>(b) * p.H + head) * p.N + row] = mx + __logf(sum);
@@ -696,6 +688,7 @@ extern "C" int cream_attn_fwd(const cream_attn_desc* d, void* stream_) {
   p.ldi = ldi;
   p.bias = d->bias_pack;
   p.out = static_cast<__nv_bfloat16*>(d->out); p.ldo = d->ld_out;
+  p.wide_out = aligned_for_256bit(d->out, d->ld_out) ? 1 : 0;
   p.lse = d->lse;
   p.dense = d->dense_bias; p.dense_sb = d->dense_stride_b; p.dense_sh = d->dense_stride_h; p.dense_si = d->dense_stride_i;
   p.causal = d->causal;
@@ -757,6 +750,6 @@ extern "C" int cream_attn_fwd(const cream_attn_desc* d, void* stream_) {
   }
   CB_REQUIRE(smem_bytes <= 113 * 1024, "shared memory budget");
   dim3 grid(ceil_div(d->N, 128), d->H, d->B);
-  attn_fwd_kernel<<<grid, kThreads, smem_bytes, stream>>>(*mq, *mkv, *mtk, *mtv, p);
+  CB_CUDA_OK(launch_chain(attn_fwd_kernel, grid, dim3(kThreads), smem_bytes, stream, 1, *mq, *mkv, *mtk, *mtv, p));
   return check_last("attn_fwd_kernel");
 }

@@ -113,6 +113,49 @@ __device__ __forceinline__ void block_add_to_global(float* dst, const float* s_s
   }
 }
 
+// ---- programmatic dependent launch (PDL) --------------------------------------------------------
+// The backward / forward of a block is a chain of ~25 dependent launches of 15-60 us each; with plain stream order
+// every kernel pays its own ramp (CTA scheduling, barrier init, TMEM allocation, tensor-map fetch) after the previous
+// kernel's LAST CTA has drained.  Kernels launched through launch_chain() carry
+// cudaLaunchAttributeProgrammaticStreamSerialization: their CTAs are placed on SMs as the previous kernel's CTAs exit
+// and run their prologue there, then block in pdl_wait() (griddepcontrol.wait: returns when every prerequisite grid
+// has COMPLETED and its writes are visible).  Contract for a kernel launched this way: pdl_trigger() first thing,
+// and pdl_wait() before its first global-memory access of any kind (reads of the predecessor's output, and writes
+// the predecessor may still be reading).  Completion is transitive - each grid waits for its predecessor before doing
+// anything - so stream order of the data is unchanged.  CREAM_PDL=0 restores plain launches (the two device
+// instructions are no-ops then).
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+bool pdl_enabled();   // tensormap.cu: CREAM_PDL != "0"
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_chain(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                                int cluster_x, Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[2];
+  unsigned n = 0;
+  if (cluster_x > 1) {
+    attr[n].id = cudaLaunchAttributeClusterDimension;
+    attr[n].val.clusterDim.x = static_cast<unsigned>(cluster_x);
+    attr[n].val.clusterDim.y = 1;
+    attr[n].val.clusterDim.z = 1;
+    ++n;
+  }
+  if (pdl_enabled()) {
+    attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[n].val.programmaticStreamSerializationAllowed = 1;
+    ++n;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = n;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // Host-side TMA tensor-map factory (cached). dims/strides in elements; strides[0]
 // is implicit (1). Returns nullptr on failure.
 const CUtensorMap* get_tensor_map(const void* base, CUtensorMapDataType dtype, int rank,

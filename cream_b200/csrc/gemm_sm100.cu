@@ -125,6 +125,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   using T = EpiTraits<EPI>;
   extern __shared__ __align__(1024) uint8_t smem[];
   require_smem_alignment(smem);
+  pdl_trigger();   // the next kernel of the chain may be scheduled as this grid's CTAs retire (it blocks in pdl_wait)
   uint8_t* epi_slots = smem + p.num_stages * p.stage_bytes;             // 2 x 16 KB, 1024-aligned
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(epi_slots + 2 * kEpiSlotBytes);
   uint64_t* empty_bar = full_bar + kMaxStages;
@@ -169,6 +170,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();      // everything above ran under the previous kernel's tail; no global access before this point
 
   if (warp == 0 && lane == 0) {
     // ===================== TMA producer (both CTAs of a pair) =====================
@@ -507,23 +509,8 @@ int launch_gemm_impl(const CUtensorMap& ta, const CUtensorMap& tb, const CUtenso
                                     cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
-  if constexpr (!kPair) {
-    gemm_bf16_kernel<EPI, false><<<grid, kNumThreads, smem_bytes, stream>>>(ta, tb, to, tx, toh, txh, p);
-  } else {
-    cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(grid);
-    cfg.blockDim = dim3(kNumThreads);
-    cfg.dynamicSmemBytes = smem_bytes;
-    cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    CB_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_bf16_kernel<EPI, true>, ta, tb, to, tx, toh, txh, p));
-  }
+  CB_CUDA_OK(launch_chain(gemm_bf16_kernel<EPI, kPair>, dim3(grid), dim3(kNumThreads), smem_bytes, stream, kPair ? 2 : 1,
+                          ta, tb, to, tx, toh, txh, p));
   return check_last("gemm_bf16_kernel launch");
 }
 

@@ -71,6 +71,8 @@ __global__ void __launch_bounds__(kWarps * 32)
 ln_fwd_vec_kernel(const float* __restrict__ x, int64_t ldx, const float* __restrict__ gamma,
                   const float* __restrict__ beta, float eps, void* __restrict__ out, int64_t ldo,
                   float* __restrict__ mean, float* __restrict__ rstd, int64_t rows, int E) {
+  pdl_trigger();
+  pdl_wait();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const float invE = 1.0f / E;
   for (int64_t r = static_cast<int64_t>(blockIdx.x) * kWarps + warp; r < rows;
@@ -311,12 +313,14 @@ ln_bwd_pipe_kernel(const void* __restrict__ dy, int64_t lddy, const float* __res
   uint64_t* empty = full + stages;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const bool has_rg = resid_grad != nullptr;
+  pdl_trigger();
   for (int i = threadIdx.x; i < 3 * E; i += blockDim.x) sacc[i] = 0.f;
-  for (int i = threadIdx.x; i < E; i += blockDim.x) sgam[i] = __ldg(gamma + i);
   if (threadIdx.x == 0) {
     for (int s = 0; s < stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], kPipeRows); }
     fence_mbar_init();
   }
+  pdl_wait();      // shared-memory setup above overlaps the previous kernel's tail; global memory from here on
+  for (int i = threadIdx.x; i < E; i += blockDim.x) sgam[i] = __ldg(gamma + i);
   __syncthreads();
   const int64_t tiles = ceil_div64(rows, kPipeRows);
 
@@ -478,7 +482,7 @@ extern "C" int cream_layernorm_fwd(const float* x, int64_t ldx, const float* gam
                      reinterpret_cast<uintptr_t>(gamma) | reinterpret_cast<uintptr_t>(beta)) & 15) == 0;
   if (vec) {
 #define CB_LN_FWD_VEC(F32, V) \
-  ln_fwd_vec_kernel<F32, V><<<grid, kWarps * 32, 0, stream>>>(x, ldx, gamma, beta, eps, out, ldo, mean, rstd, rows, E)
+  CB_CUDA_OK(launch_chain(ln_fwd_vec_kernel<F32, V>, dim3(grid), dim3(kWarps * 32), 0, stream, 1, x, ldx, gamma, beta, eps, out, ldo, mean, rstd, rows, E))
     const int v = ceil_div(E, 128);
     if (out_f32) {
       if (v <= 2) CB_LN_FWD_VEC(true, 2); else if (v == 3) CB_LN_FWD_VEC(true, 3);
@@ -541,10 +545,10 @@ static int layernorm_bwd_impl(const void* dy, int64_t lddy, int dy_f32, const fl
       CB_CUDA_OK(cudaFuncSetAttribute(ln_bwd_pipe_kernel<F32, V, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024)); \
       attr_done = true;                                                                                                 \
     }                                                                                                                   \
-    ln_bwd_pipe_kernel<F32, V, MB><<<gridp, kPipeThreads, smem_pipe, stream>>>(                                         \
+    CB_CUDA_OK(launch_chain(ln_bwd_pipe_kernel<F32, V, MB>, dim3(gridp), dim3(kPipeThreads), smem_pipe, stream, 1,       \
         dy, lddy, x, ldx, gamma, mean, rstd, resid_grad, ldrg, dx, lddx, dgamma, dbeta, rows, E,                        \
         stages, ob, ldob,                                                                                               \
-        emit ? row_scale : nullptr, rp, emit ? dbias : nullptr);                                                        \
+        emit ? row_scale : nullptr, rp, emit ? dbias : nullptr));                                                       \
   } while (0)
 #define CB_LN_BWDP(F32, V) CB_LN_BWDP_(F32, V, 1)
       if (dy_f32) { if (E <= 256) CB_LN_BWDP(true, 2); else if (E <= 512) CB_LN_BWDP(true, 4); else CB_LN_BWDP(true, 6); }

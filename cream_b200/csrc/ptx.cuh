@@ -210,6 +210,19 @@ __device__ __forceinline__ void tmem_st_wait() {
 
 // 32 lanes x 32-bit, 32 consecutive columns: thread t of the warp receives
 // row (lane_base + t), columns [col, col+32).
+// 256-bit global store (sm_100: STG.E.256).  A thread that owns a whole row writes 32 contiguous bytes per
+// instruction; with one row per lane every lane hits its own 128-byte line, so the store unit spends one pass per
+// lane either way - twice the bytes per pass compared with 16-byte stores.  `p` must be 32-byte aligned.
+__device__ __forceinline__ void stg_256(void* p, uint32_t r0, uint32_t r1, uint32_t r2, uint32_t r3, uint32_t r4,
+                                        uint32_t r5, uint32_t r6, uint32_t r7) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(r0), "r"(r1), "r"(r2), "r"(r3),
+               "r"(r4), "r"(r5), "r"(r6), "r"(r7)
+               : "memory");
+}
+__device__ __forceinline__ void stg_256(void* p, const uint32_t (&r)[8]) {
+  stg_256(p, r[0], r[1], r[2], r[3], r[4], r[5], r[6], r[7]);
+}
+
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "

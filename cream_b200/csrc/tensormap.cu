@@ -1,6 +1,7 @@
 // Host-side cache of TMA tensor maps.  The sampled-subnet slice (embed dim, heads,
 // mlp ratio) only changes the extents of a map over the FULL supernet tensor, so a
 // supernet needs a few dozen maps in total; they are encoded once and reused.
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <unordered_map>
@@ -9,6 +10,11 @@
 #include "common.cuh"
 
 namespace cb {
+
+bool pdl_enabled() {
+  static const bool on = []() { const char* e = getenv("CREAM_PDL"); return !(e != nullptr && e[0] == '0'); }();
+  return on;
+}
 
 namespace {
 

@@ -17,13 +17,17 @@ def timeit(fn, iters=20):
     for _ in range(iters): fn()
     e1.record(); torch.cuda.synchronize()
     return e0.elapsed_time(e1) / iters * 1e3
-for name, af in (("generic", None), ("structured", (14, 14))):
+import os
+ONLY = os.environ.get("CREAM_ONLY_STRUCTURED") == "1"
+for name, af in ((("structured", (14, 14)),) if ONLY else (("generic", None), ("structured", (14, 14)))):
     out, lse = ops.attention_fwd(qkv, B, h, N, 0.125, tk=tk, tv=tv, idx=(iv, ih, iv, ih), af=af)
     tf = timeit(lambda: ops.attention_fwd(qkv, B, h, N, 0.125, tk=tk, tv=tv, idx=(iv, ih, iv, ih), af=af))
     tb = timeit(lambda: ops.attention_bwd(qkv, out, lse, dout, B, h, N, 0.125, tk=tk, tv=tv, idx=(iv, ih, iv, ih), af=af))
     fl = 4.0 * B * h * N * N * 64 + 2.0 * B * h * N * 64 * 128
     by = 4.0 * B * h * N * 64 * 2
     print(f"{name:10s} fwd {tf:7.1f} us  {fl / tf / 1e6:6.1f} TFLOP/s  {by / tf / 1e3:6.0f} GB/s | bwd (rows+cols) {tb:7.1f} us")
+if ONLY:
+    sys.exit(0)
 # BASELINE config 2 shape: DeiT-S + iRPE product table on keys (B 256, 6 heads): index-table path vs structured path
 from oracle import rel_index
 import numpy as np
