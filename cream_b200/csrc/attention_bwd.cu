@@ -76,12 +76,21 @@ struct RowCtx {
   int row, row_c, sw, half;
   float delta, lsel;
   int64_t wrow;
+  uint64_t* bar_cols;   // rows -> MMA: this thread's packed dT is in TMEM (the dT . K part of dQ may start)
 };
+
+// Called by every row thread once its share of the packed dT has been written to TMEM: the tensor core starts
+// dQ = dT . K while the bucket sums are still being folded and packed (dR . TK is added after that).
+__device__ __forceinline__ void columns_done(const RowCtx& x) {
+  tmem_st_wait();
+  tc_fence_before();
+  mbar_arrive(x.bar_cols);
+}
 
 // dT / P of one query row, generic gather tables (see attention_fwd.cu for the forward twin).
 __device__ __forceinline__ void bwd_row_generic(const BwdRowsParams& p, const RowCtx& x) {
   const int Npad = p.Npad;
-  if (x.half != 0) { rows_barrier(); rows_barrier(); return; }   // keep the barrier schedule of the pair
+  if (x.half != 0) { columns_done(x); rows_barrier(); rows_barrier(); return; }   // keep the barrier schedule of the pair
   for (int k = 0; k < kNB; ++k) { sts_f32(x.s_pb + 4 * ((k + x.sw) & 63), 0.f); sts_f32(x.s_dr + 4 * k, 0.f); }
   const uint8_t* ia = p.idx_a ? p.idx_a + static_cast<int64_t>(x.row_c) * p.ldi : nullptr;
   const uint8_t* ib = p.idx_b ? p.idx_b + static_cast<int64_t>(x.row_c) * p.ldi : nullptr;
@@ -146,6 +155,7 @@ __device__ __forceinline__ void bwd_row_generic(const BwdRowsParams& p, const Ro
       stg_256(p.ws_dt + x.wrow + c * 16, dk);
     }
   }
+  columns_done(x);
   rows_barrier();
   rows_barrier();
 }
@@ -269,6 +279,7 @@ __device__ __forceinline__ void bwd_row_af(const BwdRowsParams& p, const RowCtx&
       stg_256(p.ws_dt + w0 + cc * 16, dk);
     }
   }
+  columns_done(x);
   // this thread's share of the row totals (every key hits exactly one vertical bucket)
   float psum = pf, dsum = df;
 #pragma unroll
@@ -277,10 +288,14 @@ __device__ __forceinline__ void bwd_row_af(const BwdRowsParams& p, const RowCtx&
   // scatter the register bucket sums into the shared rows read by the common tail: the thread
   // owning the first half initialises the row, its partner adds its partial sums after the barrier.
   auto put = [&](uint32_t a, float v) { if (hi) v += lds_f32(a); sts_f32(a, v); };
-  if (hi == 0)
-    for (int k = 0; k < kNB; ++k) { sts_f32(x.s_pb + 4 * ((k + x.sw) & 63), 0.f); sts_f32(x.s_dr + 4 * k, 0.f); }
-  else
+  if (hi == 0) {      // zero both bucket rows: PB (256 B, 16-byte aligned; the rotation only renames the slots) and dR (8-byte aligned)
+#pragma unroll
+    for (int k = 0; k < kNB / 4; ++k) sts_f32x4(x.s_pb + 16 * k, make_float4(0.f, 0.f, 0.f, 0.f));
+#pragma unroll
+    for (int k = 0; k < kNB / 2; ++k) sts_f32x2(x.s_dr + 8 * k, 0.f, 0.f);
+  } else {
     rows_barrier();
+  }
   if (patch) {
 #pragma unroll
     for (int t = 0; t < LR; ++t) {
@@ -357,7 +372,13 @@ __device__ __forceinline__ void bwd_row_gridprod(const BwdRowsParams& p, const R
   auto bucket_addr = [&](uint32_t off4) -> uint32_t {  // this half's private bucket row
     return hi ? x.s_pb + 4u * (((off4 >> 2) + x.sw) & 63u) : x.s_dr + off4;
   };
-  for (int k = 0; k < kNB; ++k) sts_f32(bucket_addr(4u * k), 0.f);
+  if (hi) {
+#pragma unroll
+    for (int k = 0; k < kNB / 4; ++k) sts_f32x4(x.s_pb + 16 * k, make_float4(0.f, 0.f, 0.f, 0.f));
+  } else {
+#pragma unroll
+    for (int k = 0; k < kNB / 2; ++k) sts_f32x2(x.s_dr + 8 * k, 0.f, 0.f);
+  }
 
   float colacc[G], df = 0.f;
 #pragma unroll
@@ -425,6 +446,7 @@ __device__ __forceinline__ void bwd_row_gridprod(const BwdRowsParams& p, const R
       stg_256(p.ws_dt + w0 + cc * 16, dk);
     }
   }
+  columns_done(x);
   // The cls query row gathers ONE bucket for every key, i.e. adds a constant to its logits: its exact
   // contribution to dR is sum_j dT[0, j] = 0.  What a flash-style backward would add instead is the
   // rounding residual of delta = dO . O (bf16 O), scaled by the cls row's large gradient in DeiT - so
@@ -531,6 +553,7 @@ attn_bwd_rows_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
   uint64_t* bar_abs = bars + 6;              // MMA -> rows: PBabs / dRabs ready (tensor-core structured mode)
   uint64_t* bar_p2 = bars + 7;               // rows -> MMA: packed dR written
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+  uint64_t* bar_cols = bars + 9;             // rows -> MMA: packed dT written (register-arithmetic paths)
   // overlays: PB (128 x 64 fp32, each row rotated by 2*row) over sQ|sdO ; dR (128 x 65 fp32) over sV|sTV
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -552,6 +575,7 @@ attn_bwd_rows_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
     mbar_init(bar_o, 1);
     mbar_init(bar_abs, 1);
     mbar_init(bar_p2, kRowThreads);
+    mbar_init(bar_cols, kRowThreads);
     fence_mbar_init();
   }
   if (warp == 0) tmem_alloc<512>(tmem_slot);
@@ -624,12 +648,23 @@ attn_bwd_rows_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
       umma_commit(bar_s);
       ROWS_TRACE(2);
 
-      mbar_wait(bar_p, 0);
-      tc_fence_after();
-      ROWS_TRACE(3);
       const uint32_t id_o = umma_idesc_bf16(128, kD, 0, 1);
       const int ksteps = (Npad + (p.ctx_k ? kNB : 0)) / 16;
       const int nk = Npad / 16;
+      auto dq_step = [&](int k) {   // dQ (+)= [dT | dR] [K ; TK], one K = 16 step
+        // structured paths: the packed dT of keys >= 112 sits in the spare columns (see bwd_row_af / bwd_row_gridprod)
+        const bool hi_part = (p.af_grid != 0 || p.gp_grid != 0) && k >= kAfSplitCols / 16 && k < nk;
+        const uint32_t a_col = hi_part ? kDtHiCol + 8 * (k - kAfSplitCols / 16) : 8 * k;
+        umma_ts(tmem + 192, tmem + a_col, umma_smem_desc_sw128(aK + k * 2048, 8192, 1024), id_o, k > 0);
+      };
+      if (!p.af_mma) {
+        mbar_wait(bar_cols, 0);     // every row thread has packed its dT: the key part runs under the bucket-sum tail
+        tc_fence_after();
+        for (int k = 0; k < nk; ++k) dq_step(k);
+      }
+      mbar_wait(bar_p, 0);
+      tc_fence_after();
+      ROWS_TRACE(3);
       if (p.af_mma) {
         const uint32_t id_abs = umma_idesc_bf16(128, kFeat, 0, 0);
         for (int k = 0; k < nk; ++k) {            // dQ = dT . K  (the table part follows the un-shifted dR)
@@ -649,12 +684,7 @@ attn_bwd_rows_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
         for (int k = nk; k < ksteps; ++k)         // dQ += dR . TK
           umma_ts(tmem + 192, tmem + kDrPackCol + 8 * (k - nk), umma_smem_desc_sw128(aK + k * 2048, 8192, 1024), id_o, 1u);
       } else {
-        for (int k = 0; k < ksteps; ++k) {  // dQ = [dT | dR] [K ; TK]
-          // structured paths: the packed dT of keys >= 112 sits in the spare columns (see bwd_row_af / bwd_row_gridprod)
-          const bool hi_part = (p.af_grid != 0 || p.gp_grid != 0) && k >= kAfSplitCols / 16 && k < nk;
-          const uint32_t a_col = hi_part ? kDtHiCol + 8 * (k - kAfSplitCols / 16) : 8 * k;
-          umma_ts(tmem + 192, tmem + a_col, umma_smem_desc_sw128(aK + k * 2048, 8192, 1024), id_o, k > 0);
-        }
+        for (int k = nk; k < ksteps; ++k) dq_step(k);   // the table part, behind the packed dR
       }
       umma_commit(bar_o);
     }
@@ -677,6 +707,7 @@ attn_bwd_rows_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
     x.drow = p.dense ? p.dense + b * p.dense_sb + head * p.dense_sh + x.row_c * p.dense_si : nullptr;
     x.ddrow = p.ddense ? p.ddense + ((static_cast<int64_t>(b) * p.H + head) * p.N + x.row_c) * p.N : nullptr;
     x.sw = (2 * r_local) & 63;
+    x.bar_cols = bar_cols;
 
     const int tslot = threadIdx.x == 32 ? 8 : (threadIdx.x == 160 ? 24 : -1);
 #define RT(k) do { if (tslot >= 0) ROWS_TRACE(tslot + (k)); } while (0)
@@ -706,20 +737,25 @@ attn_bwd_rows_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
       RT(1);
       {
         const int c = half;                      // each thread of the pair stages 32 of the 64 buckets
-        uint32_t raw[32];
+        uint32_t raw_r[32], raw_g[32];
+        if (p.ctx_k) tmem_ld32(x.trow + c * 32, raw_r);
+        if (p.ctx_v) tmem_ld32(x.trow + 64 + c * 32, raw_g);
+        tmem_ld_wait();
+        if (!p.af_mma) {
+          // R / dPB are in registers: the T = Q K^T MMAs may overwrite their columns while the values are staged
+          tc_fence_before();
+          mbar_arrive(bar_rfree);
+        }
         if (p.ctx_k) {
-          tmem_ld32(x.trow + c * 32, raw);
-          tmem_ld_wait();
-#pragma unroll
           const float rs = p.af_mma ? 1.0f : p.scale;   // tensor-core mode adds the UNSCALED term into T
 #pragma unroll
-          for (int i = 0; i < 32; ++i) sts_f32(x.s_r + 4 * (c * 32 + i), rs * __uint_as_float(raw[i]));
+          for (int i = 0; i < 16; ++i)
+            sts_f32x2(x.s_r + 4 * (c * 32 + 2 * i), rs * __uint_as_float(raw_r[2 * i]), rs * __uint_as_float(raw_r[2 * i + 1]));
         }
         if (p.ctx_v) {
-          tmem_ld32(x.trow + 64 + c * 32, raw);
-          tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < 32; ++i) sts_f32(x.s_dpb + 4 * (c * 32 + i), __uint_as_float(raw[i]));
+          for (int i = 0; i < 16; ++i)
+            sts_f32x2(x.s_dpb + 4 * (c * 32 + 2 * i), __uint_as_float(raw_g[2 * i]), __uint_as_float(raw_g[2 * i + 1]));
         }
       }
       if (p.af_mma) {
@@ -755,8 +791,6 @@ attn_bwd_rows_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
         tc_fence_before();
         mbar_arrive(bar_rfree);
       } else {
-        tc_fence_before();
-        mbar_arrive(bar_rfree);
         rows_barrier();                          // both halves of R / dPB staged before anyone gathers
       }
     }
@@ -819,8 +853,9 @@ attn_bwd_rows_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
 #pragma unroll
       for (int k = 0; k < 16; ++k) {
         const int b0 = c * 32 + 2 * k;
-        const float q0 = lds_f32(x.s_pb + 4 * ((b0 + x.sw) & 63)), q1 = lds_f32(x.s_pb + 4 * (((b0 + 1) + x.sw) & 63));
-        const float r0 = lds_f32(x.s_dr + 4 * b0), r1 = lds_f32(x.s_dr + 4 * (b0 + 1));
+        // b0 and the rotation are even: the pair (b0, b0 + 1) is adjacent and 8-byte aligned in both rows
+        const float2 qq = lds_f32x2(x.s_pb + 4 * ((b0 + x.sw) & 63)), rr = lds_f32x2(x.s_dr + 4 * b0);
+        const float q0 = qq.x, q1 = qq.y, r0 = rr.x, r1 = rr.y;
         if (p.gp_grid != 0) {          // grid-product path: the two halves' dR rows; no value-side bucket sums
           pk[k] = 0u;
           dk[k] = pack_bf16x2(q0 + r0, q1 + r1);

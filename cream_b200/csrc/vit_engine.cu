@@ -224,6 +224,29 @@ int side_bias_grad(cudaStream_t s, Bf16Mat dy, int64_t rows, int cols, float* db
   return bias_grad(ss.st, dy, rows, cols, dbias);
 }
 
+// The weight-gradient GEMMs are leaves too.  CREAM_SIDE_WGRAD=1 issues them on the side stream as well, so that
+// their CTAs can take the SMs a main-chain kernel leaves idle in its last wave (both are one-CTA-per-SM kernels: the
+// work is conserved, only the tails are filled).  Off by default; see DESIGN.md section 6 for the measurement.
+bool side_wgrad_enabled() {
+  static const bool on = []() { const char* e = getenv("CREAM_SIDE_WGRAD"); return e != nullptr && e[0] == '1'; }();
+  return on;
+}
+
+cudaStream_t side_fork(cudaStream_t s) {     // the side stream, ordered after everything enqueued on `s` so far
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) return s;
+  SideStream& ss = t_side[dev];
+  if (ss.st == nullptr) {
+    if (cudaStreamCreateWithFlags(&ss.st, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ss.fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ss.join, cudaEventDisableTiming) != cudaSuccess)
+      return s;
+  }
+  if (cudaEventRecord(ss.fork, s) != cudaSuccess || cudaStreamWaitEvent(ss.st, ss.fork, 0) != cudaSuccess) return s;
+  ss.pending = true;
+  return ss.st;
+}
+
 int side_join(cudaStream_t s) {
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) return CREAM_OK;
@@ -403,16 +426,18 @@ extern "C" int cream_vit_bwd(const cream_vit_desc* d, int first_stage, int last_
     // ---- FFN branch: x2 = x1 + s * fc2(gelu(fc1(ln2))) ----
     // (b.dy_bf = bf16(DropPath scale * g) and the fc2 bias gradient were produced by the LayerNorm
     //  backward of the previous stage)
-    VIT_TRY(linear_wgrad(s, M, E, ffn, b.dy_bf, l.act, p.g_wfc2, d->ld_gfc2));
+    const bool sw = side_wgrad_enabled();
+    VIT_TRY(linear_wgrad(sw ? side_fork(s) : s, M, E, ffn, b.dy_bf, l.act, p.g_wfc2, d->ld_gfc2));
     VIT_TRY(linear_dgrad(s, M, E, ffn, b.dy_bf, p.wfc2, d->ld_wfc2, CREAM_EPI_BF16_DGELU, b.dh, l.hpre.p, l.hpre.ld));
     if (p.g_bfc1) VIT_TRY(side_bias_grad(s, b.dh, M, ffn, p.g_bfc1));
-    VIT_TRY(linear_wgrad(s, M, ffn, E, b.dh, l.ln2, p.g_wfc1, d->ld_gfc1));
+    VIT_TRY(linear_wgrad(sw ? side_fork(s) : s, M, ffn, E, b.dh, l.ln2, p.g_wfc1, d->ld_gfc1));
     VIT_TRY(linear_dgrad(s, M, ffn, E, b.dh, p.wfc1, d->ld_wfc1, CREAM_EPI_BF16, b.dln));
+    if (sw) VIT_TRY(side_join(s));   // the side-stream weight gradients have read dy_bf (rewritten below)
     ++t_launches;   // ffn_layer_norm backward (+ residual gradient) -> g1, its bf16 DropPath-scaled copy, proj bias gradient
     VIT_TRY(cream_layernorm_bwd_cast(b.dln.p, b.dln.ld, 0, l.x1.p, l.x1.ld, p.ln2_g, l.mu2, l.rs2, g.p, g.ld, g1.p, g1.ld,
                                      p.g_ln2_g, p.g_ln2_b, M, E, b.dy_bf.p, b.dy_bf.ld, p.dp_scale, d->N, p.g_bproj, s));
     // ---- attention branch: x1 = x + s * proj(attn(qkv(ln1))) ----
-    VIT_TRY(linear_wgrad(s, M, E, qd, b.dy_bf, l.att, p.g_wproj, d->ld_gproj));
+    VIT_TRY(linear_wgrad(sw ? side_fork(s) : s, M, E, qd, b.dy_bf, l.att, p.g_wproj, d->ld_gproj));
     VIT_TRY(linear_dgrad(s, M, E, qd, b.dy_bf, p.wproj, d->ld_wproj, CREAM_EPI_BF16, b.datt));
     {
       cream_attn_desc at;
@@ -434,7 +459,7 @@ extern "C" int cream_vit_bwd(const cream_vit_desc* d, int first_stage, int last_
       a.g.epi = CREAM_EPI_F32_ATOMIC; a.g.out = p.g_wqkv; a.g.ldo = d->ld_gqkv;
       if (d->qkv_interleaved) { a.g.out_row_mul = 3; a.g.out_g_row = 1; }
       else { a.g.out_row_mul = 1; a.g.out_g_row = d->qkv_group_rows; }
-      VIT_TRY(run_gemm(a.g, s));
+      VIT_TRY(run_gemm(a.g, sw ? side_fork(s) : s));
     }
     {   // dln1 = dqkv Wqkv: contraction over the three row blocks of the shadow
       GemmArgs a;

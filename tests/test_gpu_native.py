@@ -251,8 +251,11 @@ def test_deit_trainer_step_runs_and_learns():
 
 def test_staged_host_batches_give_the_same_steps_as_resident_ones():
     """BatchStager: batches copied from pinned host memory on the side stream, two slots reused over 5 steps,
-    must produce the same losses as the same batches resident on the device (DropPath off; the split-K weight
-    gradients reduce in a run-dependent order, hence a 2e-4 band instead of bit equality)."""
+    must produce the same losses as the same batches resident on the device (DropPath off).  The split-K weight
+    gradients and the table-gradient bulk reduces add in a run-dependent order, so two runs of the SAME arm already
+    differ by up to 2.3e-4 after five steps at lr 1e-3 (scripts/repeat_staged_test.py, profiles/r02_staged_spread.log):
+    the band is 1e-3, an order of magnitude below what a stale or torn batch would produce (the three batches have
+    different labels, losses differ in the first digit)."""
     from cream_b200.deit import DeitIrpe, DeitTrainer
     g = torch.Generator().manual_seed(3)
     host = [(torch.randn(4, 3, 224, 224, generator=g).pin_memory(), torch.randint(0, 1000, (4,), generator=g).pin_memory())
@@ -275,7 +278,7 @@ def test_staged_host_batches_give_the_same_steps_as_resident_ones():
                 loss = tr.step(x.cuda(), y.cuda())
             out.append(float(loss))
         losses.append(out)
-    assert np.allclose(losses[0], losses[1], rtol=2e-4, atol=0), losses
+    assert np.allclose(losses[0], losses[1], rtol=1e-3, atol=0), losses
 
 
 # ------------------------------------------------------------------------------------------------
