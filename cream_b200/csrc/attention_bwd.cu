@@ -51,6 +51,7 @@ struct BwdRowsParams {
   __nv_bfloat16* ws_p; __nv_bfloat16* ws_dt;  // (B*H*N, ldw)
   float* dbias;
   int wide_out;                        // dqkv rows are 32-byte aligned: 256-bit stores
+  int stage;                           // structured paths: [P | PB] / [dT | dR] leave through per-warp staging tiles + TMA stores
   const float* dense; int64_t dense_sb, dense_sh, dense_si;   // dense additive logit term (generic path)
   float* ddense;                                              // (B,H,N,N) fp32: dS, or NULL
   long long* trace;   // CREAM_TRACE builds only
@@ -66,6 +67,13 @@ struct BwdRowsParams {
 
 __device__ __forceinline__ void rows_barrier() { asm volatile("bar.sync 2, %0;" ::"n"(kRowThreads) : "memory"); }
 
+#ifndef CREAM_ABL
+#define CREAM_ABL 0      // timing ablations (debug builds only; results are wrong when non-zero)
+#endif
+constexpr int kAfSplitCols = 112;                 // keys owned by the first thread of a row
+constexpr int kAfSplitRows = 8;                   // = kAfSplitCols / 14 grid rows
+constexpr int kDtHiCol = 464;                     // TMEM columns [464, 512): packed dT of the second half
+
 struct RowCtx {
   const float* drow;    // this row of the dense additive logit term, or NULL
   float* ddrow;         // this row of its gradient, or NULL
@@ -77,7 +85,55 @@ struct RowCtx {
   float delta, lsel;
   int64_t wrow;
   uint64_t* bar_cols;   // rows -> MMA: this thread's packed dT is in TMEM (the dT . K part of dQ may start)
+  // workspace staging (structured paths): this WARP's two tiles of 32 rows x 64 bytes (P at +0, dT at +2048),
+  // SWIZZLE_64B layout, written row-per-lane and stored by TMA (rows >= N are clipped by the tensor map)
+  uint32_t s_stage;
+  int stage, lane, row0, bh;
+  const CUtensorMap* map_sp; const CUtensorMap* map_sd;
 };
+
+// The workspace rows are 544 bytes apart, so a thread that owns a row can only ever write 32 contiguous bytes of it per
+// store: 32 cache lines per warp instruction.  Measured (timing ablation, profiles/r02_README.md): those stores were
+// 13 % of the backward.  Instead two consecutive 16-key chunks (64 bytes per row) of P and of dT are written to the
+// warp's staging tiles - 16-byte chunk c of row r at chunk c ^ ((r >> 1) & 3), the layout CU_TENSOR_MAP_SWIZZLE_64B
+// reads back, conflict-free for a row-per-lane writer - and ONE elected lane hands each tile to the TMA engine.
+__device__ __forceinline__ void stage_wait_free(const RowCtx& x) {       // the previous TMA stores have read the tiles
+  if (x.lane == 0) bulk_wait_read<0>();
+  __syncwarp();
+}
+__device__ __forceinline__ void stage_put32(const RowCtx& x, int half_of_row, const uint32_t (&pk)[8], const uint32_t (&dk)[8]) {
+  const uint32_t rowb = x.s_stage + x.lane * 64;
+  const uint32_t sw = (static_cast<uint32_t>(x.lane) >> 1) & 3u;
+  const uint32_t c0 = ((2u * half_of_row) ^ sw) << 4, c1 = ((2u * half_of_row + 1u) ^ sw) << 4;
+  sts_u32x4s(rowb + c0, pk[0], pk[1], pk[2], pk[3]);
+  sts_u32x4s(rowb + c1, pk[4], pk[5], pk[6], pk[7]);
+  sts_u32x4s(rowb + 2048 + c0, dk[0], dk[1], dk[2], dk[3]);
+  sts_u32x4s(rowb + 2048 + c1, dk[4], dk[5], dk[6], dk[7]);
+}
+__device__ __forceinline__ void stage_store(const RowCtx& x, int col) {   // both tiles -> workspace columns [col, col + 32)
+  fence_proxy_async_smem();
+  __syncwarp();
+  if (x.lane == 0) {
+    tma_store_3d_s(x.map_sp, x.s_stage, col, x.row0, x.bh);
+    tma_store_3d_s(x.map_sd, x.s_stage + 2048, col, x.row0, x.bh);
+    bulk_commit();
+  }
+}
+// One 16-key chunk of a structured path: pairs of chunks (cc even, cc + 1) go through the staging tiles; the odd
+// seventh chunk of the first half of a row is written directly.
+// (cc is a compile-time constant at every call site: the column loops are fully unrolled.)
+__device__ __forceinline__ void emit_chunk(const BwdRowsParams& p, const RowCtx& x, int cc, int hi, bool live, int64_t w0,
+                                           const uint32_t (&pk)[8], const uint32_t (&dk)[8]) {
+  if (CREAM_ABL & 1) return;
+  if (x.stage && cc < 6) {
+    if ((cc & 1) == 0 && cc >= 2) stage_wait_free(x);
+    stage_put32(x, cc & 1, pk, dk);
+    if (cc & 1) stage_store(x, kAfSplitCols * hi + (cc - 1) * 16);
+  } else if (live) {
+    stg_256(p.ws_p + w0 + cc * 16, pk);     // 16 keys = 32 bytes of this row, one 256-bit store each
+    stg_256(p.ws_dt + w0 + cc * 16, dk);
+  }
+}
 
 // Called by every row thread once its share of the packed dT has been written to TMEM: the tensor core starts
 // dQ = dT . K while the bucket sums are still being folded and packed (dR . TK is added after that).
@@ -169,12 +225,6 @@ __device__ __forceinline__ void bwd_row_generic(const BwdRowsParams& p, const Ro
 // unrolled code on "local" grid rows 0..7 with their own operand registers (the kernel is
 // instruction-fetch bound: one shared stream halves its footprint).  The only asymmetric element
 // is local key 0: the cls key for half 0, grid position (7, 13) for half 1.
-#ifndef CREAM_ABL
-#define CREAM_ABL 0      // timing ablations (debug builds only; results are wrong when non-zero)
-#endif
-constexpr int kAfSplitCols = 112;                 // keys owned by the first thread of a row
-constexpr int kAfSplitRows = 8;                   // = kAfSplitCols / 14 grid rows
-constexpr int kDtHiCol = 464;                     // TMEM columns [464, 512): packed dT of the second half
 
 template <int G>
 __device__ __forceinline__ void bwd_row_af(const BwdRowsParams& p, const RowCtx& x) {
@@ -274,10 +324,7 @@ __device__ __forceinline__ void bwd_row_af(const BwdRowsParams& p, const RowCtx&
       dk[k] = pack_bf16x2(dt[2 * k], dt[2 * k + 1]);
     }
     tmem_st8(t_out + cc * 8, dk);     // half 0: over T columns it has already read; half 1: spare columns
-    if (live && !(CREAM_ABL & 1)) {
-      stg_256(p.ws_p + w0 + cc * 16, pk);     // 16 keys = 32 bytes of this row, one 256-bit store each
-      stg_256(p.ws_dt + w0 + cc * 16, dk);
-    }
+    emit_chunk(p, x, cc, hi, live, w0, pk, dk);
   }
   columns_done(x);
   // this thread's share of the row totals (every key hits exactly one vertical bucket)
@@ -441,10 +488,7 @@ __device__ __forceinline__ void bwd_row_gridprod(const BwdRowsParams& p, const R
       dk[k] = pack_bf16x2(dt[2 * k], dt[2 * k + 1]);
     }
     tmem_st8(t_out + cc * 8, dk);
-    if (live) {
-      stg_256(p.ws_p + w0 + cc * 16, pk);     // 16 keys = 32 bytes of this row, one 256-bit store each
-      stg_256(p.ws_dt + w0 + cc * 16, dk);
-    }
+    emit_chunk(p, x, cc, hi, live, w0, pk, dk);
   }
   columns_done(x);
   // The cls query row gathers ONE bucket for every key, i.e. adds a constant to its logits: its exact
@@ -523,6 +567,7 @@ __global__ void __launch_bounds__(kRowsThreads, 1)
 attn_bwd_rows_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_kv,
                      const __grid_constant__ CUtensorMap map_do, const __grid_constant__ CUtensorMap map_o,
                      const __grid_constant__ CUtensorMap map_tk, const __grid_constant__ CUtensorMap map_tv,
+                     const __grid_constant__ CUtensorMap map_sp, const __grid_constant__ CUtensorMap map_sd,
                      const BwdRowsParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   require_smem_alignment(smem);
@@ -554,6 +599,9 @@ attn_bwd_rows_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
   uint64_t* bar_p2 = bars + 7;               // rows -> MMA: packed dR written
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
   uint64_t* bar_cols = bars + 9;             // rows -> MMA: packed dT written (register-arithmetic paths)
+  // workspace staging tiles (p.stage): 4 KB per row warp; the first four warps reuse sO (dead once delta is known),
+  // the other four a 16 KB region behind the barriers
+  uint8_t* sStage = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(bars + 16) + 1023) & ~static_cast<uintptr_t>(1023));
   // overlays: PB (128 x 64 fp32, each row rotated by 2*row) over sQ|sdO ; dR (128 x 65 fp32) over sV|sTV
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -708,6 +756,13 @@ attn_bwd_rows_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
     x.ddrow = p.ddense ? p.ddense + ((static_cast<int64_t>(b) * p.H + head) * p.N + x.row_c) * p.N : nullptr;
     x.sw = (2 * r_local) & 63;
     x.bar_cols = bar_cols;
+    x.stage = p.stage;
+    x.lane = lane;
+    x.row0 = m0 + quarter * 32;
+    x.bh = b * p.H + head;
+    x.map_sp = &map_sp;
+    x.map_sd = &map_sd;
+    x.s_stage = half == 0 ? smem_u32(sO) + quarter * 4096 : smem_u32(sStage) + quarter * 4096;
 
     const int tslot = threadIdx.x == 32 ? 8 : (threadIdx.x == 160 ? 24 : -1);
 #define RT(k) do { if (tslot >= 0) ROWS_TRACE(tslot + (k)); } while (0)
@@ -865,7 +920,19 @@ attn_bwd_rows_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
         }
       }
       if (p.ctx_k) tmem_st16(x.trow + (p.af_mma ? kDrPackCol : Npad / 2) + c * 16, dk);
-      if (row < p.N && !(CREAM_ABL & 2)) {
+      if (p.stage && !(CREAM_ABL & 2)) {
+        // this thread's 32 buckets = 64 bytes = one full row of the warp's tiles: workspace columns [Npad + 32 c, + 32)
+        stage_wait_free(x);
+        const uint32_t rowb = x.s_stage + lane * 64;
+        const uint32_t sw4 = (static_cast<uint32_t>(lane) >> 1) & 3u;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const uint32_t off = (static_cast<uint32_t>(q) ^ sw4) << 4;
+          sts_u32x4s(rowb + off, pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+          sts_u32x4s(rowb + 2048 + off, dk[4 * q], dk[4 * q + 1], dk[4 * q + 2], dk[4 * q + 3]);
+        }
+        stage_store(x, Npad + c * 32);
+      } else if (row < p.N && !(CREAM_ABL & 2)) {
         __nv_bfloat16* wp = p.ws_p + x.wrow + Npad + c * 32;
         __nv_bfloat16* wd = p.ws_dt + x.wrow + Npad + c * 32;
 #pragma unroll
@@ -895,6 +962,7 @@ attn_bwd_rows_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
       tmem_ld_wait();
       if (row < p.N && !(CREAM_ABL & 2)) store_row32_bf16(qrow + c * 32, raw, p.scale, p.wide_out != 0);
     }
+    if (p.stage && lane == 0) bulk_wait_all();   // this warp's TMA stores have completed (tiles read, writes performed)
   }
 
   tc_fence_before();
@@ -1165,7 +1233,15 @@ extern "C" int cream_attn_bwd(const cream_attn_desc* d, void* stream_) {
   const uint64_t wstrides[3] = {1, static_cast<uint64_t>(ldw), static_cast<uint64_t>(d->N) * ldw};
   const CUtensorMap* mwp = get_tensor_map(ws_p, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, wdims, wstrides, box_64, CU_TENSOR_MAP_SWIZZLE_128B);
   const CUtensorMap* mwd = get_tensor_map(ws_dt, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, wdims, wstrides, box_64, CU_TENSOR_MAP_SWIZZLE_128B);
-  if (!mq || !mkv || !mq64 || !mdo || !mdo64 || !mo || !mtk || !mtv || !mwp || !mwd) return CREAM_ERR_CUDA;
+  // store-side maps of the workspace: 32 columns (64 bytes) x 32 rows per box, SWIZZLE_64B (the rows kernel's staging tiles)
+  const uint32_t box_st[3] = {32, 32, 1};
+  const CUtensorMap* msp = get_tensor_map(ws_p, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, wdims, wstrides, box_st, CU_TENSOR_MAP_SWIZZLE_64B);
+  const CUtensorMap* msd = get_tensor_map(ws_dt, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, wdims, wstrides, box_st, CU_TENSOR_MAP_SWIZZLE_64B);
+  if (!mq || !mkv || !mq64 || !mdo || !mdo64 || !mo || !mtk || !mtv || !mwp || !mwd || !msp || !msd) return CREAM_ERR_CUDA;
+  {
+    static const bool stage_on = []() { const char* e = getenv("CREAM_BWD_STAGE"); return e != nullptr && e[0] == '1'; }();   // measured slower: off unless asked for
+    p.stage = (stage_on && (p.af_grid != 0 || p.gp_grid != 0) && !p.af_mma) ? 1 : 0;
+  }
 
   static bool attr_set = false;
   if (!attr_set) {
@@ -1174,7 +1250,8 @@ extern "C" int cream_attn_bwd(const cream_attn_desc* d, void* stream_) {
     attr_set = true;
   }
   const size_t smem_rows = 3 * 16384 + static_cast<size_t>(Npad) * 128 + 8192 +
-                           std::max<size_t>(Npad * 128, 26 * 1024) + 8192 + 2 * 128 * kStride * 4 + 4 * kIndChunk + 2 * 64 * 4 + 64 + 128;
+                           std::max<size_t>(Npad * 128, 26 * 1024) + 8192 + 2 * 128 * kStride * 4 + 4 * kIndChunk + 2 * 64 * 4 + 64 + 128 +
+                           (p.stage ? 1024 + 4 * 4096 : 0);   // + the second half's staging tiles, 1024-aligned
   CB_REQUIRE(smem_rows <= 227 * 1024, "shared memory budget");
   dim3 grid(ceil_div(d->N, 128), d->H, d->B);
 #ifdef CREAM_TRACE
@@ -1185,7 +1262,7 @@ extern "C" int cream_attn_bwd(const cream_attn_desc* d, void* stream_) {
     p.trace = trace_dev;
   }
 #endif
-  CB_CUDA_OK(launch_chain(attn_bwd_rows_kernel, grid, dim3(kRowsThreads), smem_rows, stream, 1, *mq, *mkv, *mdo, *mo, *mtk, *mtv, p));
+  CB_CUDA_OK(launch_chain(attn_bwd_rows_kernel, grid, dim3(kRowsThreads), smem_rows, stream, 1, *mq, *mkv, *mdo, *mo, *mtk, *mtv, *msp, *msd, p));
   int rc = check_last("attn_bwd_rows_kernel");
   if (rc) return rc;
 #ifdef CREAM_TRACE

@@ -129,6 +129,13 @@ __device__ __forceinline__ void bulk_load_1d(void* smem_dst, const void* gsrc, u
 }
 
 // bulk async-group completion (TMA stores / reduces issued by one thread)
+// TMA store of one box from shared memory (bulk async-group completion); `smem_addr` is a shared-space address.
+__device__ __forceinline__ void tma_store_3d_s(const CUtensorMap* m, uint32_t smem_addr, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(m)),
+               "r"(smem_addr), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void bulk_wait_read() {
