@@ -507,7 +507,7 @@ def bench_clip(args):
     W, K, B = max(3, args.warmup), args.steps, args.batch or conf["batch"]
     torch.manual_seed(0)
     net = clip.CLIP(clip.VIT_B_32["embed_dim"], clip.VIT_B_32["vision_cfg"], clip.VIT_B_32["text_cfg"]).to(dev).train()
-    tr = clip.ClipTrainer(net)
+    tr = clip.ClipTrainer(net, graph=(world == 1 and not args.no_graph))   # fixed configuration: one captured CUDA graph per step
     n_host = 4
     host_imgs, host_txts = _clip_batches(B, n_host, 1234 + rank)
     dev_imgs, dev_txts = [t.to(dev) for t in host_imgs], [t.to(dev) for t in host_txts]
@@ -551,7 +551,7 @@ def bench_clip(args):
     # per-kernel-class times of one step (python sequencing -> ops.PROFILE brackets every launch)
     from cream_b200 import ops
     ops.PROFILE = []
-    tr.step(dev_imgs[0], dev_txts[0])
+    tr._step_eager(dev_imgs[0], dev_txts[0])      # eager: every launch bracketed (the timed regions replay the graph)
     torch.cuda.synchronize()
     by_kind = {}
     for kind, a, b, fl, by in ops.PROFILE:
@@ -609,7 +609,9 @@ def bench_clip(args):
             "data": "synthetic",
             "config": {"workload": conf["workload"], "baseline_config": "c4", "global_batch": B * world, "per_gpu_batch": B,
                        "parallelism": f"dp{world}", "l2": "activations per step (> 3 GB) exceed the 126 MB L2; 4 rotating batches",
-                       "engine": "python sequencing of the C-ABI launches (one autograd node per tower)"},
+                       "engine": ("one CUDA graph per step (captured from the python sequencing of the C-ABI launches, replayed)"
+                                  if getattr(tr, "_graph", None) is not None else
+                                  "python sequencing of the C-ABI launches (one autograd node per tower)")},
             "e2e": {"value": pairs / (ms_e2e * 1e-3), "unit": UNIT,
                     "h2d_bytes_per_step": world * (B * 3 * 224 * 224 * 4 + B * 77 * 8), "d2h_bytes_per_step": 4 * world,
                     "ms_per_step": ms_e2e / K, "last_loss": last_loss},
@@ -652,6 +654,7 @@ def main():
                     help="gradient all-reduce collectives per step at N > 1: 1 = one after the backward, k = k-1 "
                          "overlapped + one after, 0 = one per layer (round-1 schedule)")
     ap.add_argument("--python-engine", action="store_true", help="sequence the kernels from Python (cross-check)")
+    ap.add_argument("--no-graph", action="store_true", help="c4: run the step eagerly instead of replaying its CUDA graph")
     ap.add_argument("--quick", action="store_true",
                     help="A/B runs (c3 / c5): the two timed regions only - no per-kernel pass, no reference legs")
     args = ap.parse_args()

@@ -500,23 +500,28 @@ class ClipTrainer:
     (train.py:525-530)."""
 
     def __init__(self, model: CLIP, lr=5e-4, betas=(0.9, 0.98), eps=1e-6, weight_decay=0.2, local_loss=True,
-                 gather_with_grad=True):
+                 gather_with_grad=True, graph=False):
+        """graph=True (single process): the whole step - both towers, loss, backward, AdamW, logit-scale clamp,
+        ~6000 launches - is captured ONCE in a CUDA graph and replayed; the configuration is fixed, so unlike the
+        supernet (a new subnet every step) nothing about the launch sequence changes from step to step."""
         self.model = model
         self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
         self.rank = dist.get_rank() if self.world > 1 else 0
         if self.world > 1:
             for p in model.parameters():
                 dist.broadcast(p.data, src=0)
+        self.use_graph = bool(graph) and self.world == 1
         named = list(model.named_parameters())
         skip = lambda n, p: p.ndim < 2 or "bn" in n or "ln" in n or "bias" in n or "logit_scale" in n
         self.opt = torch.optim.AdamW([
             dict(params=[p for n, p in named if skip(n, p)], weight_decay=0.0),
             dict(params=[p for n, p in named if not skip(n, p)], weight_decay=weight_decay)],
-            lr=lr, betas=betas, eps=eps, fused=True)
+            lr=lr, betas=betas, eps=eps, fused=True, capturable=self.use_graph)
         self.loss = ClipLoss(local_loss=local_loss, gather_with_grad=gather_with_grad, cache_labels=True,
                              rank=self.rank, world_size=self.world)
         self.params = [p for _, p in named]
         self.stager = None
+        self._graph = None
 
     def stage(self, images, texts):
         """Start the host -> device copy of the next batch on the side stream (staging.BatchStager)."""
@@ -525,17 +530,11 @@ class ClipTrainer:
             self.stager = BatchStager(self.params[0].device)
         return self.stager.stage(images, texts)
 
-    def step(self, images, texts=None):
-        """images: a batch tensor with `texts`, or the handle `stage` returned."""
-        staged = images if texts is None else None
-        if staged is not None:
-            images, texts = staged.acquire()
+    def _step_eager(self, images, texts):
         self.opt.zero_grad(set_to_none=True)
         fi, ft, scale = self.model(images, texts)
         loss = self.loss(fi, ft, scale)
         loss.backward()
-        if staged is not None:
-            staged.release()            # the text tower's backward reads the token ids once more
         if self.world > 1:
             average_gradients([p.grad for p in self.params if p.grad is not None], self.world)
         self.opt.step()
@@ -543,3 +542,56 @@ class ClipTrainer:
         with torch.no_grad():
             self.model.logit_scale.clamp_(0, math.log(100))
         return loss.detach()
+
+    def _capture(self, images, texts):
+        """Warm up (allocator pools, lazily set kernel attributes, optimizer state) WITHOUT advancing the training
+        state, then record one step.  Returns False (and leaves the trainer eager) if the capture is refused."""
+        self._g_images, self._g_texts = images.clone(), texts.clone()
+        keep = [p.detach().clone() for p in self.params]
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(2):
+                self._step_eager(self._g_images, self._g_texts)
+            with torch.no_grad():
+                for p, k in zip(self.params, keep):
+                    p.copy_(k)
+                for st in self.opt.state.values():      # moments and step counters back to a fresh optimizer
+                    for v in st.values():
+                        if torch.is_tensor(v):
+                            v.zero_()
+            ops.SHADOWS.invalidate()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        n0 = _lib.LAUNCHES[0]
+        try:
+            with torch.cuda.graph(graph):
+                self._g_loss = self._step_eager(self._g_images, self._g_texts)
+        except Exception as e:   # noqa: BLE001 - a refused capture must not take the training run down
+            import warnings
+            warnings.warn(f"cream_b200: CUDA-graph capture of the CLIP step failed ({e!r}); running eagerly")
+            self.use_graph = False
+            ops.SHADOWS.invalidate()
+            return False
+        self._graph_launches = _lib.LAUNCHES[0] - n0
+        self._graph = graph
+        return True
+
+    def step(self, images, texts=None):
+        """images: a batch tensor with `texts`, or the handle `stage` returned."""
+        staged = images if texts is None else None
+        if staged is not None:
+            images, texts = staged.acquire()
+        if self.use_graph and (self._graph is not None or self._capture(images, texts)):
+            self._g_images.copy_(images, non_blocking=True)
+            self._g_texts.copy_(texts, non_blocking=True)
+            if staged is not None:
+                staged.release()        # the slot has been copied into the graph's input buffers
+            self._graph.replay()
+            _lib.LAUNCHES[0] += self._graph_launches
+            return self._g_loss.clone()
+        loss = self._step_eager(images, texts)
+        if staged is not None:
+            staged.release()            # the text tower's backward reads the token ids once more
+        return loss

@@ -178,3 +178,23 @@ def test_contrastive_trainer_follows_the_reference_trajectory():
         # Adam normalises every element's step, so elements whose gradient is bf16 noise may step the
         # other way; the update as a whole must still agree with the fp32 reference's
         assert float((v - sd[k]).norm()) <= 0.5 * moved, (k, float((v - sd[k]).norm()), moved)
+
+
+def test_graph_replay_equals_the_eager_step():
+    """ClipTrainer(graph=True): the captured step replayed three times against the same three steps run eagerly from
+    the same initial weights - same losses and parameters up to the run-to-run re-association of the split-K reduces -
+    and the warm-up before the capture must not advance the training state."""
+    from cream_b200 import clip
+    cfg = SMALL
+    torch.manual_seed(0)
+    a = clip.CLIP(cfg["embed_dim"], cfg["vision_cfg"], cfg["text_cfg"]).cuda()
+    b = clip.CLIP(cfg["embed_dim"], cfg["vision_cfg"], cfg["text_cfg"]).cuda()
+    b.load_state_dict(a.state_dict())
+    ta, tb = clip.ClipTrainer(a, lr=1e-3, graph=True), clip.ClipTrainer(b, lr=1e-3)
+    for step in range(3):
+        images, text = _batch(cfg, 8, seed=40 + step)
+        la, lb = ta.step(images, text), tb.step(images, text)
+        assert abs(float(la) - float(lb)) <= 2e-3 * max(1.0, abs(float(lb))), (step, float(la), float(lb))
+    assert ta._graph is not None, "the capture was refused"
+    for (n, p), q in zip(a.named_parameters(), b.parameters()):
+        assert rel_err(p, q) < 2e-3, n
