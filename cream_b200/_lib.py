@@ -58,6 +58,7 @@ class AttnDesc(C.Structure):
         ("gp_grid", c_int), ("gp_w", c_int), ("gp_skip_id", c_int),
         ("gp_lut_a", C.c_uint8 * 32), ("gp_lut_b", C.c_uint8 * 32),
         ("causal", c_int),
+        ("block_len", c_int),
     ]
 
 

@@ -47,6 +47,16 @@ def block_names(prefix: str, i: int) -> List[str]:
 # ------------------------------------------------------------------------------------------------
 # transformer blocks (model.py:286-328: x += attn(ln_1(x)); x += mlp(ln_2(x)))
 # ------------------------------------------------------------------------------------------------
+def _attn_packing(B, N, causal):
+    """(batch, tokens, block_len) handed to the attention kernel.  Its query tile is 128 rows: with the image
+    tower's 50 tokens a tile would be 39 % full, so two batch items are passed as ONE 100-token sequence with
+    block-diagonal visibility (cream_attn_desc.block_len) - the token-major (B*N, .) buffers are unchanged.
+    The 77-token text tower does not fit twice into a tile and stays one item per tile."""
+    if B % 2 == 0 and 2 * N <= 128:
+        return B // 2, 2 * N, N
+    return B, N, 0
+
+
 def blocks_forward(P, prefix, layers, heads, x, B, N, causal, save):
     """x: (B*N, E) fp32 residual stream.  Returns (x_out, saved-per-block list)."""
     M, E = x.shape
@@ -55,11 +65,12 @@ def blocks_forward(P, prefix, layers, heads, x, B, N, causal, save):
     eps = 1e-5
     scale = HD ** -0.5
     saved = []
+    Ba, Na, blk = _attn_packing(B, N, causal)
     for i in range(layers):
         p = f"{prefix}resblocks.{i}."
         ln1, mu1, rs1 = ops.layernorm_fwd(x, P[p + "ln_1.weight"], P[p + "ln_1.bias"], eps, E, save_stats=save)
         qkv = ops.linear_fwd(ln1, sh.get(P[p + "attn.in_proj_weight"]), 3 * E, E, P[p + "attn.in_proj_bias"])
-        att, lse = ops.attention_fwd(qkv, B, heads, N, scale, causal=causal, need_lse=save)
+        att, lse = ops.attention_fwd(qkv, Ba, heads, Na, scale, causal=causal, need_lse=save, block=blk)
         x1 = ops.linear_fwd(att, sh.get(P[p + "attn.out_proj.weight"]), E, E, P[p + "attn.out_proj.bias"],
                             epi=EPI_F32_RESID, resid=x)
         ln2, mu2, rs2 = ops.layernorm_fwd(x1, P[p + "ln_2.weight"], P[p + "ln_2.bias"], eps, E, save_stats=save)
@@ -81,6 +92,7 @@ def blocks_backward(P, G, prefix, layers, heads, saved, g, B, N, causal):
     sh = ops.SHADOWS
     ffn = P[f"{prefix}resblocks.0.mlp.c_fc.weight"].shape[0]
     scale = HD ** -0.5
+    Ba, Na, blk = _attn_packing(B, N, causal)
     dy2 = None
     for i in reversed(range(layers)):
         p = f"{prefix}resblocks.{i}."
@@ -96,7 +108,7 @@ def blocks_backward(P, G, prefix, layers, heads, saved, g, B, N, causal):
                                          G[p + "ln_2.bias"], resid_grad=g, dbias=G[p + "attn.out_proj.bias"])
         ops.linear_wgrad(dy1, s["att"], E, E, G[p + "attn.out_proj.weight"])
         datt = ops.linear_dgrad(dy1, sh.get(P[p + "attn.out_proj.weight"]), E, E)
-        dqkv = ops.attention_bwd(s["qkv"], s["att"], s["lse"], datt, B, heads, N, scale, causal=causal)[0]
+        dqkv = ops.attention_bwd(s["qkv"], s["att"], s["lse"], datt, Ba, heads, Na, scale, causal=causal, block=blk)[0]
         ops.bias_grad(dqkv, G[p + "attn.in_proj_bias"])
         ops.linear_wgrad(dqkv, s["ln1"], 3 * E, E, G[p + "attn.in_proj_weight"])
         dln1 = ops.linear_dgrad(dqkv, sh.get(P[p + "attn.in_proj_weight"]), 3 * E, E)

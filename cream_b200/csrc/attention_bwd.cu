@@ -35,6 +35,7 @@ constexpr int kStride = 66;  // floats per row of the staged R / dPB / dR tiles 
 struct BwdRowsParams {
   int B, H, N, Npad, ldw;
   int causal;                          // generic path: key j > query i masked
+  int block_len;                       // generic path: block-diagonal attention over items of block_len tokens (0 = off)
   float scale;
   int ctx_k, ctx_v, shared_tables;
   int af_grid, af_max_rel;
@@ -154,6 +155,9 @@ __device__ __forceinline__ void bwd_row_generic(const BwdRowsParams& p, const Ro
   const uint8_t* ivb = p.idx_vb ? p.idx_vb + static_cast<int64_t>(x.row_c) * p.ldi : nullptr;
   const bool use_bias = p.bias != nullptr;
   const bool want_dr = p.ctx_k || use_bias;
+  int k_lo = 0, k_hi = x.row < p.N ? p.N : 0;      // visible keys of this row (see softmax_generic); none for padding rows
+  if (p.block_len > 0 && x.row < p.N) { k_lo = (x.row / p.block_len) * p.block_len; k_hi = k_lo + p.block_len; }
+  if (p.causal) k_hi = min(k_hi, x.row + 1);
   const int nchunks = Npad / 16;
   for (int c = 0; c < nchunks; ++c) {
     uint32_t rt[16], rp[16];
@@ -180,7 +184,7 @@ __device__ __forceinline__ void bwd_row_generic(const BwdRowsParams& p, const Ro
       if (use_bias) t += lds_f32(x.s_bias + 4 * a_id);
       if (x.drow != nullptr && c * 16 + k < p.N) t += __ldg(x.drow + c * 16 + k);
       float pr = fast_exp2(fmaf(t, kLog2e, -x.lsel));
-      if (c * 16 + k >= p.N || x.row >= p.N || (p.causal && c * 16 + k > x.row)) pr = 0.f;
+      if (c * 16 + k < k_lo || c * 16 + k >= k_hi) pr = 0.f;
       float dp = __uint_as_float(rp[k]);
       if (p.ctx_v) {
         if (iva) dp += lds_f32(x.s_dpb + 4 * va_id);
@@ -307,7 +311,8 @@ __device__ __forceinline__ void bwd_row_af(const BwdRowsParams& p, const RowCtx&
         pf = pr; df = d;
       } else {
         const int rj = (j0 - 1) / G, cj = (j0 - 1) % G;
-        pr = fast_exp2(fmaf(sl, __uint_as_float(rt[k]), rv[rj]) + rh[cj]);
+        pr = (CREAM_ABL & 8) ? fmaf(sl, __uint_as_float(rt[k]), rv[rj]) + rh[cj]
+                             : fast_exp2(fmaf(sl, __uint_as_float(rt[k]), rv[rj]) + rh[cj]);
         d = pr * (__uint_as_float(rp[k]) + gv[rj] + gh[cj]);
         if (!(CREAM_ABL & 4)) {
         prow[rj] += pr; pcol[cj] += pr;
@@ -323,7 +328,7 @@ __device__ __forceinline__ void bwd_row_af(const BwdRowsParams& p, const RowCtx&
       pk[k] = pack_bf16x2(pv[2 * k], pv[2 * k + 1]);
       dk[k] = pack_bf16x2(dt[2 * k], dt[2 * k + 1]);
     }
-    tmem_st8(t_out + cc * 8, dk);     // half 0: over T columns it has already read; half 1: spare columns
+    if (!(CREAM_ABL & 16)) tmem_st8(t_out + cc * 8, dk);     // half 0: over T columns it has already read; half 1: spare columns
     emit_chunk(p, x, cc, hi, live, w0, pk, dk);
   }
   columns_done(x);
@@ -1192,6 +1197,9 @@ extern "C" int cream_attn_bwd(const cream_attn_desc* d, void* stream_) {
   p.dense = d->dense_bias; p.dense_sb = d->dense_stride_b; p.dense_sh = d->dense_stride_h; p.dense_si = d->dense_stride_i;
   p.causal = d->causal;
   CB_REQUIRE(!d->causal || (d->af_grid == 0 && d->gp_grid == 0), "the causal mask runs on the generic gather path (no af / gp hint)");
+  p.block_len = d->block_len;
+  CB_REQUIRE(d->block_len >= 0 && (d->block_len == 0 || (d->N % d->block_len == 0 && d->af_grid == 0 && d->gp_grid == 0)),
+             "block_len must divide N; packed items run on the generic gather path");
   p.ddense = d->ddense;
   if (p.dense != nullptr || p.ddense != nullptr) p.af_grid = 0;   // generic gather path only
   if (p.af_grid != 0) {

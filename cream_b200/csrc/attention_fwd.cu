@@ -49,6 +49,7 @@ struct AttnFwdParams {
   const float* bias;                   // (H or 1, 64) pre-packed bias table, gathered by idx_a
   const float* dense; int64_t dense_sb, dense_sh, dense_si;   // dense additive logit term (generic path)
   int causal;                          // generic path: key j > query i masked
+  int block_len;                       // generic path: block-diagonal attention over items of block_len tokens (0 = off)
   __nv_bfloat16* out; int64_t ldo;     // (B*N, H*64)
   int wide_out;                        // out rows are 32-byte aligned: 256-bit stores
   float* lse;                          // (B, H, N)
@@ -67,6 +68,10 @@ __device__ __forceinline__ void softmax_generic(const AttnFwdParams& p, uint32_t
   const uint8_t* ia = p.idx_a ? p.idx_a + static_cast<int64_t>(row_c) * p.ldi : nullptr;
   const uint8_t* ib = p.idx_b ? p.idx_b + static_cast<int64_t>(row_c) * p.ldi : nullptr;
   const bool use_bias = p.bias != nullptr;
+  // visible keys of this row: [k_lo, k_hi) - its own block when items are packed, up to itself under the causal mask
+  int k_lo = 0, k_hi = p.N;
+  if (p.block_len > 0) { k_lo = (row_c / p.block_len) * p.block_len; k_hi = k_lo + p.block_len; }
+  if (p.causal) k_hi = min(k_hi, row_c + 1);
   float mx = -INFINITY;
   for (int c = 0; c < nchunks; ++c) {
     uint32_t raw[16];
@@ -87,7 +92,7 @@ __device__ __forceinline__ void softmax_generic(const AttnFwdParams& p, uint32_t
       }
       if (use_bias) t += lds_f32(sbias + 4 * a_id);
       if (drow != nullptr && c * 16 + k < p.N) t += __ldg(drow + c * 16 + k);
-      if (c * 16 + k >= p.N || (p.causal && c * 16 + k > row_c)) t = -INFINITY;
+      if (c * 16 + k < k_lo || c * 16 + k >= k_hi) t = -INFINITY;
       mx = fmaxf(mx, t);
       raw[k] = __float_as_uint(t);
     }
@@ -693,6 +698,9 @@ extern "C" int cream_attn_fwd(const cream_attn_desc* d, void* stream_) {
   p.dense = d->dense_bias; p.dense_sb = d->dense_stride_b; p.dense_sh = d->dense_stride_h; p.dense_si = d->dense_stride_i;
   p.causal = d->causal;
   CB_REQUIRE(!d->causal || (d->af_grid == 0 && d->gp_grid == 0), "the causal mask runs on the generic gather path (no af / gp hint)");
+  p.block_len = d->block_len;
+  CB_REQUIRE(d->block_len >= 0 && (d->block_len == 0 || (d->N % d->block_len == 0 && d->af_grid == 0 && d->gp_grid == 0)),
+             "block_len must divide N; packed items run on the generic gather path");
   // structured AutoFormer gather: square grid + cls, both tables, clamp never binding
   if (d->af_grid > 0 && d->dense_bias == nullptr) {
     CB_REQUIRE(d->af_grid * d->af_grid + 1 == d->N && ctx_k && ctx_v && !d->bias_pack, "af mode needs N = g*g+1 and both table packs");

@@ -437,9 +437,11 @@ def _set_dense(d, dense, B, H, N):
     d.dense_stride_i = dense.stride(2)
 
 
-def _attn_desc(B, H, N, scale, qkv, tk, tv, per_head, idx, bias, af=None, gp=None, causal=False):
+def _attn_desc(B, H, N, scale, qkv, tk, tv, per_head, idx, bias, af=None, gp=None, causal=False, block=0):
     d = AttnDesc()
     d.causal = int(bool(causal))
+    d.block_len = int(block)
+    assert block == 0 or (N % block == 0 and af is None and gp is None), "block-diagonal attention: N % block_len == 0, generic path"
     if af is not None:
         d.af_grid, d.af_max_rel = af
     if gp is not None:          # (grid, W, skip_id, lut_a, lut_b) from irpe_grid_product_structure
@@ -459,13 +461,14 @@ def _attn_desc(B, H, N, scale, qkv, tk, tv, per_head, idx, bias, af=None, gp=Non
 
 
 def attention_fwd(qkv, B, H, N, scale, *, tk=None, tv=None, per_head=False, idx=(None, None, None, None),
-                  bias=None, need_lse=True, af=None, dense=None, gp=None, causal=False):
+                  bias=None, need_lse=True, af=None, dense=None, gp=None, causal=False, block=0):
     """Fused attention forward.  qkv: (B*N, 3*H*64) bf16.  Returns (out (B*N, H*64) bf16, lse).
-    dense: optional fp32 (B|1, H|1, N, N) term added to the logits (see cream_attn_desc.dense_bias)."""
+    dense: optional fp32 (B|1, H|1, N, N) term added to the logits (see cream_attn_desc.dense_bias).
+    block: > 0 = block-diagonal attention over items of `block` tokens (see cream_attn_desc.block_len)."""
     _check_2d(qkv, torch.bfloat16, "qkv", 8)
     out = empty_bf16(B * N, H * HEAD_DIM, qkv.device)
     lse = torch.empty((B, H, N), dtype=torch.float32, device=qkv.device) if need_lse else None
-    d = _attn_desc(B, H, N, scale, qkv, tk, tv, per_head, idx, bias, af, gp, causal)
+    d = _attn_desc(B, H, N, scale, qkv, tk, tv, per_head, idx, bias, af, gp, causal, block)
     _set_dense(d, dense, B, H, N)
     d.out, d.ld_out, d.lse = _p(out), out.stride(0), _p(lse)
     nb = (NB_PACK if tk is not None else 0) + (NB_PACK if tv is not None else 0)
@@ -476,7 +479,7 @@ def attention_fwd(qkv, B, H, N, scale, *, tk=None, tv=None, per_head=False, idx=
 
 def attention_bwd(qkv, out, lse, dout, B, H, N, scale, *, tk=None, tv=None, per_head=False,
                   idx=(None, None, None, None), bias=None, af=None, dtk=None, dtv=None, dense=None, ddense=None, gp=None,
-                  causal=False):
+                  causal=False, block=0):
     """Returns (dqkv bf16, dtk_pack fp32|None, dtv_pack fp32|None, dbias fp32|None).  dtk / dtv may
     be caller-provided zeroed (T, 64, 64) fp32 accumulators.  With `dense`, pass `ddense` = an fp32
     (B, H, N, N) tensor to receive the logit gradient dS."""
@@ -491,7 +494,7 @@ def attention_bwd(qkv, out, lse, dout, B, H, N, scale, *, tk=None, tv=None, per_
     dbias = torch.zeros((T, NB_PACK), dtype=torch.float32, device=dev) if bias is not None else None
     nbytes = _lib.load().cream_attn_bwd_workspace_bytes(B, H, N)
     ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
-    d = _attn_desc(B, H, N, scale, qkv, tk, tv, per_head, idx, bias, af, gp, causal)
+    d = _attn_desc(B, H, N, scale, qkv, tk, tv, per_head, idx, bias, af, gp, causal, block)
     d.out, d.ld_out, d.lse = _p(out), out.stride(0), _p(lse)
     d.dout, d.ld_dout = _p(dout), dout.stride(0)
     d.dqkv, d.ld_dqkv = _p(dqkv), dqkv.stride(0)

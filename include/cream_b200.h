@@ -198,6 +198,12 @@ typedef struct cream_attn_desc {
    * open_clip/model.py:756-762 computed from the coordinates instead of read from a dense (N, N) term.
    * Generic gather path only (no af / gp hint). */
   int causal;
+  /* > 0: the N tokens are `N / block_len` independent items of block_len tokens laid end to end (block-diagonal
+   * attention: key j is visible to query i only when i / block_len == j / block_len; `causal` then applies inside a
+   * block).  Lets a caller whose sequences are short (TinyCLIP's 50-token image tower, open_clip/model.py:493-536)
+   * hand TWO batch items to one 128-row tile: (B, N) tokens are passed as (B / 2, 2 N) with block_len = N, no copy.
+   * N must be a multiple of block_len.  Generic gather path only. */
+  int block_len;
 } cream_attn_desc;
 
 int cream_attn_fwd(const cream_attn_desc* desc, void* stream);

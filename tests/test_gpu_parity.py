@@ -682,3 +682,23 @@ def test_attention_causal_flag_equals_the_dense_causal_mask(B, N, h):
     d2 = ops.attention_bwd(qkv, o2, l2, dout, B, h, N, 0.125, causal=True)[0]
     assert torch.isfinite(d2.float()).all()
     assert rel_err(d2.float().cpu(), d1.float().cpu()) < 1e-5
+
+
+def test_attention_packed_items_equal_separate_items():
+    """cream_attn_desc.block_len: two 50-token items per sequence (block-diagonal visibility) against the same items
+    as separate batch entries - forward, lse and dqkv; with and without the causal mask (TinyCLIP towers)."""
+    from cream_b200 import ops
+    B, N, h = 6, 50, 3
+    torch.manual_seed(21)
+    qkv = ops.empty_bf16(B * N, 3 * 64 * h); qkv.copy_(torch.randn(B * N, 3 * 64 * h, device="cuda"))
+    dout = ops.empty_bf16(B * N, 64 * h); dout.copy_(torch.randn(B * N, 64 * h, device="cuda"))
+    for causal in (False, True):
+        o1, l1 = ops.attention_fwd(qkv, B, h, N, 0.125, causal=causal)
+        o2, l2 = ops.attention_fwd(qkv, B // 2, h, 2 * N, 0.125, causal=causal, block=N)
+        assert rel_err(o2, o1) < 1e-3, causal        # bf16 outputs; the row sums run over other chunk boundaries
+        # lse is (B, H, N): the packed call returns (B/2, H, 2N) = two items side by side per head
+        l2u = l2.view(B // 2, h, 2, N).permute(0, 2, 1, 3).reshape(B, h, N)
+        assert rel_err(l2u, l1) < 1e-5, causal
+        g1 = ops.attention_bwd(qkv, o1, l1, dout, B, h, N, 0.125, causal=causal)[0]
+        g2 = ops.attention_bwd(qkv, o2, l2, dout, B // 2, h, 2 * N, 0.125, causal=causal, block=N)[0]
+        assert rel_err(g2, g1) < 2e-3, causal
