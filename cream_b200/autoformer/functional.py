@@ -211,7 +211,9 @@ class IrpeAttentionFn(torch.autograd.Function):
         return dense.transpose(2, 3).contiguous(), (k, saved)
 
     @staticmethod
-    def forward(ctx, qkv, heads, scale, ids, mode, rpe_k, rpe_v, rpe_k2=None, rpe_v2=None, rpe_q=None, rpe_q2=None):
+    def forward(ctx, qkv, heads, scale, ids, mode, rpe_k, rpe_v, rpe_k2=None, rpe_v2=None, rpe_q=None, rpe_q2=None, block=0):
+        """block > 0: the N tokens of a sequence are N / block independent items (cream_attn_desc.block_len); `ids` is
+        then the (N, N) table of the packed sequence (the caller tiles the per-item table)."""
         B, N, W3 = qkv.shape
         assert W3 == 3 * ops.HEAD_DIM * heads
         dev = qkv.device
@@ -272,21 +274,24 @@ class IrpeAttentionFn(torch.autograd.Function):
             st = ops.irpe_grid_product_structure(ids, side, N - side * side) if side * side + 1 == N else None
             if st is not None:
                 gp = (side,) + st
+        if block:
+            gp = None
         out, lse = ops.attention_fwd(qkv2, B, heads, N, scale, tk=tk, tv=tv, per_head=per_head, idx=idx, bias=bias,
-                                     dense=dense, gp=gp)
+                                     dense=dense, gp=gp, block=block)
         ctx.save_for_backward(qkv2, out, lse, tk, tv, bias, rpe_k, rpe_v, rpe_k2, rpe_v2, rpe_q, rpe_q2, dense)
-        ctx.meta = (B, heads, N, scale, idx, per_head, mode, qkv.dtype, cross, ids, qsave, gp)
+        ctx.meta = (B, heads, N, scale, idx, per_head, mode, qkv.dtype, cross, ids, qsave, gp, block)
         return out.reshape(B, N, ops.HEAD_DIM * heads)
 
     @staticmethod
     def backward(ctx, dout):
         qkv2, out, lse, tk, tv, bias, rpe_k, rpe_v, rpe_k2, rpe_v2, rpe_q, rpe_q2, dense = ctx.saved_tensors
-        B, heads, N, scale, idx, per_head, mode, dtype, cross, ids, qsave, gp = ctx.meta
+        B, heads, N, scale, idx, per_head, mode, dtype, cross, ids, qsave, gp, block = ctx.meta
         half = ops.NB_PACK // 2
         d2 = ops.as_bf16_2d(dout)
         ddense = torch.empty((B, heads, N, N), dtype=torch.float32, device=qkv2.device) if dense is not None else None
         dqkv, dtk, dtv, dbias = ops.attention_bwd(qkv2, out, lse, d2, B, heads, N, scale, tk=tk, tv=tv,
-                                                  per_head=per_head, idx=idx, bias=bias, dense=dense, ddense=ddense, gp=gp)
+                                                  per_head=per_head, idx=idx, bias=bias, dense=dense, ddense=ddense, gp=gp,
+                                                  block=block)
         gk = gv = gk2 = gv2 = gq = gq2 = None
         if rpe_q is not None:
             tabs = [rpe_q, rpe_q2] if cross else [rpe_q]
@@ -335,7 +340,7 @@ class IrpeAttentionFn(torch.autograd.Function):
                                        gv2, gv2.shape[1], half, (gv2.stride(0), gv2.stride(1), gv2.stride(2)))
             else:
                 ops.unpack_table_grads(dtv, T, gv, gv.shape[1], 0, (gv.stride(0), gv.stride(1), gv.stride(2)))
-        return dqkv.reshape(B, N, -1).to(dtype), None, None, None, None, gk, gv, gk2, gv2, gq, gq2
+        return dqkv.reshape(B, N, -1).to(dtype), None, None, None, None, gk, gv, gk2, gv2, gq, gq2, None
 
 
 class DenseAttentionFn(torch.autograd.Function):

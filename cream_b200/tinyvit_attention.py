@@ -3,12 +3,18 @@
 `Attention` mirrors TinyViT/models/tiny_vit.py:215-286 (constructor signature, parameter names
 `norm`, `qkv`, `proj`, `attention_biases`, buffer `attention_bias_idxs`, the `(B, N, C)` interface
 where B already counts windows).  LayerNorm, the qkv / proj linears and the attention core are the
-library's kernels; the per-head scalar bias `attention_biases[:, idxs]` enters the core through the
-kernel's dense additive logit term and receives its gradient from it.
+library's kernels.  The per-head scalar bias `attention_biases[:, idxs]` (tiny_vit.py:254-283):
+
+  * 7 x 7 windows (49 distinct offsets <= 64 buckets): gathered INSIDE the kernel - the bias row of the head sits in
+    shared memory and is indexed by the uint8 offset table, its gradient comes back as 64 bucket sums per head
+    (`cream_attn_desc.bias_pack` / `dbias_pack`, the iRPE bias mode); no (H, N, N) tensor exists.  Two windows share
+    one 128-row query tile: `(B, 49)` tokens are passed as `(B / 2, 98)` with block-diagonal visibility
+    (`cream_attn_desc.block_len = 49`), no copy;
+  * 14 x 14 (196 offsets > 64 buckets): through the kernel's dense additive logit term, which also returns its gradient.
 
 TinyViT uses head_dim 32 (key_dim 32, attn_ratio 1); the fused kernel is built for 64, so q, k, v
 are zero-padded to 64 channels per head (q·k and P·v are unchanged by zero channels).  A native
-32-wide variant with several 7x7 windows per CTA is the next step.
+32-wide kernel is the open item.
 """
 from __future__ import annotations
 
@@ -19,7 +25,9 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from . import ops
-from .autoformer.functional import DenseAttentionFn, SlicedLayerNormFn, SlicedLinearFn
+import numpy as np
+
+from .autoformer.functional import DenseAttentionFn, IrpeAttentionFn, SlicedLayerNormFn, SlicedLinearFn
 
 
 class Attention(nn.Module):
@@ -48,6 +56,10 @@ class Attention(nn.Module):
         n = len(points)
         self.attention_biases = nn.Parameter(torch.zeros(num_heads, len(offsets)))
         self.register_buffer("attention_bias_idxs", torch.LongTensor(idxs).view(n, n), persistent=False)
+        # host copies of the offset table for the in-kernel gather: one window, and two windows laid end to end
+        ids = np.asarray(idxs, dtype=np.int64).reshape(n, n)
+        self._ids1 = ids if len(offsets) <= ops.NB_PACK else None
+        self._ids2 = np.tile(ids, (2, 2)) if (self._ids1 is not None and 2 * n <= 128) else None
 
     def forward(self, x):  # x (B, N, C)
         B, N, C = x.shape
@@ -57,7 +69,14 @@ class Attention(nn.Module):
         q, k, v = qkv.view(B, N, H, -1).split([kd, kd, d], dim=3)
         # reference column order per head is [q | k | v]; the kernel wants (B, N, 3, H, 64)
         packed = torch.stack([F.pad(q, (0, D - kd)), F.pad(k, (0, D - kd)), F.pad(v, (0, D - d))], dim=2)
-        dense = self.attention_biases[:, self.attention_bias_idxs].float().unsqueeze(0)      # (1, H, N, N)
-        out = DenseAttentionFn.apply(packed.reshape(B, N, 3 * H * D), H, float(self.scale), dense.contiguous())
+        packed = packed.reshape(B, N, 3 * H * D)
+        if self._ids2 is not None and B % 2 == 0:       # fused bias gather, two windows per query tile
+            out = IrpeAttentionFn.apply(packed.view(B // 2, 2 * N, 3 * H * D), H, float(self.scale), self._ids2, "bias",
+                                        self.attention_biases, None, None, None, None, None, N).reshape(B, N, H * D)
+        elif self._ids1 is not None:                    # fused bias gather
+            out = IrpeAttentionFn.apply(packed, H, float(self.scale), self._ids1, "bias", self.attention_biases, None)
+        else:                                           # more than 64 distinct offsets: dense logit term
+            dense = self.attention_biases[:, self.attention_bias_idxs].float().unsqueeze(0)      # (1, H, N, N)
+            out = DenseAttentionFn.apply(packed, H, float(self.scale), dense.contiguous())
         out = out.view(B, N, H, D)[..., :d].reshape(B, N, self.dh)
         return SlicedLinearFn.apply(out, self.proj.weight, self.proj.bias, self.dh, self.proj.out_features, False)

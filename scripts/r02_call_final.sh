@@ -21,3 +21,8 @@ timeout 600 ncu --set full --clock-control none --import-source on -k regex:gemm
 python scripts/r02_make_profiles.py gpurun_out/r02_profiles > gpurun_out/r02_make_profiles.log 2>&1; echo "[summaries exit $?]"
 rm -f gpurun_out/prof_r02_gemm.ncu-rep gpurun_out/prof_r02_attention.ncu-rep
 ls gpurun_out/r02_profiles
+# timing ablations of the rows kernel's column loop (debug builds; results wrong by construction): 1 = no workspace stores,
+# 9 = + no MUFU, 25 = + no packed-dT TMEM store, 29 = + no bucket accumulations
+for a in abl1 abl9 abl25 abl29; do
+  echo "== $a"; CREAM_B200_LIB=build_trace/libcream_b200_$a.so CREAM_ATTN_TRACE=1 CREAM_ONLY_STRUCTURED=1 timeout 200 python scripts/time_attention.py 2>&1 | grep -E "structured|mid-grid" -A4 | grep -E "structured|row thread half 0" | tail -2
+done
