@@ -11,6 +11,8 @@ import threading
 from typing import Optional
 
 import numpy as np
+import weakref
+
 import torch
 
 from . import _lib
@@ -98,30 +100,49 @@ class ShadowCache:
     (`p.data.add_()`, some third-party optimizers, manual EMA / weight surgery) do NOT bump the version
     counter: after such an update call `SHADOWS.invalidate()` (or `invalidate(p)`), e.g. from an
     optimizer post-step hook; `load_state_dict` and torch's own optimizers bump the version and need
-    nothing.  Entries hold the bf16 copy of a live parameter; `clear()` releases them all."""
+    nothing.
+
+    An entry keeps its parameter's STORAGE alive.  Without that, a model that is freed and another one
+    created afterwards can put a same-shaped parameter with the same version counter at the same address
+    (the caching allocator recycles blocks, and so does the allocator of the storage objects), and the new
+    model would silently run on the old model's bf16 weights (seen once a process had built enough models:
+    tests/test_gpu_clip.py after the parity and native suites).  Entries whose parameter object has been
+    collected are dropped - releasing storage and shadow - every 1024 lookups and by `clear()`."""
 
     def __init__(self):
-        self._store = {}
+        self._store = {}      # (data_ptr, qkv) -> (shadow, tag | None, storage, weakref to the parameter | None)
+        self._gets = 0
 
     def invalidate(self, w: Optional[torch.Tensor] = None) -> None:
         """Force a re-cast on next use: of every shadow, or only of parameter `w`."""
         if w is None:
-            self._store = {k: (sh, None) for k, (sh, _) in self._store.items()}
+            self._store = {k: (e[0], None) + tuple(e[2:]) for k, e in self._store.items()}
         else:
             for k in [(w.data_ptr(), False), (w.data_ptr(), True)]:
                 if k in self._store:
-                    self._store[k] = (self._store[k][0], None)
+                    e = self._store[k]
+                    self._store[k] = (e[0], None) + tuple(e[2:])
+
+    def _purge(self) -> None:
+        dead = [k for k, e in self._store.items() if e[3] is not None and e[3]() is None]
+        for k in dead:
+            del self._store[k]
 
     def get(self, w: torch.Tensor, qkv: bool = False) -> torch.Tensor:
+        self._gets += 1
+        if (self._gets & 1023) == 0:
+            self._purge()
         key = (w.data_ptr(), qkv)
         ent = self._store.get(key)
-        tag = (w._version, w.untyped_storage()._cdata, tuple(w.shape))
+        storage = w.untyped_storage()
+        tag = (w._version, storage._cdata, tuple(w.shape))
         if ent is not None and ent[1] == tag:
             return ent[0]
         w2 = w.detach().reshape(w.shape[0], -1)
         assert w2.dtype == torch.float32 and w2.is_contiguous()
         rows, cols = w2.shape
-        sh = ent[0] if (ent is not None and ent[0].shape[0] == rows and ent[0].device == w.device) else \
+        sh = ent[0] if (ent is not None and ent[0].shape[0] == rows and ent[0].shape[1] == round_up(cols, 8)
+                        and ent[0].device == w.device) else \
             torch.empty((rows, round_up(cols, 8)), dtype=torch.bfloat16, device=w.device)
         lib = _lib.load()
         if qkv:
@@ -131,7 +152,14 @@ class ShadowCache:
         else:
             check(lib.cream_shadow_cast(_p(w2), _p(sh), rows, cols, w2.stride(0), sh.stride(0), _stream()),
                   "cream_shadow_cast")
-        self._store[key] = (sh, tag)
+        if ent is not None and ent[2]._cdata == storage._cdata and ent[3] is not None and ent[3]() is not None:
+            wref = ent[3]                       # same parameter, new version: keep watching the original object
+        else:
+            try:
+                wref = weakref.ref(w)
+            except TypeError:
+                wref = None
+        self._store[key] = (sh, tag, storage, wref)
         return sh
 
     def clear(self):

@@ -15,3 +15,13 @@ def pytest_configure(config):
 @pytest.fixture(scope="session")
 def golden_dir():
     return ROOT / "tests" / "golden"
+
+
+@pytest.fixture(autouse=True)
+def _fresh_shadows(request):
+    """Diagnostic switch (CREAM_TEST_CLEAR_SHADOWS=1): drop every cached bf16 weight shadow before each GPU test."""
+    import os
+    if os.environ.get("CREAM_TEST_CLEAR_SHADOWS") == "1" and request.node.get_closest_marker("gpu") is not None:
+        from cream_b200 import ops
+        ops.SHADOWS.clear()
+    yield
