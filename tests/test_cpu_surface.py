@@ -258,3 +258,25 @@ def test_non_square_bucket_ids_match_the_detr_copy_of_irpe():
             assert lib.cream_irpe_bucket_ids_host(my_id, h, w, skip, 1.9, 3.8, 15.2, out.ctypes.data, ctypes.byref(nbc)) == 0
             assert nbc.value == nb
             np.testing.assert_array_equal(out, mine)
+
+
+def test_short_sequence_packing_host_logic(golden_dir):
+    """Host side of cream_attn_desc.block_len: which (batch, tokens, block) the TinyCLIP towers hand to the attention kernel
+    (clip._attn_packing) and the offset tables TinyViT's windows use for the in-kernel bias gather (one window / two windows laid
+    end to end; more than 64 distinct offsets fall back to the dense logit term)."""
+    from cream_b200 import clip, ops
+    from cream_b200.tinyvit_attention import Attention
+    assert clip._attn_packing(128, 50, False) == (64, 100, 50)        # image tower: two items per 128-row tile
+    assert clip._attn_packing(127, 50, False) == (127, 50, 0)         # odd batch: one item per tile
+    assert clip._attn_packing(128, 77, True) == (128, 77, 0)          # text tower: 154 tokens do not fit a tile
+    assert clip._attn_packing(4, 64, True) == (2, 128, 64)
+    win = Attention(64, 32, 2, attn_ratio=1, resolution=(7, 7))
+    ids = win.attention_bias_idxs.numpy()
+    assert win._ids1 is not None and int(win._ids1.max()) + 1 == 49 <= ops.NB_PACK
+    np.testing.assert_array_equal(win._ids1, ids)
+    assert win._ids2.shape == (98, 98)
+    for a in range(2):
+        for b in range(2):
+            np.testing.assert_array_equal(win._ids2[49 * a:49 * (a + 1), 49 * b:49 * (b + 1)], ids)
+    full = Attention(128, 32, 4, attn_ratio=1, resolution=(14, 14))
+    assert full._ids1 is None and full._ids2 is None                   # 196 offsets: dense logit term
