@@ -595,6 +595,8 @@ class ClipTrainer:
         staged = images if texts is None else None
         if staged is not None:
             images, texts = staged.acquire()
+        if self.use_graph and self._graph is not None and (images.shape != self._g_images.shape or texts.shape != self._g_texts.shape):
+            self._graph = None          # another batch shape: the recorded launches no longer apply - capture again
         if self.use_graph and (self._graph is not None or self._capture(images, texts)):
             self._g_images.copy_(images, non_blocking=True)
             self._g_texts.copy_(texts, non_blocking=True)
