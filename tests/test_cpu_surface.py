@@ -280,3 +280,44 @@ def test_short_sequence_packing_host_logic(golden_dir):
             np.testing.assert_array_equal(win._ids2[49 * a:49 * (a + 1), 49 * b:49 * (b + 1)], ids)
     full = Attention(128, 32, 4, attn_ratio=1, resolution=(14, 14))
     assert full._ids1 is None and full._ids2 is None                   # 196 offsets: dense logit term
+
+
+def test_shadow_cache_bookkeeping(monkeypatch):
+    """ShadowCache host logic with the cast kernels stubbed out (no GPU): one cast per parameter version, a hit for another
+    wrapper of the same parameter (what autograd hands to backward), re-cast after invalidate(), the entry pins the parameter's
+    storage while the parameter lives, and the purge drops it once the parameter object is gone."""
+    import gc
+    from cream_b200 import _lib, ops
+    calls = []
+
+    class _Stub:
+        def cream_shadow_cast(self, *a):
+            calls.append("cast")
+            return 0
+
+        def cream_shadow_qkv(self, *a):
+            calls.append("qkv")
+            return 0
+
+    monkeypatch.setattr(_lib, "load", lambda: _Stub())
+    monkeypatch.setattr(ops, "_stream", lambda: 0)
+    cache = ops.ShadowCache()
+    w = torch.nn.Parameter(torch.randn(12, 20))
+    s1 = cache.get(w)
+    assert calls == ["cast"] and tuple(s1.shape) == (12, 24) and s1.dtype == torch.bfloat16
+    assert cache.get(w) is s1 and cache.get(w.detach().requires_grad_()) is s1 and calls == ["cast"]   # same storage, same version
+    with torch.no_grad():
+        w.add_(1.0)                                           # version bump: re-cast into the SAME buffer
+    assert cache.get(w) is s1 and calls == ["cast", "cast"]
+    cache.invalidate(w)
+    assert cache.get(w) is s1 and len(calls) == 3
+    sq = cache.get(w, qkv=True)
+    assert calls[-1] == "qkv" and sq is not s1
+    (key, ent), = [(k, e) for k, e in cache._store.items() if not k[1]]
+    assert ent[2]._cdata == w.untyped_storage()._cdata and ent[3]() is w
+    cache._purge()
+    assert len(cache._store) == 2                              # parameter alive: nothing dropped
+    del w, ent
+    gc.collect()
+    cache._purge()
+    assert len(cache._store) == 0                              # parameter gone: storage and shadow released
